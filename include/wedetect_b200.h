@@ -1,0 +1,178 @@
+/* wedetect_b200.h — C ABI of libwedetect_b200.so (sm_100a).
+ *
+ * The reference (WeChatCV/WeDetect) has no FFI: its boundary is Python.  This ABI
+ * is what sits directly underneath our Python mirror of that boundary.  Each entry point cites the
+ * reference function(s) whose arithmetic it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C types only; all pointers in `wd_op.p[]` are DEVICE pointers owned by the caller;
+ *   - every call enqueues work on the caller's `cudaStream_t` (passed as void*), never syncs;
+ *   - return 0 on success, negative on failure; `wd_last_error()` returns a thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Execution model: the host (Python) lowers a model into a flat array of `wd_op` records (one per
+ * kernel-level operation), `wd_program_create` validates them and pre-builds TMA descriptors,
+ * `wd_program_run` replays the whole list on a stream (optionally as a captured CUDA graph).
+ */
+#ifndef WEDETECT_B200_H
+#define WEDETECT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WD_OP_NI 40
+#define WD_OP_NF 8
+#define WD_OP_NP 16
+
+typedef struct wd_op {
+    int32_t kind;          /* enum wd_op_kind */
+    int32_t i[WD_OP_NI];   /* integer fields, meaning depends on kind (see below) */
+    float f[WD_OP_NF];     /* float fields */
+    void* p[WD_OP_NP];     /* device pointers */
+} wd_op;
+
+typedef struct wd_program wd_program;
+
+enum wd_op_kind {
+    /* Tensor-core GEMM / implicit-GEMM convolution with fused epilogue (tcgen05 + TMEM + TMA).
+     * Replaces nn.Linear / 1x1 / 3x3 s1 / 2x2-s2-transposed convolutions, BatchNorm (folded),
+     * ReLU/SiLU/GELU, LayerScale+residual and DFL of:
+     *   wedetect/models/backbones/mm_backbone.py:112-125 (Block.forward pwconv1/act/pwconv2/gamma)
+     *   wedetect/models/necks/yolo_world_pafpn.py:40-68,195-208,587-605,631-647,692-715
+     *   wedetect/models/dense_heads/yolo_world_head.py:90-108,263-294
+     *   transformers XLMRobertaModel Linear layers (mm_backbone.py:382-386)
+     * i: 0..2 D0,D1,D2 (row space, row m = (d2*D1+d1)*D0+d0)   3..5 E0,E1,E2 (tile extents, E0*E1*E2<=128)
+     *    6 Kc (K per tap, %64==0)  7 ntaps (1|9)  8 N  9..11 A strides of d0,d1,d2 (elements)
+     *    12 ldb  13 block_n (64|128|256)  14 out_dtype (0 bf16, 1 f32)  15 act (wd_act)
+     *    16 resid_dtype (0 none, 1 bf16, 2 f32)  17 ld_res  18 group_cols  19 n_groups
+     *    20..22 C strides of d0,d1,d2 (elements)  23 C stride of group  24 epi_mode (0 store, 1 DFL)
+     *    25 tap_w (3 for 3x3)  26 pad (1 for 3x3)
+     * f: 0 resid_alpha
+     * p: 0 A (bf16)  1 B (bf16 [N, ntaps*Kc])  2 C  3 bias f32[N]  4 gamma f32[N]  5 resid
+     *    6 A_lo  7 B_lo  8 C_lo   (bf16x3 "split" precise mode; null in fast mode)
+     * out = resid*alpha + gamma * act(acc + bias)        (each term optional) */
+    WD_OP_GEMM = 1,
+    /* Row LayerNorm over C (biased variance, eps inside sqrt): mm_backbone.py:145-155, F.layer_norm.
+     * i: 0 rows 1 C 2 in_dtype(1 bf16? no: 2 f32) 3 out_dtype (0 bf16, 1 f32)
+     *    4 s2d (0 | 1: write 2x2 space-to-depth layout for the stride-2 patchify conv, :193-198)
+     *    5 W 6 H (only for s2d) 7 ld_in 8 ld_out 9 has_resid (out = LN(in + resid)) 10 ld_res
+     * f: 0 eps   p: 0 in f32  1 out  2 weight f32[C]  3 bias f32[C]  4 resid f32  5 out_lo  6 out2 f32 */
+    WD_OP_LN_ROWS = 2,
+    /* Depthwise 7x7 (pad 3) + bias + LayerNorm(C) on an NHWC fp32 tensor -> bf16 rows.
+     * mm_backbone.py:114-116 (Block.forward dwconv/permute/norm).
+     * i: 0 B 1 H 2 W 3 C   f: 0 eps
+     * p: 0 in f32 [B,H,W,C]  1 out bf16 [B*H*W,C]  2 w f32[49,C]  3 b f32[C]  4 ln_w  5 ln_b  6 out_lo */
+    WD_OP_DWCONV_LN = 3,
+    /* Stem patchify: image -> bf16 rows [B*(H/4)*(W/4), 64] (48 valid = (dy,dx,c), rest 0).
+     * mm_backbone.py:188-191 (Conv2d k4 s4 input gather); data_preprocessor.py:35-36 (mean/std are
+     * folded into the stem weights by the host).
+     * i: 0 B 1 H 2 W 3 in_dtype (0 u8, 2 f32) 4 layout (0 NCHW, 1 NHWC)   f: 0 scale
+     * p: 0 in  1 out bf16  2 out_lo */
+    WD_OP_STEM_PATCH = 4,
+    /* im2col for 3x3 stride-2 pad-1 conv on NHWC bf16: rows [B*Ho*Wo, 9*C] (tap-major).
+     * yolo_world_pafpn.py:704-709,1062-1082 (downsample ConvBNReLU k3 s2).
+     * i: 0 B 1 H 2 W 3 C 4 ld_in   p: 0 in bf16  1 out bf16  2 in_lo  3 out_lo */
+    WD_OP_IM2COL_S2 = 5,
+    /* f32 -> bf16 row cast (backbone outputs c1..c4 to neck operands). i: 0 rows 1 C 2 ld_in 3 ld_out
+     * p: 0 in f32  1 out bf16  2 out_lo */
+    WD_OP_CAST_BF16 = 6,
+    /* XLM-R embeddings: word + position + token_type, LayerNorm (transformers
+     * modeling_xlm_roberta.py embeddings; position ids = cumsum(mask)*mask + pad_idx).
+     * i: 0 S (sequences) 1 L (tokens/seq) 2 Hd 3 pad_idx   f: 0 eps
+     * p: 0 ids i32[S,L] 1 mask i32[S,L] 2 word f32[V,Hd] 3 pos f32[P,Hd] 4 type f32[Hd] 5 ln_w 6 ln_b
+     *    7 out f32 [S*L,Hd]  8 out bf16  9 out_lo */
+    WD_OP_TEXT_EMBED = 7,
+    /* Short-sequence multi-head self-attention (L <= 32), one warp per (sequence, head).
+     * i: 0 S 1 L 2 heads 3 head_dim 4 ld_qkv (= 3*Hd)   f: 0 scale
+     * p: 0 qkv f32 [S*L, 3*Hd]  1 mask i32[S,L]  2 out bf16 [S*L,Hd]  3 out_lo */
+    WD_OP_ATTN_SMALL = 8,
+    /* CLS pooling + L2 normalise: out[s,:] = x[s,:] / max(||x[s,:]||, 1e-12)  (F.normalize,
+     * mm_backbone.py:387).  i: 0 S 1 C 2 ld_in   p: 0 in f32  1 out f32 */
+    WD_OP_L2NORM_ROWS = 9,
+    /* gather rows: out[s,:] = in[idx0 + s*stride,:] as bf16 (CLS token rows, mm_backbone.py:385).
+     * i: 0 S 1 C 2 row_stride 3 ld_in  p: 0 in f32  1 out bf16  2 out_lo */
+    WD_OP_GATHER_ROWS = 10,
+    /* Fold BNContrastiveHead into a GEMM weight: W'[k,c] = t[k,c]/max(||t[k]||,eps) * g[c] * exp(s),
+     * b'[k] = exp(s) * sum_c h[c]*tn[k,c] + bias (yolo_world_head.py:90-108; Uni variant without
+     * text normalisation: generate_proposal.py:1129-1131).
+     * i: 0 K 1 C 2 normalize (0|1) 3 K_pad
+     * p: 0 text f32[K,C] 1 bn_g f32[C] 2 bn_h f32[C] 3 logit_scale f32[1] 4 bias f32[1]
+     *    5 W' bf16 [K_pad,C]  6 b' f32[K_pad]  7 W'_lo */
+    WD_OP_FOLD_TEXT = 11,
+    /* Detection post-process for a batch: sigmoid, score threshold, top-k (nms_pre), box decode,
+     * rescale, class-aware greedy NMS, keep max_per_img.  Bit-exact integer/index semantics.
+     *   yolo_world_head.py:619-749 (predict_by_feat), generate_proposal.py:85-131,1000-1048,1150-1218,
+     *   mmdet filter_scores_and_topk / batched_nms.
+     * see wd_pp_params below (passed through p[0] as a HOST pointer copied at create time). */
+    WD_OP_POSTPROCESS = 12,
+    /* Gather kept proposals' embedding rows: out[b, j, :] = BN(embed[b, anchor(b,j), :]) f32.
+     * generate_proposal.py:1129,1209-1212.  i: 0 B 1 A 2 C 3 max_keep  4 nlevels 5..7 level sizes
+     * p: 0..2 embed bf16 per level [B*HW_l, C]  3 keep_anchor i32[B,max]  4 counts i32[B]
+     *    5 bn_g f32[3*C] 6 bn_h f32[3*C] 7 out f32 [B,max,C]  8..10 embed_lo per level */
+    WD_OP_GATHER_EMBED = 13,
+};
+
+enum wd_act { WD_ACT_NONE = 0, WD_ACT_RELU = 1, WD_ACT_SILU = 2, WD_ACT_GELU = 3 };
+
+/* Parameters of WD_OP_POSTPROCESS (host struct; device pointers inside). */
+typedef struct wd_pp_params {
+    int32_t B;              /* images */
+    int32_t K;              /* classes / prompts */
+    int32_t nlevels;        /* <= 4 */
+    int32_t lvl_h[4], lvl_w[4], lvl_stride[4];
+    int32_t ld_logit[4];    /* row stride (elements) of each level's logit matrix */
+    const float* logits[4]; /* f32 [B*H_l*W_l, ld_logit] pre-sigmoid */
+    const float* dist[4];   /* f32 [B*H_l*W_l, 4] ltrb in stride units (DFL output) */
+    float score_thr;        /* keep score > thr (strict), mmdet filter_scores_and_topk */
+    int32_t nms_pre;        /* top-k before NMS */
+    float iou_thr;          /* suppress iff IoU > thr (strict) */
+    int32_t max_per_img;
+    int32_t nms_mode;       /* 0: mmcv batched_nms (coordinate offsets, always)
+                               1: torchvision batched_nms (offsets iff 4*n <= 20000, else per class) */
+    int32_t tv_numel_thr;   /* nms_mode 1 only: torchvision's switch (20000 on CUDA devices, 4000 on CPU) */
+    int32_t multi_label;    /* 1: every (anchor,class) pair is a candidate; 0: argmax class per anchor */
+    const float* img_meta;  /* f32 [B, 8]: pre_sub_x, pre_sub_y, pre_div_x, pre_div_y (applied before
+                               NMS: mmdet rescale), post_sub_x, post_sub_y, post_div (after NMS: Uni
+                               un-letterbox), unused */
+    const float* clamp_wh;  /* f32 [B,2] (ori_w, ori_h); clamp applied last */
+    /* outputs (caller allocated) */
+    float* out_boxes;       /* [B, max_per_img, 4] */
+    float* out_scores;      /* [B, max_per_img] */
+    int32_t* out_labels;    /* [B, max_per_img] */
+    int32_t* out_anchor;    /* [B, max_per_img] flat anchor index (level-concatenated) */
+    int32_t* out_counts;    /* [B] */
+    /* workspace */
+    void* workspace;
+    uint64_t workspace_bytes;
+} wd_pp_params;
+
+/* ---- library-level ---------------------------------------------------------------------- */
+const char* wd_last_error(void);
+int wd_version(void);
+/* number of CUDA kernels launched by this library in this process (bench `gpu_launches`). */
+uint64_t wd_launch_count(void);
+/* device query: returns 0 and fills sm count / cc; fails loudly (negative) without a GPU. */
+int wd_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- single op (used by parity tests; builds descriptors, launches, frees) --------------- */
+int wd_op_run(const wd_op* op, void* stream);
+
+/* ---- programs ---------------------------------------------------------------------------- */
+int wd_program_create(const wd_op* ops, int n_ops, wd_program** out);
+int wd_program_run(wd_program* prog, void* stream);
+/* capture once into a CUDA graph and replay (falls back to an error, never to eager silently). */
+int wd_program_capture(wd_program* prog, void* stream);
+int wd_program_replay(wd_program* prog, void* stream);
+int wd_program_num_launches(const wd_program* prog);
+void wd_program_destroy(wd_program* prog);
+
+/* workspace size needed by WD_OP_POSTPROCESS for (B, anchors, K). */
+uint64_t wd_pp_workspace_bytes(int B, int anchors, int K, int nms_pre);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEDETECT_B200_H */

@@ -1,0 +1,501 @@
+// gemm_tc.cu — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   C[m, n] = epilogue( sum_{tap, k} A[pix(m) + off(tap), k] * B[n, tap*Kc + k] )
+//
+// * A rows live in a (d0, d1, d2) pixel space (NHWC activations: d0 = x, d1 = y, d2 = image; a plain
+//   row-major matrix is D0 = M, D1 = D2 = 1).  A tile is an (E0, E1, E2) brick of <= 128 pixels, so a
+//   3x3 convolution is 9 shifted TMA brick loads (out-of-bounds pixels are zero-filled by TMA = conv
+//   padding) — no im2col buffer.
+// * operands are bf16, K-major, 128-byte swizzled in shared memory (written by TMA, read by UMMA);
+//   accumulation is fp32 in TMEM, double-buffered (2 x BLOCK_N columns) so the epilogue of tile i
+//   overlaps the MMAs of tile i+1.
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (single elected lane), warp 2 = TMEM
+//   allocator, warps 4..11 = two epilogue warpgroups that split the accumulator in column chunks,
+//   apply bias / activation / LayerScale / residual (or DFL), stage the tile in swizzled smem and
+//   write it back with TMA stores (which clip partial tiles and scatter into concat / upsample
+//   layouts through a rank-5 tensor map).
+// * kSplit = bf16x3 "precise" mode: every fp32 operand is carried as hi + lo bf16 planes and each
+//   k-step issues A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, giving ~2^-16 relative operand error.
+//
+// Reference arithmetic replaced: see include/wedetect_b200.h (WD_OP_GEMM).
+#include "internal.h"
+#include <stdio.h>
+#include <string.h>
+
+namespace wd {
+
+constexpr int kNumEpiWG = 2;
+constexpr int kNumThreads = 128 + 128 * kNumEpiWG;
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle atom
+
+struct GemmParams {
+    CUtensorMap tmA, tmB, tmC, tmA_lo, tmB_lo, tmC_lo;
+    int D0, D1, D2, E0, E1, E2, nt0, nt1, nt2;
+    int kc_iters, ntaps, tap_w, pad;
+    int N, num_m_tiles, num_n_tiles, num_tiles;
+    int act, resid_dtype, ld_res, group_cols, epi_mode, rows_a;
+    float alpha;
+    const float* bias;
+    const float* gamma;
+    const void* resid;
+    const void* resid_lo;
+    float* dfl_out;
+};
+
+template <int BN, bool kSplit>
+struct Cfg {
+    static constexpr int A_BYTES = kTileM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = (kSplit ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int kStages = kSplit ? (BN >= 128 ? 2 : 3) : (BN == 256 ? 4 : (BN == 128 ? 5 : 6));
+    static constexpr int EPI_BUFS = (!kSplit && BN <= 128) ? 2 : 1;
+    static constexpr int EPI_BUF_BYTES = 16384 * (kSplit ? 2 : 1);
+    static constexpr int EPI_BYTES = kNumEpiWG * EPI_BUFS * EPI_BUF_BYTES;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols");
+};
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+    if (act == WD_ACT_RELU) return fmaxf(x, 0.f);
+    if (act == WD_ACT_SILU) return __fdividef(x, 1.f + __expf(-x));
+    if (act == WD_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    return x;
+}
+
+template <int BN, typename OutT, bool kSplit>
+__global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+    using C = Cfg<BN, kSplit>;
+    constexpr int CH = 128 / (int)sizeof(OutT);  // columns per epilogue chunk (one 128 B swizzle row)
+    constexpr bool kOutBf16 = sizeof(OutT) == 2;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_epi = smem + C::kStages * C::STAGE_BYTES;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
+    uint64_t* bar_empty = bar_full + C::kStages;
+    uint64_t* bar_tfull = bar_empty + C::kStages;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        tma_prefetch_desc(&p.tmC);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tfull[a], 1);
+            mbar_init(&bar_tempty[a], 4 * kNumEpiWG);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int k_iters = p.kc_iters * p.ntaps;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (kSplit ? 2u : 1u) * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+                const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
+                const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
+                for (int kit = 0; kit < k_iters; ++kit) {
+                    const int tap = kit / p.kc_iters, kc = kit - tap * p.kc_iters;
+                    const int dx = tap % p.tap_w - p.pad, dy = tap / p.tap_w - p.pad;
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * C::STAGE_BYTES;
+                    uint8_t* sB = sA + C::A_BYTES;
+                    mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
+                    tma_load_4d(&p.tmA, &bar_full[stage], sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
+                    tma_load_2d(&p.tmB, &bar_full[stage], sB, kit * kBlockK, n_blk * BN);
+                    if (kSplit) {
+                        uint8_t* sA2 = sB + C::B_BYTES;
+                        uint8_t* sB2 = sA2 + C::A_BYTES;
+                        tma_load_4d(&p.tmA_lo, &bar_full[stage], sA2, kc * kBlockK, o0 + dx, o1 + dy, o2);
+                        tma_load_2d(&p.tmB_lo, &bar_full[stage], sB2, kit * kBlockK, n_blk * BN);
+                    }
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&bar_tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kit = 0; kit < k_iters; ++kit) {
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t sB = sA + C::A_BYTES;
+                    const uint64_t adesc = umma_desc_sw128(sA);
+                    const uint64_t bdesc = umma_desc_sw128(sB);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+                        umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
+                        if (kSplit) {
+                            const uint64_t adesc2 = umma_desc_sw128(sB + C::B_BYTES);
+                            const uint64_t bdesc2 = umma_desc_sw128(sB + C::B_BYTES + C::A_BYTES);
+                            umma_bf16(tmem_d, adesc2 + 2 * k, bdesc + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, adesc + 2 * k, bdesc2 + 2 * k, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&bar_empty[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&bar_tfull[as]);  // accumulator complete -> epilogue
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue warpgroups =================
+        const int wg = (warp - 4) >> 2;
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int tid_wg = threadIdx.x - 128 - wg * 128;
+        const bool issuer = (tid_wg == 0);
+        const int r = quarter * 32 + lane;
+        uint8_t* wg_bufs = smem_epi + wg * C::EPI_BUFS * C::EPI_BUF_BYTES;
+        int as = 0;
+        uint32_t aphase = 0;
+        int buf = 0;
+        constexpr int n_chunks = BN / CH;
+
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+            const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
+            const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
+            const int i0 = r % p.E0, i1 = (r / p.E0) % p.E1, i2 = r / (p.E0 * p.E1);
+            const int d0 = o0 + i0, d1 = o1 + i1, d2 = o2 + i2;
+            const bool row_ok = (i2 < p.E2) && d0 < p.D0 && d1 < p.D1 && d2 < p.D2;
+            const long long pix = ((long long)d2 * p.D1 + d1) * p.D0 + d0;
+
+            mbar_wait(&bar_tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+
+            if (p.epi_mode == 1) {
+                // ---- DFL epilogue (BN == 64): softmax over 16 bins x 4 sides, expectation ----
+                if constexpr (BN == 64) if (wg == 0) {
+                    float v[64];
+                    tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(v));
+                    tmem_ld_32x32(taddr + 32, reinterpret_cast<uint32_t*>(v + 32));
+                    tmem_ld_wait();
+                    float out4[4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            v[s * 16 + j] += __ldg(p.bias + s * 16 + j);
+                            mx = fmaxf(mx, v[s * 16 + j]);
+                        }
+                        float den = 0.f, num = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float e = expf(v[s * 16 + j] - mx);
+                            den += e;
+                            num += e * (float)j;
+                        }
+                        out4[s] = num / den;
+                    }
+                    if (row_ok)
+                        *reinterpret_cast<float4*>(p.dfl_out + pix * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[as]);
+            } else {
+                for (int c = wg; c < n_chunks; c += kNumEpiWG) {
+                    float v[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; j += 32) tmem_ld_32x32(taddr + c * CH + j, reinterpret_cast<uint32_t*>(v + j));
+                    tmem_ld_wait();
+                    if (c + kNumEpiWG >= n_chunks) {
+                        // last TMEM read of this warp for this tile: hand the accumulator back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_tempty[as]);
+                    }
+                    const int n_base = n_blk * BN + c * CH;
+                    if (n_base < p.N) {  // warp-uniform: whole chunk beyond N is skipped (nothing to store)
+                        // ---- math: v = resid*alpha + gamma * act(acc + bias) ----
+#pragma unroll
+                        for (int j = 0; j < CH; j += 4) {
+                            const int n = n_base + j;
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                            if (n < p.N) {
+                                if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                                if (p.gamma) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + n));
+                            }
+                            v[j + 0] = act_apply(v[j + 0] + b4.x, p.act) * g4.x;
+                            v[j + 1] = act_apply(v[j + 1] + b4.y, p.act) * g4.y;
+                            v[j + 2] = act_apply(v[j + 2] + b4.z, p.act) * g4.z;
+                            v[j + 3] = act_apply(v[j + 3] + b4.w, p.act) * g4.w;
+                        }
+                        if (p.resid_dtype != 0 && row_ok) {
+                            if (p.resid_dtype == 2) {
+                                const float* rp = reinterpret_cast<const float*>(p.resid) + pix * p.ld_res + n_base;
+#pragma unroll
+                                for (int j = 0; j < CH; j += 4) {
+                                    if (n_base + j < p.N) {
+                                        const float4 x = *reinterpret_cast<const float4*>(rp + j);
+                                        v[j + 0] += p.alpha * x.x;
+                                        v[j + 1] += p.alpha * x.y;
+                                        v[j + 2] += p.alpha * x.z;
+                                        v[j + 3] += p.alpha * x.w;
+                                    }
+                                }
+                            } else {
+                                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix * p.ld_res + n_base;
+                                const __nv_bfloat16* rl = p.resid_lo ? reinterpret_cast<const __nv_bfloat16*>(p.resid_lo) + pix * p.ld_res + n_base : nullptr;
+#pragma unroll
+                                for (int j = 0; j < CH; j += 8) {
+                                    if (n_base + j < p.N) {
+                                        const uint4 x = *reinterpret_cast<const uint4*>(rp + j);
+                                        float xs[8] = {bf16_lo(x.x), bf16_hi(x.x), bf16_lo(x.y), bf16_hi(x.y),
+                                                       bf16_lo(x.z), bf16_hi(x.z), bf16_lo(x.w), bf16_hi(x.w)};
+                                        if (rl) {
+                                            const uint4 y = *reinterpret_cast<const uint4*>(rl + j);
+                                            xs[0] += bf16_lo(y.x); xs[1] += bf16_hi(y.x);
+                                            xs[2] += bf16_lo(y.y); xs[3] += bf16_hi(y.y);
+                                            xs[4] += bf16_lo(y.z); xs[5] += bf16_hi(y.z);
+                                            xs[6] += bf16_lo(y.w); xs[7] += bf16_hi(y.w);
+                                        }
+#pragma unroll
+                                        for (int q = 0; q < 8; ++q) v[j + q] += p.alpha * xs[q];
+                                    }
+                                }
+                            }
+                        }
+                        // ---- stage into swizzled smem, then TMA store ----
+                        uint8_t* sbuf = wg_bufs + buf * C::EPI_BUF_BYTES;
+                        if (issuer) tma_store_wait_read<C::EPI_BUFS - 1>();  // buffer `buf` no longer being read
+                        named_bar_sync(1 + wg, 128);
+                        uint8_t* srow = sbuf + r * 128;
+                        if constexpr (kOutBf16) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                uint4 w;
+                                w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                                w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                                w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                                w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                                *reinterpret_cast<uint4*>(srow + ((q ^ (r & 7)) << 4)) = w;
+                                if constexpr (kSplit) {
+                                    uint4 l;
+                                    l.x = pack_bf16x2(v[q * 8 + 0] - bf16_lo(w.x), v[q * 8 + 1] - bf16_hi(w.x));
+                                    l.y = pack_bf16x2(v[q * 8 + 2] - bf16_lo(w.y), v[q * 8 + 3] - bf16_hi(w.y));
+                                    l.z = pack_bf16x2(v[q * 8 + 4] - bf16_lo(w.z), v[q * 8 + 5] - bf16_hi(w.z));
+                                    l.w = pack_bf16x2(v[q * 8 + 6] - bf16_lo(w.w), v[q * 8 + 7] - bf16_hi(w.w));
+                                    *reinterpret_cast<uint4*>(srow + 16384 + ((q ^ (r & 7)) << 4)) = l;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 w = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                                *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = w;
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + wg, 128);
+                        if (issuer) {
+                            const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
+                            tma_store_5d(&p.tmC, sbuf, c0, o0, o1, o2, g);
+                            if (kSplit && kOutBf16) tma_store_5d(&p.tmC_lo, sbuf + 16384, c0, o0, o1, o2, g);
+                            tma_store_commit();
+                        }
+                        buf = (buf + 1) % C::EPI_BUFS;
+                    }
+                }
+            }
+            if (++as == 2) {
+                as = 0;
+                aphase ^= 1;
+            }
+        }
+        if (issuer) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct GemmOp : CompiledOp {
+    GemmParams prm;
+    int block_n, out_f32, split, grid, smem;
+    int launch(cudaStream_t s) override;
+};
+
+template <int BN, typename OutT, bool kSplit>
+static int launch_inst(const GemmOp& g, cudaStream_t s) {
+    auto kern = gemm_tc_kernel<BN, OutT, kSplit>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        WD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, kSplit>::SMEM_BYTES));
+        attr_set = true;
+    }
+    kern<<<g.grid, kNumThreads, Cfg<BN, kSplit>::SMEM_BYTES, s>>>(g.prm);
+    WD_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int GemmOp::launch(cudaStream_t s) {
+#define WD_DISPATCH(BN)                                                                         \
+    if (block_n == BN) {                                                                        \
+        if (!split) return out_f32 ? launch_inst<BN, float, false>(*this, s)                    \
+                                   : launch_inst<BN, __nv_bfloat16, false>(*this, s);           \
+    }
+    WD_DISPATCH(64)
+    WD_DISPATCH(128)
+    WD_DISPATCH(256)
+#undef WD_DISPATCH
+    if (split && block_n == 64) return out_f32 ? launch_inst<64, float, true>(*this, s) : launch_inst<64, __nv_bfloat16, true>(*this, s);
+    if (split && block_n == 128) return out_f32 ? launch_inst<128, float, true>(*this, s) : launch_inst<128, __nv_bfloat16, true>(*this, s);
+    set_last_error("gemm: unsupported block_n=%d split=%d", block_n, split);
+    return -1;
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
+    const int32_t* I = op.i;
+    auto g = std::make_unique<GemmOp>();
+    GemmParams& P = g->prm;
+    memset(&P, 0, sizeof(P));
+    P.D0 = I[0]; P.D1 = I[1]; P.D2 = I[2];
+    P.E0 = I[3]; P.E1 = I[4]; P.E2 = I[5];
+    const int Kc = I[6];
+    P.ntaps = I[7];
+    P.N = I[8];
+    const long long sa0 = I[9], sa1 = I[10], sa2 = I[11];
+    const int ldb = I[12];
+    g->block_n = I[13];
+    g->out_f32 = I[14];
+    P.act = I[15];
+    P.resid_dtype = I[16];
+    P.ld_res = I[17];
+    P.group_cols = I[18];
+    const int n_groups = I[19];
+    const long long sc0 = I[20], sc1 = I[21], sc2 = I[22], scg = I[23];
+    P.epi_mode = I[24];
+    P.tap_w = I[25] > 0 ? I[25] : 1;
+    P.pad = I[26];
+    P.alpha = op.f[0];
+    P.bias = (const float*)op.p[3];
+    P.gamma = (const float*)op.p[4];
+    P.resid = op.p[5];
+    P.resid_lo = op.p[9];
+    g->split = (op.p[6] != nullptr && op.p[7] != nullptr) ? 1 : 0;
+
+    WD_REQUIRE(P.D0 > 0 && P.D1 > 0 && P.D2 > 0, "gemm: bad dims %d %d %d", P.D0, P.D1, P.D2);
+    WD_REQUIRE(P.E0 > 0 && P.E1 > 0 && P.E2 > 0 && P.E0 * P.E1 * P.E2 <= kTileM, "gemm: bad tile %d %d %d", P.E0, P.E1, P.E2);
+    WD_REQUIRE(Kc > 0 && Kc % kBlockK == 0, "gemm: Kc=%d must be a positive multiple of 64", Kc);
+    WD_REQUIRE(P.ntaps == 1 || P.ntaps == 9, "gemm: ntaps=%d", P.ntaps);
+    WD_REQUIRE(P.N > 0 && P.N % 8 == 0, "gemm: N=%d must be a positive multiple of 8", P.N);
+    WD_REQUIRE(g->block_n == 64 || g->block_n == 128 || g->block_n == 256, "gemm: block_n=%d", g->block_n);
+    WD_REQUIRE(!(g->split && g->block_n == 256), "gemm: split mode supports block_n <= 128");
+    WD_REQUIRE(op.p[0] && op.p[1], "gemm: null operand");
+    WD_REQUIRE(P.group_cols > 0 && n_groups > 0 && P.group_cols * n_groups >= P.N, "gemm: bad groups");
+    const int CH = g->out_f32 ? 32 : 64;
+    WD_REQUIRE(P.group_cols % CH == 0 || n_groups == 1, "gemm: group_cols must be a multiple of the chunk width");
+    WD_REQUIRE(P.resid_dtype == 0 || (P.resid && P.ld_res % 8 == 0), "gemm: residual needs ld_res %% 8 == 0");
+    if (P.epi_mode == 1) {
+        WD_REQUIRE(g->block_n == 64 && P.N == 64 && P.bias && op.p[2], "gemm: DFL epilogue needs N == block_n == 64 and bias");
+        P.dfl_out = (float*)op.p[2];
+    } else {
+        WD_REQUIRE(op.p[2], "gemm: null output");
+    }
+
+    P.kc_iters = Kc / kBlockK;
+    P.nt0 = ceil_div(P.D0, P.E0); P.nt1 = ceil_div(P.D1, P.E1); P.nt2 = ceil_div(P.D2, P.E2);
+    P.num_m_tiles = P.nt0 * P.nt1 * P.nt2;
+    P.num_n_tiles = ceil_div(P.N, g->block_n);
+    P.num_tiles = P.num_m_tiles * P.num_n_tiles;
+    P.rows_a = P.E0 * P.E1 * P.E2;
+
+    // --- A: rank-4 (k, d0, d1, d2), bf16, box (64, E0, E1, E2), 128B swizzle
+    {
+        uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)P.D0, (uint64_t)P.D1, (uint64_t)P.D2};
+        uint64_t str[3] = {(uint64_t)sa0 * 2, (uint64_t)sa1 * 2, (uint64_t)sa2 * 2};
+        uint32_t box[4] = {kBlockK, (uint32_t)P.E0, (uint32_t)P.E1, (uint32_t)P.E2};
+        if (encode_tmap(&P.tmA, op.p[0], 2, 4, dims, str, box, true)) return -1;
+        if (g->split && encode_tmap(&P.tmA_lo, op.p[6], 2, 4, dims, str, box, true)) return -1;
+    }
+    // --- B: rank-2 (k_total, n)
+    {
+        uint64_t dims[2] = {(uint64_t)Kc * P.ntaps, (uint64_t)P.N};
+        uint64_t str[1] = {(uint64_t)ldb * 2};
+        uint32_t box[2] = {kBlockK, (uint32_t)g->block_n};
+        if (encode_tmap(&P.tmB, op.p[1], 2, 2, dims, str, box, true)) return -1;
+        if (g->split && encode_tmap(&P.tmB_lo, op.p[7], 2, 2, dims, str, box, true)) return -1;
+    }
+    // --- C: rank-5 (c, d0, d1, d2, group), box (CH, E0, E1, E2, 1)
+    if (P.epi_mode == 0) {
+        const int eb = g->out_f32 ? 4 : 2;
+        const int cols = n_groups == 1 ? P.N : P.group_cols;
+        uint64_t dims[5] = {(uint64_t)cols, (uint64_t)P.D0, (uint64_t)P.D1, (uint64_t)P.D2, (uint64_t)n_groups};
+        uint64_t str[4] = {(uint64_t)sc0 * eb, (uint64_t)sc1 * eb, (uint64_t)sc2 * eb, (uint64_t)(n_groups == 1 ? sc2 * P.D2 : scg) * eb};
+        uint32_t box[5] = {(uint32_t)CH, (uint32_t)P.E0, (uint32_t)P.E1, (uint32_t)P.E2, 1};
+        if (encode_tmap(&P.tmC, op.p[2], eb, 5, dims, str, box, true)) return -1;
+        if (g->split && !g->out_f32) {
+            WD_REQUIRE(op.p[8], "gemm: split mode with bf16 output needs C_lo");
+            if (encode_tmap(&P.tmC_lo, op.p[8], eb, 5, dims, str, box, true)) return -1;
+        }
+        if (n_groups == 1) P.group_cols = 1 << 30;  // never wrap
+    } else {
+        P.tmC = P.tmA;  // unused, keep a valid descriptor for the prefetch
+    }
+
+    const int sms = device_sm_count();
+    if (sms <= 0) return -2;
+    g->grid = P.num_tiles < sms ? P.num_tiles : sms;
+    out = std::move(g);
+    return 0;
+}
+
+}  // namespace wd

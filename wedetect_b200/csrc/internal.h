@@ -1,0 +1,35 @@
+// internal.h — host-side plumbing shared by the op implementations.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <vector>
+#include <memory>
+#include <atomic>
+#include "../../include/wedetect_b200.h"
+#include "common.cuh"
+
+namespace wd {
+
+extern std::atomic<uint64_t> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+int device_sm_count();
+
+// A compiled op: validated parameters + prebuilt TMA descriptors; `launch` enqueues its kernel(s).
+struct CompiledOp {
+    virtual ~CompiledOp() {}
+    virtual int launch(cudaStream_t s) = 0;
+    virtual int num_kernels() const { return 1; }
+};
+
+// Encode a tiled bf16/f32 tensor map (rank <= 5).  dims/box are innermost-first; strides are in BYTES
+// for dims 1..rank-1.  swizzle128: inner box must span exactly 128 bytes.
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out);
+int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out);  // LN / dwconv / stem / im2col / cast / text
+int compile_postprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out);
+
+}  // namespace wd

@@ -1,0 +1,585 @@
+// postprocess.cu — detection post-process on device, no host synchronisation, bit-exact index logic.
+//
+//   scores = sigmoid(logits); candidates = {(anchor, class) : score > thr}            (multi-label)
+//   order candidates by (score desc, flat index asc)  == stable sort of the reference  -> top nms_pre
+//   decode ltrb*stride around the prior, optional rescale, class-aware greedy NMS (IoU > thr, strict),
+//   keep the first max_per_img survivors in score order, clamp.
+//
+// Reference: wedetect/models/dense_heads/yolo_world_head.py:619-749, generate_proposal.py:85-131,
+// 1000-1048, 1150-1218; mmdet filter_scores_and_topk; mmcv.ops.batched_nms / torchvision.ops.batched_nms
+// (SURVEY.md §8c).  Every floating-point step that feeds a comparison uses explicit round-to-nearest
+// intrinsics (no FMA contraction) so the CPU oracle (oracle/postprocess_ref.c) reproduces it bit for bit.
+//
+// Pipeline (all sizes live on the device):
+//   1 pp_candidates   : one pass over the logits, warp-aggregated append of 64-bit keys
+//                       key = image | (0x3FFFFFFF - score_bits) | flat_index
+//   2 radix sort #1   : stable LSD radix sort (8-bit digits, warp match_any multisplit) of the keys
+//   3 pp_segments     : per-image segment starts, n_sel = min(count, nms_pre)
+//   4 pp_decode       : box decode / rescale of the selected candidates, max coordinate (mmcv offsets),
+//                       second key = image | class | rank
+//   5 radix sort #2   : groups candidates by (image, class) keeping score order inside a class
+//   6 pp_nms          : one block per (class, image) segment: chunked greedy NMS with 128-bit masks
+//   7 pp_finalize     : first max_per_img kept candidates in rank order -> outputs
+#include "internal.h"
+#include <string.h>
+
+namespace wd {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ROWS = 16;                       // rows of 32 keys per warp
+constexpr int RS_TILE = RS_THREADS * RS_ROWS;     // 4096 keys per block-tile
+constexpr int RS_GRID = 148 * 4;
+
+struct PPCtrl {  // lives in device memory
+    unsigned int total;      // candidates appended
+    unsigned int total2;     // selected candidates (sum of n_sel)
+    unsigned int overflow;
+    unsigned int pad;
+};
+
+struct PPDev {
+    wd_pp_params p;
+    int A;                  // anchors per image
+    int lvl_off[5];         // anchor offset of each level
+    unsigned long long cap; // key capacity
+    int idx_bits, b_bits, cls_bits;
+    // workspace pointers
+    unsigned long long *keys0, *keys1, *keys2a, *keys2b;
+    unsigned int* hist;
+    PPCtrl* ctrl;
+    unsigned int *counts, *seg, *nsel, *seg2;
+    unsigned int* maxc;     // per image max coordinate (order-preserving uint encoding of float)
+    float4* cand_box;
+    float* cand_score;
+    int *cand_label, *cand_anchor;
+    unsigned char* keep;
+};
+
+__device__ __forceinline__ float sigmoid_dr(float x) {
+    // correctly-rounded-in-practice sigmoid: evaluate in double, round once to float
+    return (float)(1.0 / (1.0 + exp(-(double)x)));
+}
+__device__ __forceinline__ unsigned int float_ord(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_float(unsigned int o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+
+__global__ void pp_reset_kernel(PPDev d) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        d.ctrl->total = 0;
+        d.ctrl->total2 = 0;
+        d.ctrl->overflow = 0;
+    }
+    if (t < d.p.B) {
+        d.counts[t] = 0;
+        d.maxc[t] = 0;  // smaller than the encoding of any float
+    }
+}
+
+// one thread per (image, anchor-in-level, class) element; consecutive threads walk classes (contiguous)
+__global__ void __launch_bounds__(256) pp_candidates_kernel(PPDev d, int lvl) {
+    const int K = d.p.K;
+    const int hw = d.p.lvl_h[lvl] * d.p.lvl_w[lvl];
+    const long long total = (long long)d.p.B * hw * K;
+    const float* logits = d.p.logits[lvl];
+    const int ld = d.p.ld_logit[lvl];
+    const float thr = d.p.score_thr;
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long start = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long iters = (total + stride - 1) / stride;
+    for (long long it = 0; it < iters; ++it) {
+        const long long t = start + it * stride;
+        bool pass = false;
+        unsigned long long key = 0;
+        int b = 0;
+        if (t < total) {
+            const int k = (int)(t % K);
+            const long long row = t / K;  // b*hw + a
+            b = (int)(row / hw);
+            const int a = (int)(row % hw);
+            const float s = sigmoid_dr(logits[row * ld + k]);
+            if (s > thr) {
+                pass = true;
+                const unsigned int inv = 0x3FFFFFFFu - (__float_as_uint(s) & 0x3FFFFFFFu);
+                const unsigned long long idx = (unsigned long long)(d.lvl_off[lvl] + a) * K + k;
+                key = ((unsigned long long)b << (d.idx_bits + 30)) | ((unsigned long long)inv << d.idx_bits) | idx;
+            }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            unsigned int base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(&d.ctrl->total, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass) {
+                const unsigned long long pos = (unsigned long long)base + __popc(m & ((1u << lane) - 1));
+                if (pos < d.cap) d.keys0[pos] = key;
+                else d.ctrl->overflow = 1;
+                const unsigned int grp = __match_any_sync(m, b);  // lanes of this warp that hit the same image
+                if (lane == __ffs(grp) - 1) atomicAdd(&d.counts[b], (unsigned int)__popc(grp));
+            }
+        }
+    }
+}
+
+// ---------------- stable LSD radix sort (keys only, 8-bit digit) ----------------
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ n_ptr, int shift,
+                                                             unsigned int* __restrict__ hist) {
+    __shared__ unsigned int h[256];
+    const unsigned int n = *n_ptr;
+    const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    for (unsigned int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        h[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned long long base = (unsigned long long)tile * RS_TILE;
+#pragma unroll
+        for (int i = 0; i < RS_ROWS; ++i) {
+            const unsigned long long idx = base + (unsigned long long)i * RS_THREADS + threadIdx.x;
+            if (idx < n) atomicAdd(&h[(unsigned int)(keys[idx] >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        hist[(unsigned long long)threadIdx.x * num_tiles + tile] = h[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) rs_scan_kernel(const unsigned int* __restrict__ n_ptr, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int part[1024];
+    const unsigned int n = *n_ptr;
+    const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    const unsigned long long len = 256ull * num_tiles;
+    const unsigned long long per = (len + 1023) / 1024;
+    const unsigned long long lo = per * threadIdx.x, hi = (lo + per < len) ? lo + per : len;
+    unsigned int s = 0;
+    for (unsigned long long i = lo; i < hi; ++i) s += hist[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const unsigned int t = part[i];
+            part[i] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    unsigned int run = part[threadIdx.x];
+    for (unsigned long long i = lo; i < hi; ++i) {
+        const unsigned int t = hist[i];
+        hist[i] = run;
+        run += t;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long* __restrict__ out,
+                                                                const unsigned int* __restrict__ n_ptr, int shift, const unsigned int* __restrict__ hist) {
+    __shared__ unsigned int wh[RS_THREADS / 32][256];
+    const unsigned int n = *n_ptr;
+    const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int lt = (1u << lane) - 1;
+    for (unsigned int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int w = 0; w < RS_THREADS / 32; ++w) wh[w][threadIdx.x] = 0;
+        __syncthreads();
+        unsigned long long k[RS_ROWS];
+        unsigned short rank[RS_ROWS];
+        const unsigned long long base = (unsigned long long)tile * RS_TILE + (unsigned long long)warp * (32 * RS_ROWS);
+#pragma unroll
+        for (int i = 0; i < RS_ROWS; ++i) {
+            const unsigned long long idx = base + (unsigned long long)i * 32 + lane;
+            const bool valid = idx < n;
+            k[i] = valid ? keys[idx] : 0ull;
+            const unsigned int dgt = valid ? ((unsigned int)(k[i] >> shift) & 255u) : 256u;
+            const unsigned int peers = __match_any_sync(0xffffffffu, dgt);
+            unsigned int prev = 0;
+            if (valid) prev = wh[warp][dgt];
+            __syncwarp();
+            if (valid && (peers & lt) == 0) wh[warp][dgt] = prev + __popc(peers);
+            __syncwarp();
+            rank[i] = (unsigned short)(prev + __popc(peers & lt));
+        }
+        __syncthreads();
+        {
+            const unsigned int dgt = threadIdx.x;
+            unsigned int run = hist[(unsigned long long)dgt * num_tiles + tile];
+#pragma unroll
+            for (int w = 0; w < RS_THREADS / 32; ++w) {
+                const unsigned int t = wh[w][dgt];
+                wh[w][dgt] = run;
+                run += t;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RS_ROWS; ++i) {
+            const unsigned long long idx = base + (unsigned long long)i * 32 + lane;
+            if (idx < n) {
+                const unsigned int dgt = (unsigned int)(k[i] >> shift) & 255u;
+                out[wh[warp][dgt] + rank[i]] = k[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------- segments, decode ----------------
+__global__ void pp_segments_kernel(PPDev d) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned int run = 0, run2 = 0;
+        for (int b = 0; b < d.p.B; ++b) {
+            d.seg[b] = run;
+            d.seg2[b] = run2;
+            const unsigned int c = d.counts[b];
+            const unsigned int ns = c < (unsigned int)d.p.nms_pre ? c : (unsigned int)d.p.nms_pre;
+            d.nsel[b] = ns;
+            run += c;
+            run2 += ns;
+        }
+        d.seg[d.p.B] = run;
+        d.seg2[d.p.B] = run2;
+        d.ctrl->total2 = run2;
+    }
+}
+
+__global__ void __launch_bounds__(256) pp_decode_kernel(PPDev d, const unsigned long long* __restrict__ sorted) {
+    const int b = blockIdx.y;
+    const unsigned int ns = d.nsel[b];
+    const int K = d.p.K;
+    const float* meta = d.p.img_meta + b * 8;
+    const float psx = meta[0], psy = meta[1], pdx = meta[2], pdy = meta[3];
+    float local_max = -INFINITY;
+    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < ns; r += gridDim.x * blockDim.x) {
+        const unsigned long long key = sorted[d.seg[b] + r];
+        const unsigned int idx = (unsigned int)(key & ((1ull << d.idx_bits) - 1));
+        const unsigned int inv = (unsigned int)(key >> d.idx_bits) & 0x3FFFFFFFu;
+        const float score = __uint_as_float(0x3FFFFFFFu - inv);
+        const int anchor = idx / K, cls = idx % K;
+        int lvl = 0;
+        while (lvl + 1 < d.p.nlevels && anchor >= d.lvl_off[lvl + 1]) ++lvl;
+        const int a = anchor - d.lvl_off[lvl];
+        const int w = d.p.lvl_w[lvl], hw = d.p.lvl_h[lvl] * w;
+        const float stride = (float)d.p.lvl_stride[lvl];
+        // MlvlPointGenerator: (i + 0.5) * stride (generate_proposal.py:880-892)
+        const float px = __fmul_rn((float)(a % w) + 0.5f, stride);
+        const float py = __fmul_rn((float)(a / w) + 0.5f, stride);
+        const float4 lt = *reinterpret_cast<const float4*>(d.p.dist[lvl] + ((long long)b * hw + a) * 4);
+        // flatten_bbox_preds * stride, then distance2bbox (yolo_world_head.py:654-667, coder :51-53)
+        float x1 = __fsub_rn(px, __fmul_rn(lt.x, stride));
+        float y1 = __fsub_rn(py, __fmul_rn(lt.y, stride));
+        float x2 = __fadd_rn(px, __fmul_rn(lt.z, stride));
+        float y2 = __fadd_rn(py, __fmul_rn(lt.w, stride));
+        // mmdet rescale before NMS (yolo_world_head.py:728-734); identity when sub = 0, div = 1
+        x1 = __fdiv_rn(__fsub_rn(x1, psx), pdx);
+        y1 = __fdiv_rn(__fsub_rn(y1, psy), pdy);
+        x2 = __fdiv_rn(__fsub_rn(x2, psx), pdx);
+        y2 = __fdiv_rn(__fsub_rn(y2, psy), pdy);
+        const unsigned int o = d.seg2[b] + r;
+        d.cand_box[o] = make_float4(x1, y1, x2, y2);
+        d.cand_score[o] = score;
+        d.cand_label[o] = cls;
+        d.cand_anchor[o] = anchor;
+        d.keep[o] = 0;
+        d.keys2a[o] = ((unsigned long long)b << (16 + d.cls_bits)) | ((unsigned long long)cls << 16) | r;
+        local_max = fmaxf(local_max, fmaxf(fmaxf(x1, y1), fmaxf(x2, y2)));
+    }
+    local_max = warp_max(local_max);
+    if ((threadIdx.x & 31) == 0 && local_max > -INFINITY) atomicMax(&d.maxc[b], float_ord(local_max));
+}
+
+// ---------------- class-aware greedy NMS: one block per (class, image) ----------------
+__device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float area_b, float thr) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    return __fdiv_rn(inter, uni) > thr;
+}
+
+__global__ void __launch_bounds__(128) pp_nms_kernel(PPDev d, const unsigned long long* __restrict__ sorted2, float4* __restrict__ kept_scratch) {
+    __shared__ float4 cbox[128];
+    __shared__ float carea[128];
+    __shared__ unsigned int cmask[128][4];
+    __shared__ unsigned char calive[128];
+    __shared__ int s_nk;
+    const int cls = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const unsigned int lo_b = d.seg2[b], hi_b = d.seg2[b + 1];
+    if (lo_b == hi_b) return;
+    // segment of this class inside the image's (class, rank)-sorted key range
+    const unsigned long long k_lo = ((unsigned long long)b << (16 + d.cls_bits)) | ((unsigned long long)cls << 16);
+    const unsigned long long k_hi = k_lo + (1ull << 16);
+    unsigned int lo = lo_b, hi = hi_b;
+    while (lo < hi) {
+        const unsigned int mid = (lo + hi) >> 1;
+        if (sorted2[mid] < k_lo) lo = mid + 1; else hi = mid;
+    }
+    const unsigned int s0 = lo;
+    hi = hi_b;
+    while (lo < hi) {
+        const unsigned int mid = (lo + hi) >> 1;
+        if (sorted2[mid] < k_hi) lo = mid + 1; else hi = mid;
+    }
+    const unsigned int s1 = lo;
+    const int n = (int)(s1 - s0);
+    if (n == 0) return;
+
+    // coordinate offsets (mmcv: always; torchvision: only when 4 * n_img <= tv_numel_thr)
+    const unsigned int n_img = hi_b - lo_b;
+    bool use_off = d.p.nms_mode == 0 || (4u * n_img <= (unsigned int)d.p.tv_numel_thr);
+    float off = 0.f;
+    if (use_off) off = __fmul_rn((float)cls, __fadd_rn(ord_float(d.maxc[b]), 1.0f));
+    const float thr = d.p.iou_thr;
+    float4* kept = kept_scratch + s0;  // at most n kept boxes, private to this segment
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+
+    for (int base = 0; base < n; base += 128) {
+        const int t = base + tid;
+        const bool valid = t < n;
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned int slot = 0;
+        if (valid) {
+            const unsigned int r = (unsigned int)(sorted2[s0 + t] & 0xFFFFu);
+            slot = lo_b + r;
+            const float4 bx = d.cand_box[slot];
+            mine = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+        }
+        const float area = __fmul_rn(__fsub_rn(mine.z, mine.x), __fsub_rn(mine.w, mine.y));
+        bool alive = valid;
+        const int nk = s_nk;
+        for (int i = 0; i < nk && alive; ++i) {
+            const float4 kb = kept[i];
+            const float ka = __fmul_rn(__fsub_rn(kb.z, kb.x), __fsub_rn(kb.w, kb.y));
+            if (iou_gt(kb, ka, mine, area, thr)) alive = false;
+        }
+        cbox[tid] = mine;
+        carea[tid] = area;
+        calive[tid] = alive ? 1 : 0;
+        __syncthreads();
+        unsigned int m[4] = {0, 0, 0, 0};
+        if (alive) {
+            for (int j = tid + 1; j < 128 && base + j < n; ++j)
+                if (calive[j] && iou_gt(mine, area, cbox[j], carea[j], thr)) m[j >> 5] |= 1u << (j & 31);
+        }
+        cmask[tid][0] = m[0]; cmask[tid][1] = m[1]; cmask[tid][2] = m[2]; cmask[tid][3] = m[3];
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int rem[4] = {0, 0, 0, 0};
+            int nk2 = s_nk;
+            const int lim = (n - base) < 128 ? (n - base) : 128;
+            for (int j = 0; j < lim; ++j) {
+                if (calive[j] && !((rem[j >> 5] >> (j & 31)) & 1u)) {
+                    kept[nk2++] = cbox[j];
+                    calive[j] = 2;  // kept
+                    rem[0] |= cmask[j][0]; rem[1] |= cmask[j][1]; rem[2] |= cmask[j][2]; rem[3] |= cmask[j][3];
+                }
+            }
+            s_nk = nk2;
+        }
+        __syncthreads();
+        if (valid && calive[tid] == 2) d.keep[slot] = 1;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) pp_finalize_kernel(PPDev d) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int ns = d.nsel[b], lo_b = d.seg2[b];
+    const int maxk = d.p.max_per_img;
+    const float* meta = d.p.img_meta + b * 8;
+    const float qsx = meta[4], qsy = meta[5], qd = meta[6];
+    const float cw = d.p.clamp_wh[b * 2 + 0], chh = d.p.clamp_wh[b * 2 + 1];
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (unsigned int r0 = 0; r0 < ns; r0 += 256) {
+        const unsigned int r = r0 + tid;
+        const bool k = r < ns && d.keep[lo_b + r] != 0;
+        const unsigned int m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        const int pos = off + __popc(m & ((1u << lane) - 1));
+        if (k && pos < maxk) {
+            const float4 bx = d.cand_box[lo_b + r];
+            float x1 = __fdiv_rn(__fsub_rn(bx.x, qsx), qd), y1 = __fdiv_rn(__fsub_rn(bx.y, qsy), qd);
+            float x2 = __fdiv_rn(__fsub_rn(bx.z, qsx), qd), y2 = __fdiv_rn(__fsub_rn(bx.w, qsy), qd);
+            x1 = fminf(fmaxf(x1, 0.f), cw); x2 = fminf(fmaxf(x2, 0.f), cw);
+            y1 = fminf(fmaxf(y1, 0.f), chh); y2 = fminf(fmaxf(y2, 0.f), chh);
+            const long long o = (long long)b * maxk + pos;
+            *reinterpret_cast<float4*>(d.p.out_boxes + o * 4) = make_float4(x1, y1, x2, y2);
+            d.p.out_scores[o] = d.cand_score[lo_b + r];
+            d.p.out_labels[o] = d.cand_label[lo_b + r];
+            d.p.out_anchor[o] = d.cand_anchor[lo_b + r];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+        if (s_base >= maxk) break;
+    }
+    const int cnt = s_base < maxk ? s_base : maxk;
+    if (tid == 0) d.p.out_counts[b] = cnt;
+    for (int j = cnt + tid; j < maxk; j += 256) {
+        const long long o = (long long)b * maxk + j;
+        *reinterpret_cast<float4*>(d.p.out_boxes + o * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        d.p.out_scores[o] = 0.f;
+        d.p.out_labels[o] = -1;
+        d.p.out_anchor[o] = -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static int bits_for(unsigned long long n) {  // bits needed to represent values < n
+    int b = 1;
+    while ((1ull << b) < n) ++b;
+    return b;
+}
+static unsigned long long align256(unsigned long long x) { return (x + 255) & ~255ull; }
+
+struct PPLayout {
+    unsigned long long off_keys0, off_keys1, off_hist, off_ctrl, off_counts, off_seg, off_nsel, off_seg2, off_maxc, off_box, off_score, off_label,
+        off_anchor, off_keys2a, off_keys2b, off_keep, off_kept, total;
+};
+static PPLayout pp_layout(int B, int A, int K, int nms_pre) {
+    PPLayout L;
+    const unsigned long long cap = (unsigned long long)B * A * K;
+    const unsigned long long sel = (unsigned long long)B * nms_pre < cap ? (unsigned long long)B * nms_pre : cap;
+    const unsigned long long tiles = (cap + RS_TILE - 1) / RS_TILE + 1;
+    unsigned long long o = 0;
+    L.off_keys0 = o; o = align256(o + cap * 8);
+    L.off_keys1 = o; o = align256(o + cap * 8);
+    L.off_hist = o; o = align256(o + tiles * 256 * 4);
+    L.off_ctrl = o; o = align256(o + sizeof(PPCtrl));
+    L.off_counts = o; o = align256(o + (B + 1) * 4ull);
+    L.off_seg = o; o = align256(o + (B + 1) * 4ull);
+    L.off_nsel = o; o = align256(o + (B + 1) * 4ull);
+    L.off_seg2 = o; o = align256(o + (B + 1) * 4ull);
+    L.off_maxc = o; o = align256(o + (B + 1) * 4ull);
+    L.off_box = o; o = align256(o + sel * 16);
+    L.off_score = o; o = align256(o + sel * 4);
+    L.off_label = o; o = align256(o + sel * 4);
+    L.off_anchor = o; o = align256(o + sel * 4);
+    L.off_keys2a = o; o = align256(o + sel * 8);
+    L.off_keys2b = o; o = align256(o + sel * 8);
+    L.off_keep = o; o = align256(o + sel);
+    L.off_kept = o; o = align256(o + sel * 16);
+    L.total = o;
+    return L;
+}
+
+struct PostOp : CompiledOp {
+    PPDev d;
+    int passes1, passes2, kernels;
+    int num_kernels() const override { return kernels; }
+    int sort(unsigned long long* a, unsigned long long* b, const unsigned int* n_ptr, int passes, cudaStream_t s) {
+        for (int p = 0; p < passes; ++p) {
+            const unsigned long long* src = (p & 1) ? b : a;
+            unsigned long long* dst = (p & 1) ? a : b;
+            rs_hist_kernel<<<RS_GRID, RS_THREADS, 0, s>>>(src, n_ptr, p * 8, d.hist);
+            rs_scan_kernel<<<1, 1024, 0, s>>>(n_ptr, d.hist);
+            rs_scatter_kernel<<<RS_GRID, RS_THREADS, 0, s>>>(src, dst, n_ptr, p * 8, d.hist);
+            count_launch(3);
+        }
+        WD_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int launch(cudaStream_t s) override {
+        pp_reset_kernel<<<(d.p.B + 255) / 256, 256, 0, s>>>(d);
+        count_launch();
+        for (int l = 0; l < d.p.nlevels; ++l) {
+            const long long total = (long long)d.p.B * d.p.lvl_h[l] * d.p.lvl_w[l] * d.p.K;
+            long long g = (total + 255) / 256;
+            if (g > 148 * 16) g = 148 * 16;
+            pp_candidates_kernel<<<(int)g, 256, 0, s>>>(d, l);
+            count_launch();
+        }
+        if (sort(d.keys0, d.keys1, &d.ctrl->total, passes1, s)) return -2;
+        const unsigned long long* sorted1 = (passes1 & 1) ? d.keys1 : d.keys0;
+        pp_segments_kernel<<<1, 32, 0, s>>>(d);
+        pp_decode_kernel<<<dim3(32, d.p.B), 256, 0, s>>>(d, sorted1);
+        count_launch(2);
+        if (sort(d.keys2a, d.keys2b, &d.ctrl->total2, passes2, s)) return -2;
+        const unsigned long long* sorted2 = (passes2 & 1) ? d.keys2b : d.keys2a;
+        pp_nms_kernel<<<dim3(d.p.K, d.p.B), 128, 0, s>>>(d, sorted2, kept);
+        pp_finalize_kernel<<<d.p.B, 256, 0, s>>>(d);
+        count_launch(2);
+        WD_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    float4* kept;
+};
+
+int compile_postprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
+    WD_REQUIRE(op.p[0], "postprocess: p[0] must point to a host wd_pp_params");
+    if (device_sm_count() <= 0) return -2;
+    auto o = std::make_unique<PostOp>();
+    memset(&o->d, 0, sizeof(o->d));
+    o->d.p = *reinterpret_cast<const wd_pp_params*>(op.p[0]);
+    const wd_pp_params& p = o->d.p;
+    WD_REQUIRE(p.B > 0 && p.B <= 1024 && p.K > 0 && p.nlevels >= 1 && p.nlevels <= 4, "postprocess: bad B/K/nlevels");
+    WD_REQUIRE(p.multi_label == 1, "postprocess: only multi_label=True is implemented (all shipped configs)");
+    WD_REQUIRE(p.nms_pre > 0 && p.nms_pre <= 65535 && p.max_per_img > 0, "postprocess: nms_pre must be in [1, 65535]");
+    WD_REQUIRE(p.nms_mode == 0 || p.nms_mode == 1, "postprocess: bad nms_mode");
+    int A = 0;
+    for (int l = 0; l < p.nlevels; ++l) {
+        WD_REQUIRE(p.logits[l] && p.dist[l] && p.lvl_h[l] > 0 && p.lvl_w[l] > 0 && p.ld_logit[l] >= p.K, "postprocess: bad level %d", l);
+        o->d.lvl_off[l] = A;
+        A += p.lvl_h[l] * p.lvl_w[l];
+    }
+    o->d.lvl_off[p.nlevels] = A;
+    o->d.A = A;
+    WD_REQUIRE(p.img_meta && p.clamp_wh && p.out_boxes && p.out_scores && p.out_labels && p.out_anchor && p.out_counts, "postprocess: null pointer");
+    const unsigned long long cap = (unsigned long long)p.B * A * p.K;
+    WD_REQUIRE(cap < (1ull << 32), "postprocess: B*A*K too large");
+    o->d.cap = cap;
+    o->d.idx_bits = bits_for((unsigned long long)A * p.K);
+    o->d.b_bits = bits_for(p.B);
+    o->d.cls_bits = bits_for(p.K);
+    WD_REQUIRE(o->d.idx_bits + 30 + o->d.b_bits <= 64, "postprocess: key overflow");
+    const PPLayout L = pp_layout(p.B, A, p.K, p.nms_pre);
+    WD_REQUIRE(p.workspace && p.workspace_bytes >= L.total, "postprocess: workspace too small (%llu < %llu)", (unsigned long long)p.workspace_bytes,
+               (unsigned long long)L.total);
+    WD_REQUIRE((reinterpret_cast<uintptr_t>(p.workspace) & 255) == 0, "postprocess: workspace must be 256-byte aligned");
+    uint8_t* w = reinterpret_cast<uint8_t*>(p.workspace);
+    o->d.keys0 = (unsigned long long*)(w + L.off_keys0);
+    o->d.keys1 = (unsigned long long*)(w + L.off_keys1);
+    o->d.hist = (unsigned int*)(w + L.off_hist);
+    o->d.ctrl = (PPCtrl*)(w + L.off_ctrl);
+    o->d.counts = (unsigned int*)(w + L.off_counts);
+    o->d.seg = (unsigned int*)(w + L.off_seg);
+    o->d.nsel = (unsigned int*)(w + L.off_nsel);
+    o->d.seg2 = (unsigned int*)(w + L.off_seg2);
+    o->d.maxc = (unsigned int*)(w + L.off_maxc);
+    o->d.cand_box = (float4*)(w + L.off_box);
+    o->d.cand_score = (float*)(w + L.off_score);
+    o->d.cand_label = (int*)(w + L.off_label);
+    o->d.cand_anchor = (int*)(w + L.off_anchor);
+    o->d.keys2a = (unsigned long long*)(w + L.off_keys2a);
+    o->d.keys2b = (unsigned long long*)(w + L.off_keys2b);
+    o->d.keep = (unsigned char*)(w + L.off_keep);
+    o->kept = (float4*)(w + L.off_kept);
+    o->passes1 = (o->d.idx_bits + 30 + o->d.b_bits + 7) / 8;
+    o->passes2 = (16 + o->d.cls_bits + o->d.b_bits + 7) / 8;
+    o->kernels = 1 + p.nlevels + 3 * (o->passes1 + o->passes2) + 4;
+    out = std::move(o);
+    return 0;
+}
+
+}  // namespace wd
+
+extern "C" uint64_t wd_pp_workspace_bytes(int B, int anchors, int K, int nms_pre) {
+    if (B <= 0 || anchors <= 0 || K <= 0 || nms_pre <= 0) return 0;
+    return wd::pp_layout(B, anchors, K, nms_pre).total;
+}

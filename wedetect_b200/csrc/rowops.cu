@@ -1,0 +1,693 @@
+// rowops.cu — the HBM-/CUDA-core-bound kernels around the tensor-core GEMMs:
+//   LayerNorm rows (+ space-to-depth write), depthwise 7x7 + LayerNorm, stem patch gather,
+//   stride-2 im2col, casts, XLM-R embedding / short attention / pooling, contrastive-head folding,
+//   kept-proposal embedding gather.
+// All activations are NHWC ("rows" = pixels, columns = channels), loads/stores are 8/16-byte vectors,
+// coalesced along channels.  `*_lo` outputs are the low bf16 plane of the bf16x3 precise mode.
+#include "internal.h"
+#include <functional>
+#include <math.h>
+
+namespace wd {
+
+struct FnOp : CompiledOp {
+    std::function<int(cudaStream_t)> fn;
+    int launch(cudaStream_t s) override { return fn(s); }
+};
+
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, float a, float b, float c, float d) {
+    uint2 w;
+    w.x = pack_bf16x2(a, b);
+    w.y = pack_bf16x2(c, d);
+    *reinterpret_cast<uint2*>(hi + idx) = w;
+    if (lo) {
+        uint2 l;
+        l.x = pack_bf16x2(a - bf16_lo(w.x), b - bf16_hi(w.x));
+        l.y = pack_bf16x2(c - bf16_lo(w.y), d - bf16_hi(w.y));
+        *reinterpret_cast<uint2*>(lo + idx) = l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over rows (one warp per row).  mm_backbone.py:145-155 / F.layer_norm semantics:
+// u = mean(x); s = mean((x-u)^2); y = (x-u)/sqrt(s+eps)*w + b
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 12;  // C <= 1536
+
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, int rows, int C, int ld_in, const float* __restrict__ w,
+                                                      const float* __restrict__ b, float eps, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                                                      float* out_f32, int ld_out, int s2d, int W, int H) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* x = in + (long long)row * ld_in;
+    float4 v[kLnMaxVec];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < C) {
+            v[i] = *reinterpret_cast<const float4*>(x + c);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < C) {
+            const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + bb * bb) + (cc * cc + d * d);
+        }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)C + eps);
+    long long orow = row;
+    int coff = 0;
+    if (s2d) {
+        const int xx = row % W, yy = (row / W) % H, bi = row / (W * H);
+        orow = ((long long)bi * (H / 2) + yy / 2) * (W / 2) + xx / 2;
+        coff = ((yy & 1) * 2 + (xx & 1)) * C;
+    }
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < C) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+            const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x;
+            const float y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+            const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z;
+            const float y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+            if (out_hi) store_bf16x4(out_hi, out_lo, orow * ld_out + coff + c, y0, y1, y2, y3);
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * C + c) = make_float4(y0, y1, y2, y3);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 7x7 (pad 3) + bias + LayerNorm(C) -> bf16.   mm_backbone.py:114-116.
+// block = C/4 threads (rounded up to a warp multiple); a block owns a strip of TY x TX output pixels
+// and ALL channels of them (needed for the per-pixel LayerNorm); a thread owns 4 channels.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDwTX = 8, kDwTY = 2;
+
+__global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict__ in, int B, int H, int W, int C, const float* __restrict__ wt,
+                                                         const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                                         float eps, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+    __shared__ float red[kDwTY * kDwTX][12];
+    const int cg = threadIdx.x;
+    const int c = cg * 4;
+    const bool active = c < C;
+    const int x0 = blockIdx.x * kDwTX, y0 = blockIdx.y * kDwTY, bi = blockIdx.z;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    float4 acc[kDwTY][kDwTX];
+#pragma unroll
+    for (int oy = 0; oy < kDwTY; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < kDwTX; ++ox) acc[oy][ox] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (active) {
+        const float* inb = in + (long long)bi * H * W * C + c;
+#pragma unroll 1
+        for (int iy = 0; iy < kDwTY + 6; ++iy) {
+            const int yin = y0 - 3 + iy;
+            if (yin < 0 || yin >= H) continue;
+            float4 wrow[kDwTY][7];
+#pragma unroll
+            for (int oy = 0; oy < kDwTY; ++oy) {
+                const int dy = iy - oy;
+#pragma unroll
+                for (int dx = 0; dx < 7; ++dx)
+                    wrow[oy][dx] = (dy >= 0 && dy < 7) ? __ldg(reinterpret_cast<const float4*>(wt + (long long)(dy * 7 + dx) * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float* inr = inb + (long long)yin * W * C;
+#pragma unroll
+            for (int ix = 0; ix < kDwTX + 6; ++ix) {
+                const int xin = x0 - 3 + ix;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (xin >= 0 && xin < W) v = __ldg(reinterpret_cast<const float4*>(inr + (long long)xin * C));
+#pragma unroll
+                for (int oy = 0; oy < kDwTY; ++oy) {
+#pragma unroll
+                    for (int ox = 0; ox < kDwTX; ++ox) {
+                        const int dx = ix - ox;
+                        if (dx >= 0 && dx < 7) {
+                            acc[oy][ox].x = fmaf(v.x, wrow[oy][dx].x, acc[oy][ox].x);
+                            acc[oy][ox].y = fmaf(v.y, wrow[oy][dx].y, acc[oy][ox].y);
+                            acc[oy][ox].z = fmaf(v.z, wrow[oy][dx].z, acc[oy][ox].z);
+                            acc[oy][ox].w = fmaf(v.w, wrow[oy][dx].w, acc[oy][ox].w);
+                        }
+                    }
+                }
+            }
+        }
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+#pragma unroll
+        for (int oy = 0; oy < kDwTY; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < kDwTX; ++ox) {
+                acc[oy][ox].x += b4.x; acc[oy][ox].y += b4.y; acc[oy][ox].z += b4.z; acc[oy][ox].w += b4.w;
+            }
+    }
+
+    // ---- LayerNorm over channels: two block reductions (mean, then centred second moment) ----
+    float mean[kDwTY][kDwTX], rstd[kDwTY][kDwTX];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int oy = 0; oy < kDwTY; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < kDwTX; ++ox) {
+                float s = 0.f;
+                if (active) {
+                    const float4 a = acc[oy][ox];
+                    if (pass == 0) s = (a.x + a.y) + (a.z + a.w);
+                    else {
+                        const float m = mean[oy][ox];
+                        s = ((a.x - m) * (a.x - m) + (a.y - m) * (a.y - m)) + ((a.z - m) * (a.z - m) + (a.w - m) * (a.w - m));
+                    }
+                }
+                s = warp_sum(s);
+                if (lane == 0) red[oy * kDwTX + ox][warp] = s;
+            }
+        __syncthreads();
+#pragma unroll
+        for (int oy = 0; oy < kDwTY; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < kDwTX; ++ox) {
+                float t = 0.f;
+                for (int w2 = 0; w2 < nwarps; ++w2) t += red[oy * kDwTX + ox][w2];
+                if (pass == 0) mean[oy][ox] = t / (float)C;
+                else rstd[oy][ox] = 1.f / sqrtf(t / (float)C + eps);
+            }
+        __syncthreads();
+    }
+    if (!active) return;
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(lnw + c));
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(lnb + c));
+#pragma unroll
+    for (int oy = 0; oy < kDwTY; ++oy) {
+        const int y = y0 + oy;
+        if (y >= H) continue;
+#pragma unroll
+        for (int ox = 0; ox < kDwTX; ++ox) {
+            const int x = x0 + ox;
+            if (x >= W) continue;
+            const float m = mean[oy][ox], r = rstd[oy][ox];
+            const float4 a = acc[oy][ox];
+            const long long idx = (((long long)bi * H + y) * W + x) * C + c;
+            store_bf16x4(out_hi, out_lo, idx, (a.x - m) * r * w4.x + g4.x, (a.y - m) * r * w4.y + g4.y, (a.z - m) * r * w4.z + g4.z,
+                         (a.w - m) * r * w4.w + g4.w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem patch gather: NCHW image -> rows [B*(H/4)*(W/4), 64], k = c*16 + dy*4 + dx (48 valid, 16 zero)
+// ------------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void stem_patch_kernel(const InT* __restrict__ in, int B, int H, int W, float scale, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+    const int Wo = W / 4, Ho = H / 4;
+    const long long total = (long long)B * Ho * Wo * 16;  // 16 groups of 4 k-values per row
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int grp = (int)(t & 15);
+        const long long m = t >> 4;
+        const int px = (int)(m % Wo), py = (int)((m / Wo) % Ho), bi = (int)(m / ((long long)Wo * Ho));
+        float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+        if (grp < 12) {
+            const int ch = grp >> 2, dy = grp & 3;
+            const InT* src = in + (((long long)bi * 3 + ch) * H + (py * 4 + dy)) * W + px * 4;
+            a = (float)src[0] * scale; b = (float)src[1] * scale; c = (float)src[2] * scale; d = (float)src[3] * scale;
+        }
+        store_bf16x4(out_hi, out_lo, m * 64 + grp * 4, a, b, c, d);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col for 3x3 stride-2 pad-1 conv, bf16 NHWC -> rows [B*Ho*Wo, 9*C], k = (ky*3+kx)*C + c
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ in_lo, int B, int H, int W, int C, int ld_in,
+                                 __nv_bfloat16* out, __nv_bfloat16* out_lo) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const int vec = C / 8;
+    const long long total = (long long)B * Ho * Wo * 9 * vec;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(t % vec);
+        long long r = t / vec;
+        const int tap = (int)(r % 9);
+        r /= 9;
+        const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho), bi = (int)(r / ((long long)Wo * Ho));
+        const int iy = oy * 2 + tap / 3 - 1, ix = ox * 2 + tap % 3 - 1;
+        uint4 v = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            const long long src = (((long long)bi * H + iy) * W + ix) * ld_in + cv * 8;
+            v = *reinterpret_cast<const uint4*>(in + src);
+            if (in_lo) l = *reinterpret_cast<const uint4*>(in_lo + src);
+        }
+        const long long dst = r * (9LL * C) + (long long)tap * C + cv * 8;
+        *reinterpret_cast<uint4*>(out + dst) = v;
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + dst) = l;
+    }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, long long rows, int C, int ld_in, int ld_out, __nv_bfloat16* out, __nv_bfloat16* out_lo) {
+    const int vec = C / 4;
+    const long long total = rows * vec;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / vec;
+        const int c = (int)(t % vec) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+        store_bf16x4(out, out_lo, r * ld_out + c, v.x, v.y, v.z, v.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// XLM-R embeddings + LayerNorm (one warp per token)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) text_embed_kernel(const int* __restrict__ ids, int S, int L, int Hd, int pad_idx, const float* __restrict__ word,
+                                                         const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ lnw,
+                                                         const float* __restrict__ lnb, float eps, float* out_f32, __nv_bfloat16* out_hi,
+                                                         __nv_bfloat16* out_lo) {
+    const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tok >= S * L) return;
+    const int lane = threadIdx.x & 31;
+    const int s = tok / L, l = tok % L;
+    const int id = ids[tok];
+    int pos_id = pad_idx;
+    if (id != pad_idx) {
+        int cnt = 0;
+        for (int j = 0; j <= l; ++j) cnt += (ids[s * L + j] != pad_idx) ? 1 : 0;
+        pos_id = cnt + pad_idx;
+    }
+    const float* wr = word + (long long)id * Hd;
+    const float* pr = pos + (long long)pos_id * Hd;
+    float4 v[8];  // Hd <= 1024
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < Hd) {
+            const float4 a = *reinterpret_cast<const float4*>(wr + c);
+            const float4 t = *reinterpret_cast<const float4*>(type + c);
+            const float4 p4 = *reinterpret_cast<const float4*>(pr + c);
+            // HF order: inputs_embeds + token_type_embeddings, then + position_embeddings
+            v[i] = make_float4((a.x + t.x) + p4.x, (a.y + t.y) + p4.y, (a.z + t.z) + p4.z, (a.w + t.w) + p4.w);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(sum) / (float)Hd;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < Hd) {
+            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + b * b) + (cc * cc + d * d);
+        }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)Hd + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < Hd) {
+            const float4 ww = *reinterpret_cast<const float4*>(lnw + c);
+            const float4 bb = *reinterpret_cast<const float4*>(lnb + c);
+            const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x, y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+            const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z, y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+            const long long idx = (long long)tok * Hd + c;
+            *reinterpret_cast<float4*>(out_f32 + idx) = make_float4(y0, y1, y2, y3);
+            store_bf16x4(out_hi, out_lo, idx, y0, y1, y2, y3);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// short-sequence attention: one warp per (sequence, head); L <= 32, head_dim == 64.
+// softmax(q k^T * scale + mask) v, masked keys get -inf (== HF additive float-min mask after softmax)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_small_kernel(const float* __restrict__ qkv, const int* __restrict__ mask, int S, int L, int heads, int ld,
+                                                         float scale, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * 4 + warp;
+    if (pair >= S * heads) return;
+    const int s = pair / heads, h = pair % heads;
+    const int Hd = heads * 64;
+    float* Q = sm + warp * (3 * L * 65);
+    float* K = Q + L * 65;
+    float* V = K + L * 65;
+    for (int t = lane; t < L * 64; t += 32) {
+        const int j = t >> 6, d = t & 63;
+        const float* row = qkv + (long long)(s * L + j) * ld + h * 64 + d;
+        Q[j * 65 + d] = row[0];
+        K[j * 65 + d] = row[Hd];
+        V[j * 65 + d] = row[2 * Hd];
+    }
+    __syncwarp();
+    const bool key_ok = lane < L && mask[s * L + (lane < L ? lane : 0)] != 0;
+    for (int i = 0; i < L; ++i) {
+        float sc = -INFINITY;
+        if (lane < L) {
+            float a = 0.f;
+#pragma unroll 16
+            for (int d = 0; d < 64; ++d) a = fmaf(Q[i * 65 + d], K[lane * 65 + d], a);
+            sc = key_ok ? a * scale : -INFINITY;
+        }
+        const float mx = warp_max(sc);
+        const float e = (lane < L && key_ok) ? expf(sc - mx) : 0.f;
+        const float den = warp_sum(e);
+        const float pj = e / den;
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float pp = __shfl_sync(0xffffffffu, pj, j);
+            o0 = fmaf(pp, V[j * 65 + lane], o0);
+            o1 = fmaf(pp, V[j * 65 + lane + 32], o1);
+        }
+        const long long idx = (long long)(s * L + i) * Hd + h * 64;
+        __nv_bfloat16 h0 = __float2bfloat16_rn(o0), h1 = __float2bfloat16_rn(o1);
+        out_hi[idx + lane] = h0;
+        out_hi[idx + lane + 32] = h1;
+        if (out_lo) {
+            out_lo[idx + lane] = __float2bfloat16_rn(o0 - __bfloat162float(h0));
+            out_lo[idx + lane + 32] = __float2bfloat16_rn(o1 - __bfloat162float(h1));
+        }
+    }
+}
+
+__global__ void l2norm_rows_kernel(const float* __restrict__ in, int S, int C, int ld_in, float* out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= S) return;
+    const int lane = threadIdx.x & 31;
+    float sq = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float v = in[(long long)row * ld_in + c];
+        sq += v * v;
+    }
+    const float nrm = fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
+    for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = in[(long long)row * ld_in + c] / nrm;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ in, int S, int C, int row_stride, int ld_in, __nv_bfloat16* out, __nv_bfloat16* out_lo) {
+    const int vec = C / 4;
+    const long long total = (long long)S * vec;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / vec;
+        const int c = (int)(t % vec) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(in + r * row_stride * ld_in + c);
+        store_bf16x4(out, out_lo, r * C + c, v.x, v.y, v.z, v.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fold BNContrastiveHead (+ optional L2-normalised text) into GEMM weights; one block per class k
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fold_text_kernel(const float* __restrict__ text, int K, int C, int normalize, const float* __restrict__ g,
+                                                        const float* __restrict__ hh, const float* __restrict__ logit_scale, const float* __restrict__ bias,
+                                                        __nv_bfloat16* W, __nv_bfloat16* W_lo, float* bprime) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int k = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k >= K) {  // zero padding rows
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            W[(long long)k * C + c] = __float2bfloat16_rn(0.f);
+            if (W_lo) W_lo[(long long)k * C + c] = __float2bfloat16_rn(0.f);
+        }
+        if (threadIdx.x == 0) bprime[k] = 0.f;
+        return;
+    }
+    const float* t = text + (long long)k * C;
+    float inv = 1.f;
+    if (normalize) {
+        float sq = 0.f;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) sq += t[c] * t[c];
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+            for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+            bc = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+        }
+        __syncthreads();
+        inv = bc;
+        __syncthreads();
+    }
+    const float es = expf(logit_scale[0]);
+    float dot = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float tn = t[c] * inv;
+        const float wv = tn * g[c] * es;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+        W[(long long)k * C + c] = hi;
+        if (W_lo) W_lo[(long long)k * C + c] = __float2bfloat16_rn(wv - __bfloat162float(hi));
+        dot += hh[c] * tn;
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+        bprime[k] = es * tot + bias[0];
+    }
+}
+
+// kept proposals -> BN'd embedding rows (generate_proposal.py:1129, 1209-1212)
+struct GatherEmbedArgs {
+    const __nv_bfloat16* emb[3];
+    const __nv_bfloat16* emb_lo[3];
+    int lvl_size[3];
+    int nlevels, B, C, max_keep;
+};
+__global__ void gather_embed_kernel(GatherEmbedArgs a, const int* __restrict__ keep_anchor, const int* __restrict__ counts, const float* __restrict__ g,
+                                    const float* __restrict__ hh, float* out) {
+    const int j = blockIdx.x, b = blockIdx.y;
+    float* o = out + ((long long)b * a.max_keep + j) * a.C;
+    if (j >= counts[b]) {
+        for (int c = threadIdx.x; c < a.C; c += blockDim.x) o[c] = 0.f;
+        return;
+    }
+    int anchor = keep_anchor[b * a.max_keep + j];
+    int lvl = 0;
+    while (lvl + 1 < a.nlevels && anchor >= a.lvl_size[lvl]) {
+        anchor -= a.lvl_size[lvl];
+        ++lvl;
+    }
+    const long long row = (long long)b * a.lvl_size[lvl] + anchor;
+    const __nv_bfloat16* e = a.emb[lvl] + row * a.C;
+    const __nv_bfloat16* el = a.emb_lo[lvl] ? a.emb_lo[lvl] + row * a.C : nullptr;
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        float v = __bfloat162float(e[c]);
+        if (el) v += __bfloat162float(el[c]);
+        o[c] = v * g[lvl * a.C + c] + hh[lvl * a.C + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: compile
+// ------------------------------------------------------------------------------------------------
+static int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 32;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
+    auto f = std::make_unique<FnOp>();
+    const int32_t* I = op.i;
+    void* const* P = op.p;
+    const float* F = op.f;
+    if (device_sm_count() <= 0) return -2;
+    switch (op.kind) {
+        case WD_OP_LN_ROWS: {
+            const int rows = I[0], C = I[1], s2d = I[4], W = I[5], H = I[6], ld_in = I[7], ld_out = I[8];
+            const float eps = F[0];
+            WD_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= kLnMaxVec * 128, "ln_rows: bad shape rows=%d C=%d", rows, C);
+            WD_REQUIRE(P[0] && P[2] && P[3] && (P[1] || P[6]), "ln_rows: null pointer");
+            WD_REQUIRE(!s2d || (W % 2 == 0 && H % 2 == 0 && rows % (W * H) == 0 && P[1]), "ln_rows: bad s2d geometry");
+            WD_REQUIRE(ld_in % 4 == 0 && ld_out % 4 == 0, "ln_rows: ld must be a multiple of 4");
+            const float* in = (const float*)P[0];
+            const float *w = (const float*)P[2], *b = (const float*)P[3];
+            __nv_bfloat16 *oh = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[5];
+            float* of = (float*)P[6];
+            f->fn = [=](cudaStream_t s) {
+                ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_DWCONV_LN: {
+            const int B = I[0], H = I[1], W = I[2], C = I[3];
+            const float eps = F[0];
+            WD_REQUIRE(B > 0 && H > 0 && W > 0 && C % 4 == 0 && C / 4 <= 384, "dwconv_ln: bad shape");
+            WD_REQUIRE(P[0] && P[1] && P[2] && P[3] && P[4] && P[5], "dwconv_ln: null pointer");
+            const float* in = (const float*)P[0];
+            __nv_bfloat16 *oh = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[6];
+            const float *wt = (const float*)P[2], *bs = (const float*)P[3], *lw = (const float*)P[4], *lb = (const float*)P[5];
+            const int threads = ((C / 4 + 31) / 32) * 32;
+            f->fn = [=](cudaStream_t s) {
+                dim3 grid((W + kDwTX - 1) / kDwTX, (H + kDwTY - 1) / kDwTY, B);
+                dwconv7_ln_kernel<<<grid, threads, 0, s>>>(in, B, H, W, C, wt, bs, lw, lb, eps, oh, ol);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_STEM_PATCH: {
+            const int B = I[0], H = I[1], W = I[2], dt = I[3], layout = I[4];
+            const float scale = F[0];
+            WD_REQUIRE(B > 0 && H % 4 == 0 && W % 4 == 0 && layout == 0 && (dt == 0 || dt == 2), "stem_patch: bad arguments");
+            WD_REQUIRE(P[0] && P[1], "stem_patch: null pointer");
+            const void* in = P[0];
+            __nv_bfloat16 *oh = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[2];
+            const long long total = (long long)B * (H / 4) * (W / 4) * 16;
+            f->fn = [=](cudaStream_t s) {
+                if (dt == 0) stem_patch_kernel<uint8_t><<<grid_for(total, 256), 256, 0, s>>>((const uint8_t*)in, B, H, W, scale, oh, ol);
+                else stem_patch_kernel<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)in, B, H, W, scale, oh, ol);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_IM2COL_S2: {
+            const int B = I[0], H = I[1], W = I[2], C = I[3], ld_in = I[4];
+            WD_REQUIRE(B > 0 && H > 0 && W > 0 && C % 8 == 0 && ld_in % 8 == 0 && P[0] && P[1], "im2col_s2: bad arguments");
+            const __nv_bfloat16 *in = (const __nv_bfloat16*)P[0], *inl = (const __nv_bfloat16*)P[2];
+            __nv_bfloat16 *o = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[3];
+            const long long total = (long long)B * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * 9 * (C / 8);
+            f->fn = [=](cudaStream_t s) {
+                im2col_s2_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, inl, B, H, W, C, ld_in, o, ol);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_CAST_BF16: {
+            const int rows = I[0], C = I[1], ld_in = I[2], ld_out = I[3];
+            WD_REQUIRE(rows > 0 && C % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && P[0] && P[1], "cast_bf16: bad arguments");
+            const float* in = (const float*)P[0];
+            __nv_bfloat16 *o = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[2];
+            f->fn = [=](cudaStream_t s) {
+                cast_bf16_kernel<<<grid_for((long long)rows * (C / 4), 256), 256, 0, s>>>(in, rows, C, ld_in, ld_out, o, ol);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_TEXT_EMBED: {
+            const int S = I[0], L = I[1], Hd = I[2], pad_idx = I[3];
+            const float eps = F[0];
+            WD_REQUIRE(S > 0 && L > 0 && Hd % 4 == 0 && Hd <= 1024, "text_embed: bad shape");
+            for (int k = 0; k <= 8; ++k) WD_REQUIRE(k == 1 || P[k], "text_embed: null pointer %d", k);
+            const int* ids = (const int*)P[0];
+            const float *word = (const float*)P[2], *pos = (const float*)P[3], *type = (const float*)P[4], *lw = (const float*)P[5], *lb = (const float*)P[6];
+            float* of = (float*)P[7];
+            __nv_bfloat16 *oh = (__nv_bfloat16*)P[8], *ol = (__nv_bfloat16*)P[9];
+            f->fn = [=](cudaStream_t s) {
+                text_embed_kernel<<<(S * L + 7) / 8, 256, 0, s>>>(ids, S, L, Hd, pad_idx, word, pos, type, lw, lb, eps, of, oh, ol);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_ATTN_SMALL: {
+            const int S = I[0], L = I[1], heads = I[2], hd = I[3], ld = I[4];
+            const float scale = F[0];
+            WD_REQUIRE(S > 0 && L > 0 && L <= 32 && hd == 64 && heads > 0 && P[0] && P[1] && P[2], "attn_small: needs L <= 32 and head_dim == 64");
+            const float* qkv = (const float*)P[0];
+            const int* mask = (const int*)P[1];
+            __nv_bfloat16 *oh = (__nv_bfloat16*)P[2], *ol = (__nv_bfloat16*)P[3];
+            const int smem = 4 * 3 * L * 65 * (int)sizeof(float);
+            f->fn = [=](cudaStream_t s) {
+                static bool attr = false;
+                if (!attr) {
+                    WD_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * 32 * 65 * 4));
+                    attr = true;
+                }
+                attn_small_kernel<<<(S * heads + 3) / 4, 128, smem, s>>>(qkv, mask, S, L, heads, ld, scale, oh, ol);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_L2NORM_ROWS: {
+            const int S = I[0], C = I[1], ld_in = I[2];
+            WD_REQUIRE(S > 0 && C > 0 && P[0] && P[1], "l2norm_rows: bad arguments");
+            const float* in = (const float*)P[0];
+            float* o = (float*)P[1];
+            f->fn = [=](cudaStream_t s) {
+                l2norm_rows_kernel<<<(S + 7) / 8, 256, 0, s>>>(in, S, C, ld_in, o);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_GATHER_ROWS: {
+            const int S = I[0], C = I[1], rs = I[2], ld_in = I[3];
+            WD_REQUIRE(S > 0 && C % 4 == 0 && ld_in % 4 == 0 && P[0] && P[1], "gather_rows: bad arguments");
+            const float* in = (const float*)P[0];
+            __nv_bfloat16 *o = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[2];
+            f->fn = [=](cudaStream_t s) {
+                gather_rows_kernel<<<grid_for((long long)S * (C / 4), 256), 256, 0, s>>>(in, S, C, rs, ld_in, o, ol);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_FOLD_TEXT: {
+            const int K = I[0], C = I[1], normalize = I[2], Kpad = I[3];
+            WD_REQUIRE(K > 0 && C > 0 && Kpad >= K, "fold_text: bad shape");
+            for (int k = 0; k <= 6; ++k) WD_REQUIRE(P[k], "fold_text: null pointer %d", k);
+            const float *t = (const float*)P[0], *g = (const float*)P[1], *hh = (const float*)P[2], *ls = (const float*)P[3], *bi = (const float*)P[4];
+            __nv_bfloat16 *Wd = (__nv_bfloat16*)P[5], *Wl = (__nv_bfloat16*)P[7];
+            float* bp = (float*)P[6];
+            f->fn = [=](cudaStream_t s) {
+                fold_text_kernel<<<Kpad, 256, 0, s>>>(t, K, C, normalize, g, hh, ls, bi, Wd, Wl, bp);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_GATHER_EMBED: {
+            GatherEmbedArgs a;
+            a.B = I[0]; a.C = I[2]; a.max_keep = I[3]; a.nlevels = I[4];
+            WD_REQUIRE(a.B > 0 && a.C > 0 && a.max_keep > 0 && a.nlevels >= 1 && a.nlevels <= 3, "gather_embed: bad shape");
+            for (int l = 0; l < 3; ++l) {
+                a.lvl_size[l] = I[5 + l];
+                a.emb[l] = (const __nv_bfloat16*)P[l];
+                a.emb_lo[l] = (const __nv_bfloat16*)P[8 + l];
+            }
+            WD_REQUIRE(P[0] && P[3] && P[4] && P[5] && P[6] && P[7], "gather_embed: null pointer");
+            const int* ka = (const int*)P[3];
+            const int* cnt = (const int*)P[4];
+            const float *g = (const float*)P[5], *hh = (const float*)P[6];
+            float* o = (float*)P[7];
+            f->fn = [=](cudaStream_t s) {
+                gather_embed_kernel<<<dim3(a.max_keep, a.B), 128, 0, s>>>(a, ka, cnt, g, hh, o);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        default: set_last_error("rowops: unknown kind %d", op.kind); return -1;
+    }
+    out = std::move(f);
+    return 0;
+}
+
+}  // namespace wd
