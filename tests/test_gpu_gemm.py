@@ -1,0 +1,165 @@
+"""GPU parity of the tcgen05 GEMM / implicit-conv op (through the C ABI) vs the fp32 torch reference."""
+import pytest
+import torch
+
+import ref_ops as R
+from util import report_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _run(op_or_ops):
+    from wedetect_b200 import _lib as L
+    ops_ = op_or_ops if isinstance(op_or_ops, (list, tuple)) else [op_or_ops]
+    for op in ops_:
+        L.run_op(op, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+
+
+def _rand_bf16(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,K,N,block_n", [
+    (128, 64, 64, 64),       # single tile, single k-iteration
+    (256, 128, 128, 128),
+    (1000, 512, 384, None),  # M tail, 3 n-tiles of 128
+    (300, 192, 80, None),    # N not a multiple of the chunk/tile (80), K = 3 iterations
+    (128 * 400, 128, 512, 256),  # many tiles per CTA: barrier phases wrap, TMEM double buffering
+    (640, 2048, 256, 256),   # long K loop
+])
+def test_linear_plain(M, K, N, block_n):
+    from wedetect_b200 import ops
+    A, W = _rand_bf16(M, K, seed=1), _rand_bf16(N, K, seed=2, scale=0.05)
+    C = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=_dev())
+    _run(ops.linear(A.to(_dev()), W.to(_dev()), C, block_n=block_n))
+    ref = R.linear_ref(A, W)
+    report_close(f"linear {M}x{K}x{N}", C, ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_linear_epilogue_f32(act):
+    from wedetect_b200 import ops
+    M, K, N = 777, 256, 256
+    A, W = _rand_bf16(M, K, seed=3), _rand_bf16(N, K, seed=4, scale=0.06)
+    g = torch.Generator().manual_seed(5)
+    bias, gamma = torch.randn(N, generator=g), torch.rand(N, generator=g) + 0.5
+    resid = torch.randn(M, N, generator=g)
+    C = torch.zeros(M, N, dtype=torch.float32, device=_dev())
+    d = _dev()
+    _run(ops.linear(A.to(d), W.to(d), C, bias=bias.to(d), gamma=gamma.to(d), resid=resid.to(d), alpha=0.75, act=act))
+    ref = R.linear_ref(A, W, bias=bias, act=act, gamma=gamma, resid=resid, alpha=0.75)
+    report_close(f"linear epilogue act={act}", C, ref, rtol=1e-4, atol=2e-4)
+
+
+def test_linear_inplace_residual_f32():
+    """ConvNeXt pwconv2: out = x + gamma * (h @ W^T + b), written in place over x."""
+    from wedetect_b200 import ops
+    M, K, N = 1500, 512, 128
+    A, W = _rand_bf16(M, K, seed=6), _rand_bf16(N, K, seed=7, scale=0.04)
+    g = torch.Generator().manual_seed(8)
+    bias, gamma = torch.randn(N, generator=g), torch.rand(N, generator=g) * 0.45 + 0.05
+    x = torch.randn(M, N, generator=g)
+    d = _dev()
+    xd = x.to(d)
+    _run(ops.linear(A.to(d), W.to(d), xd, bias=bias.to(d), gamma=gamma.to(d), resid=xd, alpha=1.0))
+    ref = R.linear_ref(A, W, bias=bias, gamma=gamma, resid=x, alpha=1.0)
+    report_close("linear in-place residual", xd, ref, rtol=1e-4, atol=2e-4)
+
+
+def test_linear_slice_output_bf16_resid():
+    """Output into a channel slice of a wider buffer (concat fusion) + bf16 residual."""
+    from wedetect_b200 import ops
+    M, K, N = 900, 128, 128
+    A, W = _rand_bf16(M, K, seed=9), _rand_bf16(N, K, seed=10, scale=0.08)
+    resid = _rand_bf16(M, N, seed=11)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(12))
+    d = _dev()
+    buf = torch.full((M, 384), 3.0, dtype=torch.bfloat16, device=d)
+    C = buf[:, 128:256]
+    _run(ops.linear(A.to(d), W.to(d), C, bias=bias.to(d), resid=resid.to(d), alpha=1.25, act=2))
+    ref = R.linear_ref(A, W, bias=bias, act=2, resid=resid, alpha=1.25)
+    report_close("linear slice", C, ref, rtol=1e-2, atol=1e-2)
+    assert float((buf[:, :128].float() - 3).abs().max()) == 0 and float((buf[:, 256:].float() - 3).abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 20, 20, 64, 64), (3, 40, 40, 128, 128), (1, 80, 80, 64, 256), (5, 25, 25, 64, 64)])
+def test_conv3x3(B, H, W, Cin, N):
+    from wedetect_b200 import ops
+    A, Wt = _rand_bf16(B, H, W, Cin, seed=13), _rand_bf16(N, 9 * Cin, seed=14, scale=0.04)
+    g = torch.Generator().manual_seed(15)
+    bias = torch.randn(N, generator=g)
+    resid = _rand_bf16(B, H, W, N, seed=16) if Cin == N else None
+    d = _dev()
+    C = torch.zeros(B, H, W, N, dtype=torch.bfloat16, device=d)
+    _run(ops.conv3x3(A.to(d), Wt.to(d), C, bias=bias.to(d), act=2, resid=None if resid is None else resid.to(d), alpha=0.9))
+    ref = R.conv3x3_ref(A, Wt, bias=bias, act=2, resid=resid, alpha=0.9)
+    report_close(f"conv3x3 {B}x{H}x{W}x{Cin}->{N}", C.reshape(-1, N), ref.reshape(-1, N), rtol=1e-2, atol=1e-2)
+
+
+def test_deconv2x2_into_slice():
+    from wedetect_b200 import ops
+    B, H, W, Cin, Co = 2, 20, 20, 128, 128
+    A, Wt = _rand_bf16(B, H, W, Cin, seed=17), _rand_bf16(4 * Co, Cin, seed=18, scale=0.06)
+    bias = torch.randn(Co, generator=torch.Generator().manual_seed(19))
+    d = _dev()
+    buf = torch.full((B, 2 * H, 2 * W, 3 * Co), 5.0, dtype=torch.bfloat16, device=d)
+    C = buf[..., :Co]
+    _run(ops.deconv2x2(A.to(d), Wt.to(d), C, torch.cat([bias, bias]).to(d)))
+    ref = R.deconv2x2_ref(A, Wt, bias)
+    report_close("deconv2x2", C.reshape(-1, Co), ref.reshape(-1, Co), rtol=1e-2, atol=1e-2)
+    assert float((buf[..., Co:].float() - 5).abs().max()) == 0
+
+
+def test_dfl_epilogue():
+    from wedetect_b200 import ops
+    M, K = 1111, 64
+    A, Wt = _rand_bf16(M, K, seed=20), _rand_bf16(64, K, seed=21, scale=0.3)
+    bias = torch.randn(64, generator=torch.Generator().manual_seed(22))
+    d = _dev()
+    C = torch.zeros(M, 4, dtype=torch.float32, device=d)
+    _run(ops.linear(A.to(d), Wt.to(d), C, bias=bias.to(d), dfl=True))
+    report_close("dfl", C, R.dfl_ref(A, Wt, bias), rtol=1e-4, atol=1e-4)
+
+
+def test_linear_split_precise():
+    """bf16x3 split mode reproduces an fp32 GEMM to ~1e-5 relative."""
+    from wedetect_b200 import ops
+    M, K, N = 515, 256, 192
+    g = torch.Generator().manual_seed(23)
+    A, Wt = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    bias = torch.randn(N, generator=g)
+    Ah, Al = R.split_hi_lo(A)
+    Wh, Wl = R.split_hi_lo(Wt)
+    d = _dev()
+    C = torch.zeros(M, N, dtype=torch.float32, device=d)
+    _run(ops.linear(Ah.to(d), Wh.to(d), C, bias=bias.to(d), act=3, A_lo=Al.to(d), W_lo=Wl.to(d)))
+    ref = R.act_ref(A.double() @ Wt.double().t() + bias.double(), 3).float()
+    report_close("linear split f32", C, ref, rtol=2e-5, atol=2e-5)
+    # bf16 hi/lo outputs
+    Ch = torch.zeros(M, N, dtype=torch.bfloat16, device=d)
+    Cl = torch.zeros(M, N, dtype=torch.bfloat16, device=d)
+    _run(ops.linear(Ah.to(d), Wh.to(d), Ch, bias=bias.to(d), act=2, A_lo=Al.to(d), W_lo=Wl.to(d), C_lo=Cl))
+    ref2 = R.act_ref(A.double() @ Wt.double().t() + bias.double(), 2).float()
+    report_close("linear split hi+lo", Ch.float() + Cl.float(), ref2, rtol=3e-5, atol=3e-5)
+
+
+def test_conv3x3_split_precise():
+    from wedetect_b200 import ops
+    B, H, W, Cin, N = 2, 20, 20, 64, 128
+    g = torch.Generator().manual_seed(24)
+    A, Wt = torch.randn(B, H, W, Cin, generator=g), torch.randn(N, 9 * Cin, generator=g) * 0.04
+    Ah, Al = R.split_hi_lo(A)
+    Wh, Wl = R.split_hi_lo(Wt)
+    d = _dev()
+    Ch = torch.zeros(B, H, W, N, dtype=torch.bfloat16, device=d)
+    Cl = torch.zeros_like(Ch)
+    _run(ops.conv3x3(Ah.to(d), Wh.to(d), Ch, A_lo=Al.to(d), W_lo=Wl.to(d), C_lo=Cl))
+    w = Wt.view(N, 3, 3, Cin).permute(0, 3, 1, 2).double()
+    ref = torch.nn.functional.conv2d(A.permute(0, 3, 1, 2).double(), w, padding=1).permute(0, 2, 3, 1).float()
+    report_close("conv3x3 split", (Ch.float() + Cl.float()).reshape(-1, N), ref.reshape(-1, N), rtol=3e-5, atol=3e-5)

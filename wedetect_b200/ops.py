@@ -1,0 +1,329 @@
+"""Builders that turn torch tensor *views* into `wd_op` records for the C ABI.
+
+torch is used only for device memory (data_ptr / strides); nothing here computes.
+All activations are NHWC: a feature map is a view [B, H, W, C] whose last stride is 1, a matrix is
+[rows, cols].  Channel slices of a wider buffer (concat fusion) are plain views.
+"""
+import functools
+
+import torch
+
+from . import _lib as L
+from ._lib import WdOp
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise ValueError(f"{name}: innermost stride must be 1")
+
+
+@functools.lru_cache(maxsize=None)
+def pick_tile(W, H, B):
+    """(E0,E1,E2) brick of <= 128 pixels minimising wasted MMA rows; ties -> wider E0 (longer TMA runs)."""
+    best = None
+    for e0 in range(1, min(W, 128) + 1):
+        for e1 in range(1, min(H, 128 // e0) + 1):
+            e2 = max(1, min(B, 128 // (e0 * e1)))
+            tiles = -(-W // e0) * -(-H // e1) * -(-B // e2)
+            key = (tiles, -e0, -e1)
+            if best is None or key < best[0]:
+                best = (key, (e0, e1, e2))
+    return best[1]
+
+
+def pick_block_n(N, out_f32=False, split=False):
+    """Tile width minimising padded columns, weighted by the relative MMA efficiency of each width."""
+    cands = ((128, 1.15), (64, 1.5)) if split else ((256, 1.0), (128, 1.15), (64, 1.5))
+    best = None
+    for bn, pen in cands:
+        cost = -(-N // bn) * bn * pen
+        if best is None or cost < best[0]:
+            best = (cost, bn)
+    return best[1]
+
+
+def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, block_n=None, out_f32=False,
+             act=L.ACT_NONE, bias=None, gamma=None, resid=None, ld_res=0, alpha=1.0, group_cols=None, n_groups=1,
+             c_gstride=0, dfl=False, A_lo=None, W_lo=None, C_lo=None, resid_lo=None):
+    op = WdOp()
+    op.kind = L.OP_GEMM
+    split = A_lo is not None and W_lo is not None
+    if block_n is None:
+        block_n = 64 if dfl else pick_block_n(N, out_f32, split)
+    I = op.i
+    I[0], I[1], I[2] = dims
+    I[3], I[4], I[5] = tile
+    I[6], I[7], I[8] = Kc, ntaps, N
+    I[9], I[10], I[11] = a_strides
+    I[12], I[13], I[14], I[15] = ldb, block_n, 1 if out_f32 else 0, act
+    if resid is not None:
+        I[16] = 2 if resid.dtype == torch.float32 else 1
+        I[17] = ld_res
+    I[18] = group_cols if group_cols is not None else N
+    I[19] = n_groups
+    I[20], I[21], I[22] = c_strides
+    I[23] = c_gstride
+    I[24] = 1 if dfl else 0
+    I[25], I[26] = (3, 1) if ntaps == 9 else (1, 0)
+    op.f[0] = alpha
+    for k, t in enumerate((A, W, C, bias, gamma, resid, A_lo, W_lo, C_lo, resid_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def _flat_strides(ld, rows):
+    big = max(8, ((ld * max(rows, 1) + 7) // 8) * 8)
+    return (ld, big, big)
+
+
+def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, dfl=False,
+           A_lo=None, W_lo=None, C_lo=None, resid_lo=None):
+    """C[M, N] = epi(A[M, K] @ W[N, K]^T); A / C / resid may be column slices of wider row-major buffers."""
+    _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and K % 64 == 0, (W.shape, K)
+    out_f32 = C.dtype == torch.float32
+    if dfl:
+        assert C.shape == (M, 4) and C.is_contiguous() and out_f32
+        c_str = (4, 8, 8)
+    else:
+        assert C.shape[0] == M and C.shape[1] == N and C.stride(1) == 1, (C.shape, M, N)
+        c_str = _flat_strides(C.stride(0), M)
+    ld_res = 0
+    if resid is not None:
+        assert resid.shape == (M, N) and resid.stride(1) == 1
+        ld_res = resid.stride(0)
+    return gemm_raw(A=A, W=W, C=C, dims=(M, 1, 1), tile=(128, 1, 1), Kc=K, N=N, a_strides=_flat_strides(A.stride(0), M),
+                    ldb=W.stride(0), c_strides=c_str, block_n=block_n, out_f32=out_f32, act=act, bias=bias, gamma=gamma,
+                    resid=resid, ld_res=ld_res, alpha=alpha, dfl=dfl, A_lo=A_lo, W_lo=W_lo, C_lo=C_lo, resid_lo=resid_lo)
+
+
+def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, A_lo=None, W_lo=None,
+            C_lo=None, resid_lo=None):
+    """3x3 stride-1 pad-1 convolution as 9 shifted TMA brick loads.  A [B,H,W,Cin], W [N, 9*Cin] (tap-major)."""
+    _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
+    B, H, Wd, Cin = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == 9 * Cin and Cin % 64 == 0
+    assert C.shape == (B, H, Wd, N) and C.stride(3) == 1
+    ld_res = 0
+    if resid is not None:
+        assert resid.shape == (B, H, Wd, N) and resid.stride(3) == 1
+        ld_res = resid.stride(2)
+        assert resid.stride(1) == Wd * ld_res and resid.stride(0) == H * Wd * ld_res
+    return gemm_raw(A=A, W=W, C=C, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Cin, ntaps=9, N=N,
+                    a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
+                    c_strides=(C.stride(2), C.stride(1), C.stride(0)), block_n=block_n, out_f32=C.dtype == torch.float32,
+                    act=act, bias=bias, resid=resid, ld_res=ld_res, alpha=alpha, A_lo=A_lo, W_lo=W_lo, C_lo=C_lo,
+                    resid_lo=resid_lo)
+
+
+def deconv2x2(A, W, C, bias2, *, A_lo=None, W_lo=None, C_lo=None):
+    """ConvTranspose2d(k=2, s=2) as two GEMMs (dy = 0, 1) whose TMA stores scatter into the 2x upsampled map.
+    A [B,H,W,Cin]; W [4*Co, Cin] rows ordered (dy, dx, co); C [B,2H,2W,Co] (may be a channel slice);
+    bias2 f32 [2*Co] = bias repeated for dx = 0, 1."""
+    _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
+    B, H, Wd, Cin = A.shape
+    Co = W.shape[0] // 4
+    assert C.shape == (B, 2 * H, 2 * Wd, Co) and Co % 64 == 0 and Cin % 64 == 0
+    ops = []
+    for dy in range(2):
+        Wdy = W[dy * 2 * Co:(dy + 1) * 2 * Co]
+        Cdy = C[:, dy]
+        ops.append(gemm_raw(A=A, W=Wdy, C=Cdy, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Cin, N=2 * Co,
+                            a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
+                            c_strides=(2 * C.stride(2), 2 * C.stride(1), C.stride(0)), group_cols=Co, n_groups=2,
+                            c_gstride=C.stride(2), bias=bias2, out_f32=False,
+                            A_lo=A_lo, W_lo=None if W_lo is None else W_lo[dy * 2 * Co:(dy + 1) * 2 * Co],
+                            C_lo=None if C_lo is None else C_lo[:, dy]))
+    return ops
+
+
+def ln_rows(x, w, b, eps, *, out_bf16=None, out_lo=None, out_f32=None, s2d_hw=None):
+    _chk(x, torch.float32, "x")
+    rows, C = x.shape
+    op = WdOp()
+    op.kind = L.OP_LN_ROWS
+    op.i[0], op.i[1] = rows, C
+    op.i[7] = x.stride(0)
+    if s2d_hw is not None:
+        H, W = s2d_hw
+        op.i[4], op.i[5], op.i[6] = 1, W, H
+        assert out_bf16 is not None and out_bf16.shape == (rows // 4, 4 * C)
+    op.i[8] = out_bf16.stride(0) if out_bf16 is not None else C
+    op.f[0] = eps
+    if out_f32 is not None:
+        assert out_f32.is_contiguous() and out_f32.shape == (rows, C)
+    for k, t in ((0, x), (1, out_bf16), (2, w), (3, b), (5, out_lo), (6, out_f32)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def dwconv_ln(x, out, w49, bias, ln_w, ln_b, eps, out_lo=None):
+    _chk(x, torch.float32, "x")
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel() and w49.shape == (49, C)
+    op = WdOp()
+    op.kind = L.OP_DWCONV_LN
+    op.i[0], op.i[1], op.i[2], op.i[3] = B, H, W, C
+    op.f[0] = eps
+    for k, t in enumerate((x, out, w49, bias, ln_w, ln_b, out_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def stem_patch(img, out, scale=1.0, out_lo=None):
+    B, C3, H, W = img.shape
+    assert C3 == 3 and img.is_contiguous() and out.shape == (B * (H // 4) * (W // 4), 64) and out.is_contiguous()
+    op = WdOp()
+    op.kind = L.OP_STEM_PATCH
+    op.i[0], op.i[1], op.i[2] = B, H, W
+    op.i[3] = 0 if img.dtype == torch.uint8 else 2
+    assert img.dtype in (torch.uint8, torch.float32)
+    op.f[0] = scale
+    for k, t in enumerate((img, out, out_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def im2col_s2(x, out, x_lo=None, out_lo=None):
+    _chk(x, torch.bfloat16, "x")
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    assert out.shape == (B * Ho * Wo, 9 * C) and out.is_contiguous()
+    assert x.stride(1) == W * x.stride(2) and x.stride(0) == H * W * x.stride(2)
+    op = WdOp()
+    op.kind = L.OP_IM2COL_S2
+    op.i[0], op.i[1], op.i[2], op.i[3], op.i[4] = B, H, W, C, x.stride(2)
+    for k, t in enumerate((x, out, x_lo, out_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def cast_bf16(x, out, out_lo=None):
+    _chk(x, torch.float32, "x")
+    rows, C = x.shape
+    op = WdOp()
+    op.kind = L.OP_CAST_BF16
+    op.i[0], op.i[1], op.i[2], op.i[3] = rows, C, x.stride(0), out.stride(0)
+    for k, t in enumerate((x, out, out_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def text_embed(ids, word, pos, typ, ln_w, ln_b, eps, pad_idx, out_f32, out_bf16, out_lo=None):
+    S, Lt = ids.shape
+    assert ids.dtype == torch.int32 and ids.is_contiguous()
+    Hd = word.shape[1]
+    op = WdOp()
+    op.kind = L.OP_TEXT_EMBED
+    op.i[0], op.i[1], op.i[2], op.i[3] = S, Lt, Hd, pad_idx
+    op.f[0] = eps
+    for k, t in ((0, ids), (2, word), (3, pos), (4, typ), (5, ln_w), (6, ln_b), (7, out_f32), (8, out_bf16), (9, out_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def attn_small(qkv, mask, out, heads, scale, out_lo=None):
+    S, Lt = mask.shape
+    assert mask.dtype == torch.int32 and qkv.dtype == torch.float32 and qkv.is_contiguous()
+    op = WdOp()
+    op.kind = L.OP_ATTN_SMALL
+    op.i[0], op.i[1], op.i[2], op.i[3], op.i[4] = S, Lt, heads, 64, qkv.shape[1]
+    op.f[0] = scale
+    for k, t in enumerate((qkv, mask, out, out_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def l2norm_rows(x, out):
+    op = WdOp()
+    op.kind = L.OP_L2NORM_ROWS
+    op.i[0], op.i[1], op.i[2] = x.shape[0], x.shape[1], x.stride(0)
+    op.p[0], op.p[1] = _ptr(x), _ptr(out)
+    return op
+
+
+def gather_rows(x, out, S, row_stride, out_lo=None):
+    op = WdOp()
+    op.kind = L.OP_GATHER_ROWS
+    op.i[0], op.i[1], op.i[2], op.i[3] = S, x.shape[1], row_stride, x.stride(0)
+    for k, t in enumerate((x, out, out_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def fold_text(text, bn_g, bn_h, logit_scale, bias, Wout, bout, normalize, Wout_lo=None):
+    K, C = text.shape
+    assert text.dtype == torch.float32 and text.is_contiguous() and Wout.shape[1] == C and Wout.is_contiguous()
+    op = WdOp()
+    op.kind = L.OP_FOLD_TEXT
+    op.i[0], op.i[1], op.i[2], op.i[3] = K, C, 1 if normalize else 0, Wout.shape[0]
+    for k, t in enumerate((text, bn_g, bn_h, logit_scale, bias, Wout, bout, Wout_lo)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def gather_embed(embeds, keep_anchor, counts, bn_g, bn_h, out, embeds_lo=None):
+    B, max_keep, C = out.shape
+    op = WdOp()
+    op.kind = L.OP_GATHER_EMBED
+    op.i[0], op.i[2], op.i[3], op.i[4] = B, C, max_keep, len(embeds)
+    for l, e in enumerate(embeds):
+        op.i[5 + l] = e.shape[0] // B
+        op.p[l] = _ptr(e)
+        if embeds_lo is not None:
+            op.p[8 + l] = _ptr(embeds_lo[l])
+    for k, t in ((3, keep_anchor), (4, counts), (5, bn_g), (6, bn_h), (7, out)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+class PostProcess:
+    """Owns the wd_pp_params struct + workspace and produces the WD_OP_POSTPROCESS record."""
+
+    def __init__(self, *, logits, dists, level_hw, strides, K, B, score_thr, nms_pre, iou_thr, max_per_img, nms_mode,
+                 img_meta, clamp_wh, tv_numel_thr=20000, multi_label=True):
+        import ctypes
+        dev = logits[0].device
+        A = sum(h * w for h, w in level_hw)
+        self.B, self.K, self.A, self.max_per_img = B, K, A, max_per_img
+        lib = L.load(require_gpu=False)
+        nbytes = int(lib.wd_pp_workspace_bytes(B, A, K, nms_pre))
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-self.workspace.data_ptr()) % 256
+        self.boxes = torch.empty(B, max_per_img, 4, dtype=torch.float32, device=dev)
+        self.scores = torch.empty(B, max_per_img, dtype=torch.float32, device=dev)
+        self.labels = torch.empty(B, max_per_img, dtype=torch.int32, device=dev)
+        self.anchors = torch.empty(B, max_per_img, dtype=torch.int32, device=dev)
+        self.counts = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.img_meta, self.clamp_wh = img_meta, clamp_wh
+        assert img_meta.shape == (B, 8) and img_meta.dtype == torch.float32 and clamp_wh.shape == (B, 2)
+        p = L.PPParams()
+        p.B, p.K, p.nlevels = B, K, len(logits)
+        for l, ((h, w), s) in enumerate(zip(level_hw, strides)):
+            p.lvl_h[l], p.lvl_w[l], p.lvl_stride[l] = h, w, s
+            assert logits[l].dtype == torch.float32 and logits[l].shape[0] == B * h * w and logits[l].stride(1) == 1
+            assert dists[l].shape == (B * h * w, 4) and dists[l].is_contiguous() and dists[l].dtype == torch.float32
+            p.ld_logit[l] = logits[l].stride(0)
+            p.logits[l] = logits[l].data_ptr()
+            p.dist[l] = dists[l].data_ptr()
+        p.score_thr, p.nms_pre, p.iou_thr, p.max_per_img = score_thr, nms_pre, iou_thr, max_per_img
+        p.nms_mode, p.tv_numel_thr, p.multi_label = nms_mode, tv_numel_thr, 1 if multi_label else 0
+        p.img_meta, p.clamp_wh = img_meta.data_ptr(), clamp_wh.data_ptr()
+        p.out_boxes, p.out_scores = self.boxes.data_ptr(), self.scores.data_ptr()
+        p.out_labels, p.out_anchor, p.out_counts = self.labels.data_ptr(), self.anchors.data_ptr(), self.counts.data_ptr()
+        p.workspace, p.workspace_bytes = self.workspace.data_ptr() + off, nbytes
+        self.params = p
+        self._keep = (logits, dists)
+        op = WdOp()
+        op.kind = L.OP_POSTPROCESS
+        op.p[0] = ctypes.addressof(p)
+        self.op = op
