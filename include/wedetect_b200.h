@@ -49,7 +49,9 @@ enum wd_op_kind {
      *    12 ldb  13 block_n (64|128|256)  14 out_dtype (0 bf16, 1 f32)  15 act (wd_act)
      *    16 resid_dtype (0 none, 1 bf16, 2 f32)  17 ld_res  18 group_cols  19 n_groups
      *    20..22 C strides of d0,d1,d2 (elements)  23 C stride of group  24 epi_mode (0 store, 1 DFL)
-     *    25 tap_w (3 for 3x3)  26 pad (1 for 3x3)
+     *    25 tap_w (3 for 3x3)  26 pad (1 for 3x3)  27 group_valid (columns of a group present in memory, 0 = group_cols)
+     *    28 K_valid (channels of A present in memory, 0 = Kc; TMA zero-fills up to Kc)
+     *    29 BK_valid (columns of B present in memory, 0 = ntaps*Kc)
      * f: 0 resid_alpha
      * p: 0 A (bf16)  1 B (bf16 [N, ntaps*Kc])  2 C  3 bias f32[N]  4 gamma f32[N]  5 resid
      *    6 A_lo  7 B_lo  8 C_lo   (bf16x3 "split" precise mode; null in fast mode)
@@ -63,8 +65,8 @@ enum wd_op_kind {
     WD_OP_LN_ROWS = 2,
     /* Depthwise 7x7 (pad 3) + bias + LayerNorm(C) on an NHWC fp32 tensor -> bf16 rows.
      * mm_backbone.py:114-116 (Block.forward dwconv/permute/norm).
-     * i: 0 B 1 H 2 W 3 C   f: 0 eps
-     * p: 0 in f32 [B,H,W,C]  1 out bf16 [B*H*W,C]  2 w f32[49,C]  3 b f32[C]  4 ln_w  5 ln_b  6 out_lo */
+     * i: 0 B 1 H 2 W 3 C 4 ld_out (0 = C)   f: 0 eps
+     * p: 0 in f32 [B,H,W,C]  1 out bf16 [B*H*W,ld_out]  2 w f32[49,C]  3 b f32[C]  4 ln_w  5 ln_b  6 out_lo */
     WD_OP_DWCONV_LN = 3,
     /* Stem patchify: image -> bf16 rows [B*(H/4)*(W/4), 64] (48 valid = (dy,dx,c), rest 0).
      * mm_backbone.py:188-191 (Conv2d k4 s4 input gather); data_preprocessor.py:35-36 (mean/std are

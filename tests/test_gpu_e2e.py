@@ -1,0 +1,131 @@
+"""End-to-end GPU parity: the lowered program (C ABI) vs the CPU fp32 oracle, stage by stage.
+
+precise (bf16x3) mode carries the north-star gates: |logit error| <= 1e-3 and IDENTICAL kept
+(anchor, class) indices; fast (bf16) mode is held to measured engineering tolerances.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+D = "cuda:0"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _nhwc(t):  # oracle NCHW -> rows x C
+    return t.permute(0, 2, 3, 1).reshape(-1, t.shape[1])
+
+
+def _err(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    d = (got - ref).abs()
+    return dict(max_abs=float(d.max()), rel_rms=float(d.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-12)), ref_absmax=float(ref.abs().max()))
+
+
+def run_case(size, B, H, W, K, *, uni, precise, regime, seed=0):
+    from oracle import functional as Fn, synth
+    from oracle.postprocess import postprocess_ref, identity_meta
+    from wedetect_b200 import plan, schema, weights
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    sd = synth.synth_state_dict(size, seed=seed, uni=uni, num_prompts=K, with_text=False, regime=regime)
+    imgs = synth.synth_images(B, H, W, seed=seed + 2)
+    g = torch.Generator().manual_seed(seed + 5)
+    text = None if uni else torch.randn(K, schema.EMBED_DIM, generator=g)
+    with torch.no_grad():
+        ref = Fn.vision_forward(sd, size, imgs, text=text, prompts=sd.get("embeddings"))
+    Wt = weights.prepare_vision(sd, size, D, precise=precise)
+    kw = dict(score_thr=0.0, nms_mode=1, max_per_img=300) if uni else dict(score_thr=0.001, nms_mode=0, max_per_img=300)
+    p = plan.VisionPlan(Wt, size, B, H, W, K=K, uni=uni, **kw)
+    if not uni:
+        p.set_text(text.to(D))
+    p.image.copy_(imgs.to(D))
+    p.run()
+    torch.cuda.synchronize()
+    errs = {}
+    for s in range(4):
+        errs[f"c{s + 1}"] = _err(p.stage_x[s], _nhwc(ref["backbone"][s]))
+    for l in range(3):
+        pl = p.pyramid[l]
+        got = pl.hi.float() + (pl.lo.float() if pl.lo is not None else 0)
+        errs[f"p{l + 3}"] = _err(got, _nhwc(ref["neck"][l]))
+        lv = ref["levels"][l]
+        e = p.embeds[l]
+        ge = (e.hi.float() + (e.lo.float() if e.lo is not None else 0)) * Wt[f"head.contrast.{l}.g"] + Wt[f"head.contrast.{l}.h"]
+        errs[f"embed{l}"] = _err(ge, lv["embed"].reshape(-1, schema.EMBED_DIM))
+        errs[f"logit{l}"] = _err(p.logits[l][:, :K], lv["logits"].reshape(-1, K))
+        errs[f"dist{l}"] = _err(p.dists[l], lv["dist"].reshape(-1, 4))
+    # reference detections from the ORACLE's own logits / distances
+    meta, clamp = identity_meta(B, H, W)
+    lhw = schema.level_hw(H, W)
+    det_ref = postprocess_ref([lv["logits"].reshape(-1, K) for lv in ref["levels"]], [lv["dist"].reshape(-1, 4) for lv in ref["levels"]], lhw,
+                              list(schema.STRIDES), K=K, B=B, score_thr=kw["score_thr"], nms_pre=30000, iou_thr=0.7, max_per_img=300,
+                              nms_mode=kw["nms_mode"], img_meta=meta, clamp_wh=clamp)
+    det = {k: v.cpu() for k, v in p.results().items()}
+    same = []
+    for b in range(B):
+        n = int(det_ref["counts"][b])
+        a = set(zip(det["anchors"][b, :int(det["counts"][b])].tolist(), det["labels"][b, :int(det["counts"][b])].tolist()))
+        r = set(zip(det_ref["anchors"][b, :n].tolist(), det_ref["labels"][b, :n].tolist()))
+        same.append(len(a & r) / max(1, len(r)))
+    errs["det_overlap"] = same
+    errs["det_counts"] = [det["counts"].tolist(), det_ref["counts"].tolist()]
+    os.makedirs(OUT, exist_ok=True)
+    tag = f"{size}_{'uni' if uni else 'text'}_{'precise' if precise else 'fast'}_{regime}_{H}x{W}_B{B}_K{K}"
+    with open(os.path.join(OUT, f"e2e_{tag}.json"), "w") as f:
+        json.dump(errs, f, indent=1)
+    print(tag, json.dumps({k: (round(v["max_abs"], 5), round(v["rel_rms"], 6)) if isinstance(v, dict) else v for k, v in errs.items()}))
+    return errs, det, det_ref, p, ref
+
+
+@pytest.mark.parametrize("size,K", [("tiny", 5), ("base", 80)])
+def test_e2e_fast(size, K):
+    errs, det, det_ref, p, ref = run_case(size, 2, 320, 320, K, uni=False, precise=False, regime="sparse")
+    for s in range(4):
+        assert errs[f"c{s + 1}"]["rel_rms"] < 1e-2, (s, errs[f"c{s + 1}"])
+    for l in range(3):
+        assert errs[f"p{l + 3}"]["rel_rms"] < 3e-2, errs[f"p{l + 3}"]
+        assert errs[f"logit{l}"]["max_abs"] < 0.25, errs[f"logit{l}"]
+        assert errs[f"dist{l}"]["max_abs"] < 0.5, errs[f"dist{l}"]
+    assert min(errs["det_overlap"]) > 0.8, errs["det_overlap"]
+
+
+@pytest.mark.parametrize("size,K,uni", [("tiny", 5, False), ("base", 80, False), ("base", 256, True)])
+def test_e2e_precise_north_star(size, K, uni):
+    """bf16x3 path: logits within 1e-3 of the fp32 reference and identical kept indices / labels."""
+    errs, det, det_ref, p, ref = run_case(size, 2, 320, 320, K, uni=uni, precise=True, regime="sparse")
+    for l in range(3):
+        assert errs[f"logit{l}"]["max_abs"] <= 1e-3, errs[f"logit{l}"]
+        assert errs[f"dist{l}"]["max_abs"] <= 1e-3, errs[f"dist{l}"]
+    assert torch.equal(det["counts"], det_ref["counts"])
+    assert torch.equal(det["anchors"], det_ref["anchors"]), "kept anchor indices differ"
+    assert torch.equal(det["labels"], det_ref["labels"]), "kept labels differ"
+    assert float((det["scores"] - det_ref["scores"]).abs().max()) <= 1e-3
+    assert float((det["boxes"] - det_ref["boxes"]).abs().max()) <= 1e-2
+    if uni:
+        lv = torch.cat([l_["embed"] for l_ in ref["levels"]], 1)
+        for b in range(2):
+            n = int(det_ref["counts"][b])
+            want = lv[b, det_ref["anchors"][b, :n].long()]
+            assert float((det["embeddings"][b, :n] - want).abs().max()) <= 2e-3
+
+
+def test_cuda_graph_replay_matches_eager():
+    from oracle import synth
+    from wedetect_b200 import plan, schema, weights
+    size, B, H, W, K = "tiny", 2, 320, 320, 16
+    sd = synth.synth_state_dict(size, seed=3, with_text=False, regime="sparse")
+    Wt = weights.prepare_vision(sd, size, D)
+    p = plan.VisionPlan(Wt, size, B, H, W, K=K)
+    p.set_text(torch.randn(K, schema.EMBED_DIM, generator=torch.Generator().manual_seed(1)).to(D))
+    p.image.copy_(synth.synth_images(B, H, W).to(D))
+    p.run()
+    torch.cuda.synchronize()
+    eager = {k: v.clone() for k, v in p.results().items()}
+    p.capture()
+    p.image.copy_(synth.synth_images(B, H, W).to(D))
+    p.run()
+    torch.cuda.synchronize()
+    for k, v in p.results().items():
+        assert torch.equal(v, eager[k]), k

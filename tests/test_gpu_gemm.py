@@ -32,6 +32,8 @@ def _rand_bf16(*shape, scale=1.0, seed=0):
     (300, 192, 80, None),    # N not a multiple of the chunk/tile (80), K = 3 iterations
     (128 * 400, 128, 512, 256),  # many tiles per CTA: barrier phases wrap, TMEM double buffering
     (640, 2048, 256, 256),   # long K loop
+    (500, 96, 384, None),    # K = 96: second k-chunk half zero-filled by TMA
+    (260, 864, 96, None),    # im2col of a 96-channel 3x3 s2 conv (K = 9*96)
 ])
 def test_linear_plain(M, K, N, block_n):
     from wedetect_b200 import ops
@@ -88,7 +90,15 @@ def test_linear_slice_output_bf16_resid():
     assert float((buf[:, :128].float() - 3).abs().max()) == 0 and float((buf[:, 256:].float() - 3).abs().max()) == 0
 
 
-@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 20, 20, 64, 64), (3, 40, 40, 128, 128), (1, 80, 80, 64, 256), (5, 25, 25, 64, 64)])
+def _pad_taps(Wt, Cin):
+    """[N, 9*Cin] -> [N, 9*pad64(Cin)] zero padded per tap (the layout conv3x3 expects)."""
+    Kc = (Cin + 63) // 64 * 64
+    out = torch.zeros(Wt.shape[0], 9, Kc, dtype=Wt.dtype)
+    out[:, :, :Cin] = Wt.view(Wt.shape[0], 9, Cin)
+    return out.view(Wt.shape[0], 9 * Kc)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 20, 20, 64, 64), (3, 40, 40, 128, 128), (1, 80, 80, 64, 256), (5, 25, 25, 64, 64), (2, 20, 20, 96, 96), (1, 40, 40, 48, 48)])
 def test_conv3x3(B, H, W, Cin, N):
     from wedetect_b200 import ops
     A, Wt = _rand_bf16(B, H, W, Cin, seed=13), _rand_bf16(N, 9 * Cin, seed=14, scale=0.04)
@@ -97,20 +107,26 @@ def test_conv3x3(B, H, W, Cin, N):
     resid = _rand_bf16(B, H, W, N, seed=16) if Cin == N else None
     d = _dev()
     C = torch.zeros(B, H, W, N, dtype=torch.bfloat16, device=d)
-    _run(ops.conv3x3(A.to(d), Wt.to(d), C, bias=bias.to(d), act=2, resid=None if resid is None else resid.to(d), alpha=0.9))
+    _run(ops.conv3x3(A.to(d), _pad_taps(Wt, Cin).to(d), C, bias=bias.to(d), act=2, resid=None if resid is None else resid.to(d), alpha=0.9))
     ref = R.conv3x3_ref(A, Wt, bias=bias, act=2, resid=resid, alpha=0.9)
     report_close(f"conv3x3 {B}x{H}x{W}x{Cin}->{N}", C.reshape(-1, N), ref.reshape(-1, N), rtol=1e-2, atol=1e-2)
 
 
-def test_deconv2x2_into_slice():
+@pytest.mark.parametrize("Cin,Co", [(128, 128), (96, 96), (192, 192)])
+def test_deconv2x2_into_slice(Cin, Co):
     from wedetect_b200 import ops
-    B, H, W, Cin, Co = 2, 20, 20, 128, 128
+    B, H, W = 2, 20, 20
     A, Wt = _rand_bf16(B, H, W, Cin, seed=17), _rand_bf16(4 * Co, Cin, seed=18, scale=0.06)
     bias = torch.randn(Co, generator=torch.Generator().manual_seed(19))
     d = _dev()
     buf = torch.full((B, 2 * H, 2 * W, 3 * Co), 5.0, dtype=torch.bfloat16, device=d)
     C = buf[..., :Co]
-    _run(ops.deconv2x2(A.to(d), Wt.to(d), C, torch.cat([bias, bias]).to(d)))
+    Cg = (Co + 63) // 64 * 64
+    Wp = torch.zeros(4, Cg, Cin, dtype=torch.bfloat16)
+    Wp[:, :Co] = Wt.view(4, Co, Cin)
+    bp = torch.zeros(2, Cg)
+    bp[:, :Co] = bias
+    _run(ops.deconv2x2(A.to(d), Wp.view(4 * Cg, Cin).to(d), C, bp.view(-1).to(d)))
     ref = R.deconv2x2_ref(A, Wt, bias)
     report_close("deconv2x2", C.reshape(-1, Co), ref.reshape(-1, Co), rtol=1e-2, atol=1e-2)
     assert float((buf[..., Co:].float() - 5).abs().max()) == 0
@@ -159,7 +175,7 @@ def test_conv3x3_split_precise():
     d = _dev()
     Ch = torch.zeros(B, H, W, N, dtype=torch.bfloat16, device=d)
     Cl = torch.zeros_like(Ch)
-    _run(ops.conv3x3(Ah.to(d), Wh.to(d), Ch, A_lo=Al.to(d), W_lo=Wl.to(d), C_lo=Cl))
+    _run(ops.conv3x3(Ah.to(d), _pad_taps(Wh, Cin).to(d), Ch, A_lo=Al.to(d), W_lo=_pad_taps(Wl, Cin).to(d), C_lo=Cl))
     w = Wt.view(N, 3, 3, Cin).permute(0, 3, 1, 2).double()
     ref = torch.nn.functional.conv2d(A.permute(0, 3, 1, 2).double(), w, padding=1).permute(0, 2, 3, 1).float()
     report_close("conv3x3 split", (Ch.float() + Cl.float()).reshape(-1, N), ref.reshape(-1, N), rtol=3e-5, atol=3e-5)

@@ -425,6 +425,9 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     P.epi_mode = I[24];
     P.tap_w = I[25] > 0 ? I[25] : 1;
     P.pad = I[26];
+    const int group_valid = I[27] > 0 ? I[27] : I[18];   // columns of a group that exist in memory
+    const int k_valid = I[28] > 0 ? I[28] : Kc;          // A channels that exist (rest zero-filled by TMA)
+    const long long bk_valid = I[29] > 0 ? I[29] : (long long)Kc * I[7];
     P.alpha = op.f[0];
     P.bias = (const float*)op.p[3];
     P.gamma = (const float*)op.p[4];
@@ -460,7 +463,8 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
 
     // --- A: rank-4 (k, d0, d1, d2), bf16, box (64, E0, E1, E2), 128B swizzle
     {
-        uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)P.D0, (uint64_t)P.D1, (uint64_t)P.D2};
+        WD_REQUIRE(k_valid <= Kc && k_valid % 8 == 0, "gemm: K_valid=%d must be <= Kc and a multiple of 8", k_valid);
+        uint64_t dims[4] = {(uint64_t)k_valid, (uint64_t)P.D0, (uint64_t)P.D1, (uint64_t)P.D2};
         uint64_t str[3] = {(uint64_t)sa0 * 2, (uint64_t)sa1 * 2, (uint64_t)sa2 * 2};
         uint32_t box[4] = {kBlockK, (uint32_t)P.E0, (uint32_t)P.E1, (uint32_t)P.E2};
         if (encode_tmap(&P.tmA, op.p[0], 2, 4, dims, str, box, true)) return -1;
@@ -468,7 +472,8 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     }
     // --- B: rank-2 (k_total, n)
     {
-        uint64_t dims[2] = {(uint64_t)Kc * P.ntaps, (uint64_t)P.N};
+        WD_REQUIRE(bk_valid <= (long long)Kc * P.ntaps && bk_valid % 8 == 0, "gemm: bad B K extent");
+        uint64_t dims[2] = {(uint64_t)bk_valid, (uint64_t)P.N};
         uint64_t str[1] = {(uint64_t)ldb * 2};
         uint32_t box[2] = {kBlockK, (uint32_t)g->block_n};
         if (encode_tmap(&P.tmB, op.p[1], 2, 2, dims, str, box, true)) return -1;
@@ -477,7 +482,7 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     // --- C: rank-5 (c, d0, d1, d2, group), box (CH, E0, E1, E2, 1)
     if (P.epi_mode == 0) {
         const int eb = g->out_f32 ? 4 : 2;
-        const int cols = n_groups == 1 ? P.N : P.group_cols;
+        const int cols = n_groups == 1 ? P.N : group_valid;
         uint64_t dims[5] = {(uint64_t)cols, (uint64_t)P.D0, (uint64_t)P.D1, (uint64_t)P.D2, (uint64_t)n_groups};
         uint64_t str[4] = {(uint64_t)sc0 * eb, (uint64_t)sc1 * eb, (uint64_t)sc2 * eb, (uint64_t)(n_groups == 1 ? sc2 * P.D2 : scg) * eb};
         uint32_t box[5] = {(uint32_t)CH, (uint32_t)P.E0, (uint32_t)P.E1, (uint32_t)P.E2, 1};

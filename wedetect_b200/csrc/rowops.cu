@@ -94,7 +94,7 @@ constexpr int kDwTX = 8, kDwTY = 2;
 
 __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict__ in, int B, int H, int W, int C, const float* __restrict__ wt,
                                                          const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                                         float eps, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                                                         float eps, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ld_out) {
     __shared__ float red[kDwTY * kDwTX][12];
     const int cg = threadIdx.x;
     const int c = cg * 4;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict
             if (x >= W) continue;
             const float m = mean[oy][ox], r = rstd[oy][ox];
             const float4 a = acc[oy][ox];
-            const long long idx = (((long long)bi * H + y) * W + x) * C + c;
+            const long long idx = (((long long)bi * H + y) * W + x) * ld_out + c;
             store_bf16x4(out_hi, out_lo, idx, (a.x - m) * r * w4.x + g4.x, (a.y - m) * r * w4.y + g4.y, (a.z - m) * r * w4.z + g4.z,
                          (a.w - m) * r * w4.w + g4.w);
         }
@@ -530,9 +530,11 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             __nv_bfloat16 *oh = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[6];
             const float *wt = (const float*)P[2], *bs = (const float*)P[3], *lw = (const float*)P[4], *lb = (const float*)P[5];
             const int threads = ((C / 4 + 31) / 32) * 32;
+            const int ld_out = I[4] > 0 ? I[4] : C;
+            WD_REQUIRE(ld_out >= C && ld_out % 4 == 0, "dwconv_ln: bad ld_out");
             f->fn = [=](cudaStream_t s) {
                 dim3 grid((W + kDwTX - 1) / kDwTX, (H + kDwTY - 1) / kDwTY, B);
-                dwconv7_ln_kernel<<<grid, threads, 0, s>>>(in, B, H, W, C, wt, bs, lw, lb, eps, oh, ol);
+                dwconv7_ln_kernel<<<grid, threads, 0, s>>>(in, B, H, W, C, wt, bs, lw, lb, eps, oh, ol, ld_out);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
                 return 0;

@@ -50,7 +50,7 @@ def pick_block_n(N, out_f32=False, split=False):
 
 def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, block_n=None, out_f32=False,
              act=L.ACT_NONE, bias=None, gamma=None, resid=None, ld_res=0, alpha=1.0, group_cols=None, n_groups=1,
-             c_gstride=0, dfl=False, A_lo=None, W_lo=None, C_lo=None, resid_lo=None):
+             c_gstride=0, dfl=False, A_lo=None, W_lo=None, C_lo=None, resid_lo=None, group_valid=0, k_valid=0, bk_valid=0):
     op = WdOp()
     op.kind = L.OP_GEMM
     split = A_lo is not None and W_lo is not None
@@ -71,6 +71,7 @@ def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, 
     I[23] = c_gstride
     I[24] = 1 if dfl else 0
     I[25], I[26] = (3, 1) if ntaps == 9 else (1, 0)
+    I[27], I[28], I[29] = group_valid, k_valid, bk_valid
     op.f[0] = alpha
     for k, t in enumerate((A, W, C, bias, gamma, resid, A_lo, W_lo, C_lo, resid_lo)):
         op.p[k] = _ptr(t)
@@ -88,7 +89,8 @@ def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_N
     _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
     M, K = A.shape
     N = W.shape[0]
-    assert W.shape[1] == K and K % 64 == 0, (W.shape, K)
+    assert W.shape[1] == K and K % 8 == 0, (W.shape, K)
+    Kc = (K + 63) // 64 * 64
     out_f32 = C.dtype == torch.float32
     if dfl:
         assert C.shape == (M, 4) and C.is_contiguous() and out_f32
@@ -100,9 +102,10 @@ def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_N
     if resid is not None:
         assert resid.shape == (M, N) and resid.stride(1) == 1
         ld_res = resid.stride(0)
-    return gemm_raw(A=A, W=W, C=C, dims=(M, 1, 1), tile=(128, 1, 1), Kc=K, N=N, a_strides=_flat_strides(A.stride(0), M),
+    return gemm_raw(A=A, W=W, C=C, dims=(M, 1, 1), tile=(128, 1, 1), Kc=Kc, N=N, a_strides=_flat_strides(A.stride(0), M),
                     ldb=W.stride(0), c_strides=c_str, block_n=block_n, out_f32=out_f32, act=act, bias=bias, gamma=gamma,
-                    resid=resid, ld_res=ld_res, alpha=alpha, dfl=dfl, A_lo=A_lo, W_lo=W_lo, C_lo=C_lo, resid_lo=resid_lo)
+                    resid=resid, ld_res=ld_res, alpha=alpha, dfl=dfl, A_lo=A_lo, W_lo=W_lo, C_lo=C_lo, resid_lo=resid_lo,
+                    k_valid=K, bk_valid=K)
 
 
 def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, A_lo=None, W_lo=None,
@@ -111,14 +114,15 @@ def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_
     _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
     B, H, Wd, Cin = A.shape
     N = W.shape[0]
-    assert W.shape[1] == 9 * Cin and Cin % 64 == 0
+    Kc = (Cin + 63) // 64 * 64
+    assert W.shape[1] == 9 * Kc and Cin % 8 == 0, "W must be [N, 9*pad64(Cin)] (zero padded per tap)"
     assert C.shape == (B, H, Wd, N) and C.stride(3) == 1
     ld_res = 0
     if resid is not None:
         assert resid.shape == (B, H, Wd, N) and resid.stride(3) == 1
         ld_res = resid.stride(2)
         assert resid.stride(1) == Wd * ld_res and resid.stride(0) == H * Wd * ld_res
-    return gemm_raw(A=A, W=W, C=C, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Cin, ntaps=9, N=N,
+    return gemm_raw(A=A, W=W, C=C, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Kc, k_valid=Cin, ntaps=9, N=N,
                     a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
                     c_strides=(C.stride(2), C.stride(1), C.stride(0)), block_n=block_n, out_f32=C.dtype == torch.float32,
                     act=act, bias=bias, resid=resid, ld_res=ld_res, alpha=alpha, A_lo=A_lo, W_lo=W_lo, C_lo=C_lo,
@@ -131,17 +135,20 @@ def deconv2x2(A, W, C, bias2, *, A_lo=None, W_lo=None, C_lo=None):
     bias2 f32 [2*Co] = bias repeated for dx = 0, 1."""
     _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
     B, H, Wd, Cin = A.shape
-    Co = W.shape[0] // 4
-    assert C.shape == (B, 2 * H, 2 * Wd, Co) and Co % 64 == 0 and Cin % 64 == 0
+    Co = C.shape[3]
+    Cg = W.shape[0] // 4          # rows per (dy, dx) group, = pad64(Co) with zero rows beyond Co
+    assert C.shape == (B, 2 * H, 2 * Wd, Co) and Cg % 64 == 0 and Cg >= Co and W.shape[1] == Cin and Cin % 8 == 0
+    assert bias2.shape == (2 * Cg,)
+    Kc = (Cin + 63) // 64 * 64
     ops = []
     for dy in range(2):
-        Wdy = W[dy * 2 * Co:(dy + 1) * 2 * Co]
+        Wdy = W[dy * 2 * Cg:(dy + 1) * 2 * Cg]
         Cdy = C[:, dy]
-        ops.append(gemm_raw(A=A, W=Wdy, C=Cdy, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Cin, N=2 * Co,
-                            a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
-                            c_strides=(2 * C.stride(2), 2 * C.stride(1), C.stride(0)), group_cols=Co, n_groups=2,
-                            c_gstride=C.stride(2), bias=bias2, out_f32=False,
-                            A_lo=A_lo, W_lo=None if W_lo is None else W_lo[dy * 2 * Co:(dy + 1) * 2 * Co],
+        ops.append(gemm_raw(A=A, W=Wdy, C=Cdy, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Kc, k_valid=Cin, bk_valid=Cin,
+                            N=2 * Cg, a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
+                            c_strides=(2 * C.stride(2), 2 * C.stride(1), C.stride(0)), group_cols=Cg, group_valid=Co,
+                            n_groups=2, c_gstride=C.stride(2), bias=bias2, out_f32=False,
+                            A_lo=A_lo, W_lo=None if W_lo is None else W_lo[dy * 2 * Cg:(dy + 1) * 2 * Cg],
                             C_lo=None if C_lo is None else C_lo[:, dy]))
     return ops
 
@@ -169,10 +176,10 @@ def ln_rows(x, w, b, eps, *, out_bf16=None, out_lo=None, out_f32=None, s2d_hw=No
 def dwconv_ln(x, out, w49, bias, ln_w, ln_b, eps, out_lo=None):
     _chk(x, torch.float32, "x")
     B, H, W, C = x.shape
-    assert x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel() and w49.shape == (49, C)
+    assert x.is_contiguous() and out.shape == (B * H * W, C) and out.stride(1) == 1 and w49.shape == (49, C)
     op = WdOp()
     op.kind = L.OP_DWCONV_LN
-    op.i[0], op.i[1], op.i[2], op.i[3] = B, H, W, C
+    op.i[0], op.i[1], op.i[2], op.i[3], op.i[4] = B, H, W, C, out.stride(0)
     op.f[0] = eps
     for k, t in enumerate((x, out, w49, bias, ln_w, ln_b, out_lo)):
         op.p[k] = _ptr(t)
