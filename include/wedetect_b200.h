@@ -169,6 +169,9 @@ int wd_program_run(wd_program* prog, void* stream);
 int wd_program_capture(wd_program* prog, void* stream);
 int wd_program_replay(wd_program* prog, void* stream);
 int wd_program_num_launches(const wd_program* prog);
+int wd_program_num_ops(const wd_program* prog);
+/* measurement helper: eager run with CUDA events between ops; ms_per_op has wd_program_num_ops entries. */
+int wd_program_run_timed(wd_program* prog, void* stream, float* ms_per_op);
 void wd_program_destroy(wd_program* prog);
 
 /* workspace size needed by WD_OP_POSTPROCESS for (B, anchors, K). */

@@ -1,0 +1,128 @@
+"""Pins the travelling CPU oracle: (a) against golden vectors produced by the UNMODIFIED reference modules
+(tests/golden/reference_stages.pt, generator: tests/golden/make_golden.py), (b) against the reference itself when
+/root/reference is mounted (this container), (c) the C post-process against the reference's own
+filter_scores_and_topk + torchvision.ops.batched_nms, and an mmcv.ops.batched_nms restatement."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden", "reference_stages.pt")
+
+
+def _digest_close(t, g, rtol=2e-4, atol=2e-4):
+    t = t.detach().float().reshape(-1)
+    assert t.numel() == g["numel"]
+    idx = torch.linspace(0, t.numel() - 1, g["sample"].numel()).long()
+    torch.testing.assert_close(t[idx], g["sample"], rtol=rtol, atol=atol * max(1.0, g["absmax"]))
+    assert abs(float(t.mean()) - g["mean"]) <= atol * max(1.0, g["absmax"])
+    assert abs(float(t.std()) - g["std"]) <= 1e-3 * max(1.0, g["std"])
+
+
+def test_functional_oracle_matches_reference_goldens():
+    from oracle import functional as Fn, synth
+    gold = torch.load(GOLD)["base_320"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.synth_state_dict("base", seed=0, uni=True, regime="sparse")
+    x = synth.synth_images(2, 320, 320, seed=2)
+    with torch.no_grad():
+        out = Fn.vision_forward(sd, "base", x, prompts=sd["embeddings"])
+        text = torch.randn(80, 768, generator=torch.Generator().manual_seed(5))
+        tout = Fn.head(sd, out["neck"], text=text)
+    for i in range(4):
+        _digest_close(out["backbone"][i].permute(0, 2, 3, 1), gold[f"c{i + 1}"])
+    for i in range(3):
+        _digest_close(out["neck"][i].permute(0, 2, 3, 1), gold[f"p{i + 3}"])
+        _digest_close(out["levels"][i]["embed"], gold[f"embed{i}"])
+        _digest_close(out["levels"][i]["logits"], gold[f"logit{i}"])
+        _digest_close(out["levels"][i]["dist"], gold[f"dist{i}"])
+        _digest_close(tout[i]["logits"], gold[f"text_logit{i}"])
+    # final proposals through the C post-process oracle (torchvision rule as on the CPU: numel threshold 4000)
+    from oracle.postprocess import postprocess_ref, identity_meta
+    from wedetect_b200 import schema
+    meta, clamp = identity_meta(2, 320, 320)
+    det = postprocess_ref([lv["logits"].reshape(-1, 256) for lv in out["levels"]], [lv["dist"].reshape(-1, 4) for lv in out["levels"]],
+                          schema.level_hw(320, 320), list(schema.STRIDES), K=256, B=2, score_thr=0.0, nms_pre=30000, iou_thr=0.7,
+                          max_per_img=300, nms_mode=1, tv_numel_thr=4000, img_meta=meta, clamp_wh=torch.full((2, 2), 1e9))
+    for b, g in enumerate(gold["proposals"]):
+        n = int(det["counts"][b])
+        assert n == len(g["scores"])
+        torch.testing.assert_close(det["scores"][b, :n], g["scores"], rtol=1e-4, atol=1e-5)
+        # head_predict leaves boxes unclamped (the clamp happens in forward(), generate_proposal.py:1114-1115)
+        torch.testing.assert_close(det["boxes"][b, :n], g["bboxes"].clamp(min=0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not mounted")
+def test_schema_and_oracle_match_reference_modules_live():
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import generate_proposal as gp
+    from make_golden import to_gp_key
+    from oracle import functional as Fn, synth
+    from wedetect_b200 import schema
+    for size in ("base", "large"):
+        m = gp.SimpleYOLOWorldDetector(size, 768, 256, 300)
+        ref_shapes = {k: tuple(v.shape) for k, v in schema.normalize_state_dict(m.state_dict()).items()}
+        assert ref_shapes == dict(schema.param_shapes(size, uni=True))
+    sd = synth.synth_state_dict("base", seed=4, uni=True, regime="dense")
+    m = gp.SimpleYOLOWorldDetector("base", 768, 256, 300).eval()
+    m.load_state_dict({to_gp_key(k): v for k, v in sd.items()}, strict=True)
+    x = synth.synth_images(1, 256, 256, seed=9)
+    with torch.no_grad():
+        f = m.backbone(x)
+        n = m.neck(f)
+        out = Fn.vision_forward(sd, "base", x, prompts=sd["embeddings"])
+    for a, b in zip(f, out["backbone"]):
+        assert float((a - b).abs().max()) <= 1e-5
+    for a, b in zip(n, out["neck"]):
+        assert float((a - b).abs().max()) <= 1e-4
+
+
+def _torch_reference_postprocess(scores, boxes, thr, topk, iou, n_keep, offsets_always):
+    """The reference's own code path in torch: filter_scores_and_topk (generate_proposal.py:85-131 semantics,
+    stable order) + batched NMS (mmcv-style offsets or torchvision.ops.batched_nms)."""
+    import torchvision
+    valid = scores > thr
+    s = scores[valid]
+    idx = torch.nonzero(valid)
+    s, order = s.sort(descending=True, stable=True)
+    k = min(topk, idx.size(0))
+    s, idx = s[:k], idx[order[:k]]
+    keep_idxs, labels = idx.unbind(1)
+    b = boxes[keep_idxs]
+    if offsets_always:  # mmcv.ops.batched_nms: coordinate trick regardless of size
+        off = labels.to(b) * (b.max() + torch.tensor(1).to(b))
+        keep = torchvision.ops.nms(b + off[:, None], s, iou)
+    else:
+        keep = torchvision.ops.batched_nms(b.float(), s.float(), labels, iou)
+    keep = keep[:n_keep]
+    return b[keep], s[keep], labels[keep], keep_idxs[keep]
+
+
+@pytest.mark.parametrize("offsets_always", [True, False])
+def test_c_postprocess_matches_torch_reference_ops(offsets_always):
+    from oracle.postprocess import postprocess_ref, identity_meta
+    g = torch.Generator().manual_seed(3)
+    hw, strides, K, B = [(20, 20), (10, 10), (5, 5)], [8, 16, 32], 12, 1
+    logits = [torch.randn(h * w, K, generator=g) * 1.5 - 2.0 for h, w in hw]
+    dists = [torch.rand(h * w, 4, generator=g) * 6 for h, w in hw]
+    meta, clamp = identity_meta(B, 160, 160)
+    det = postprocess_ref(logits, dists, hw, strides, K=K, B=B, score_thr=0.05, nms_pre=1000, iou_thr=0.6, max_per_img=100,
+                          nms_mode=0 if offsets_always else 1, tv_numel_thr=4000, img_meta=meta, clamp_wh=torch.full((1, 2), 1e9))
+    # torch side: sigmoid in double rounded once (the oracle's definition), decode as the reference does
+    scores = torch.cat([torch.sigmoid(l.double()).float() for l in logits])
+    pri = []
+    for (h, w), s in zip(hw, strides):
+        yy, xx = torch.meshgrid((torch.arange(h) + 0.5) * s, (torch.arange(w) + 0.5) * s, indexing="ij")
+        pri.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+    pri = torch.cat(pri)
+    d = torch.cat([dd * s for dd, s in zip(dists, strides)])
+    boxes = torch.stack([pri[:, 0] - d[:, 0], pri[:, 1] - d[:, 1], pri[:, 0] + d[:, 2], pri[:, 1] + d[:, 3]], -1)
+    tb, ts, tl, ta = _torch_reference_postprocess(scores, boxes, 0.05, 1000, 0.6, 100, offsets_always)
+    n = int(det["counts"][0])
+    assert n == len(ts)
+    assert torch.equal(det["anchors"][0, :n].long(), ta) and torch.equal(det["labels"][0, :n].long(), tl)
+    assert torch.equal(det["scores"][0, :n], ts) and torch.equal(det["boxes"][0, :n], tb.clamp(min=0))

@@ -19,7 +19,7 @@ ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
 EXPORTS = [
     "wd_last_error", "wd_version", "wd_launch_count", "wd_device_info", "wd_op_run", "wd_program_create",
     "wd_program_run", "wd_program_capture", "wd_program_replay", "wd_program_num_launches",
-    "wd_program_destroy", "wd_pp_workspace_bytes",
+    "wd_program_destroy", "wd_pp_workspace_bytes", "wd_program_num_ops", "wd_program_run_timed",
 ]
 
 
@@ -74,6 +74,8 @@ def load(require_gpu=True):
         lib.wd_program_capture.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.wd_program_replay.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.wd_program_num_launches.argtypes = [ctypes.c_void_p]
+        lib.wd_program_num_ops.argtypes = [ctypes.c_void_p]
+        lib.wd_program_run_timed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
         lib.wd_program_destroy.argtypes = [ctypes.c_void_p]
         lib.wd_program_destroy.restype = None
         lib.wd_pp_workspace_bytes.argtypes = [ctypes.c_int] * 4
@@ -127,6 +129,13 @@ class Program:
 
     def run(self, stream=0):
         check(self._lib.wd_program_run(self._h, ctypes.c_void_p(stream)), "wd_program_run")
+
+    def run_timed(self, stream=0):
+        """Eager run with CUDA events between ops -> list of per-op milliseconds (measurement helper)."""
+        n = int(self._lib.wd_program_num_ops(self._h))
+        ms = (ctypes.c_float * n)()
+        check(self._lib.wd_program_run_timed(self._h, ctypes.c_void_p(stream), ms), "wd_program_run_timed")
+        return list(ms)
 
     def capture(self, stream):
         check(self._lib.wd_program_capture(self._h, ctypes.c_void_p(stream)), "wd_program_capture")

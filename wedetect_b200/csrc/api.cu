@@ -186,6 +186,34 @@ int wd_program_run(wd_program* prog, void* stream) {
     return 0;
 }
 
+int wd_program_num_ops(const wd_program* prog) { return prog ? (int)prog->ops.size() : 0; }
+
+// Eager replay with a CUDA event between consecutive ops: ms_per_op[i] = device time of op i (which may be
+// several kernels, e.g. the post-process).  Synchronises the stream at the end (measurement helper only).
+int wd_program_run_timed(wd_program* prog, void* stream, float* ms_per_op) {
+    if (!prog || !ms_per_op) {
+        wd::set_last_error("wd_program_run_timed: bad arguments");
+        return -1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t n = prog->ops.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) WD_CHECK_CUDA(cudaEventCreate(&e));
+    WD_CHECK_CUDA(cudaEventRecord(ev[0], s));
+    int rc = 0;
+    for (size_t i = 0; i < n && rc == 0; ++i) {
+        rc = prog->ops[i]->launch(s);
+        cudaEventRecord(ev[i + 1], s);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == 0 && e == cudaSuccess)
+        for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+    for (auto& x : ev) cudaEventDestroy(x);
+    if (rc) return rc;
+    WD_CHECK_CUDA(e);
+    return 0;
+}
+
 int wd_program_capture(wd_program* prog, void* stream) {
     if (!prog) {
         wd::set_last_error("wd_program_capture: null program");

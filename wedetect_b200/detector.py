@@ -1,0 +1,279 @@
+"""Host-side mirror of the reference's detector interface, backed by the sm_100a program executor.
+
+    YOLOWorldDetector        <- wedetect/models/detectors/yolo_world.py:35-113 (text-conditioned, mmdet path:
+                                reparameterize / test_step / predict, called by infer_wedetect.py:113-183)
+    SimpleYOLOWorldDetector  <- generate_proposal.py:1052-1218 (WeDetect-Uni: learned prompts, proposals +
+                                768-d embeddings), also used by eval_retrieval/extract_embedding.py
+
+Same names, argument meaning and error behaviour; the arithmetic runs in libwedetect_b200.so through
+`plan.VisionPlan` / `plan.TextPlan`.  There is no PyTorch / CPU fallback: constructing a detector without
+the CUDA library or an sm_100 device raises.
+"""
+import itertools
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import plan, schema, weights
+from .structures import DetDataSample, InstanceData
+
+_DEF_TEST_CFG = dict(multi_label=True, nms_pre=30000, score_thr=0.001, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300)
+
+
+def _size_from_cfg(model_cfg):
+    return model_cfg["backbone"]["image_model"]["model_name"]
+
+
+class YOLOWorldDetector:
+    """Text-conditioned detector facade.  `model_cfg` is the `model=` dict of config/wedetect_*.py."""
+
+    def __init__(self, model_cfg=None, *, size=None, test_cfg=None, device="cuda:0", precise=False, tokenizer=None):
+        L.load(require_gpu=True)
+        self.model_cfg = model_cfg
+        self.size = size or _size_from_cfg(model_cfg)
+        if self.size not in schema.SIZES:
+            raise ValueError(f"unknown model size {self.size!r}")
+        self.test_cfg = dict(_DEF_TEST_CFG if test_cfg is None else test_cfg)
+        if model_cfg is not None and model_cfg.get("test_cfg") and test_cfg is None:
+            self.test_cfg = dict(model_cfg["test_cfg"])
+        if model_cfg is not None and model_cfg.get("mm_neck", False):
+            raise NotImplementedError("mm_neck=True (text-guided neck) is not used by any shipped config")
+        self.device = torch.device(device)
+        self.precise = precise
+        self._tokenizer = tokenizer
+        self._plans = {}
+        self._text_plans = {}
+        self._text_cache = {}
+        self._vw = {}
+        self._tw = None
+        self._sd = None
+        self.texts = None
+        self.text_feats = None
+
+    # --- nn.Module-ish surface used by the entry points ---
+    def eval(self):
+        return self
+
+    def to(self, device):
+        return self
+
+    def load_state_dict(self, sd, strict=False):
+        sd = schema.normalize_state_dict(sd)
+        need = schema.param_shapes(self.size, with_text=any(k.startswith("backbone.text_model.") for k in sd))
+        missing = [k for k in need if k not in sd]
+        bad = [k for k in need if k in sd and tuple(sd[k].shape) != tuple(need[k])]
+        if bad:
+            raise RuntimeError(f"size mismatch for {bad[:4]} ...")
+        if missing:
+            raise RuntimeError(f"missing keys in checkpoint: {missing[:4]} ... ({len(missing)} total)")
+        self._sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+        self._plans.clear(); self._text_plans.clear(); self._text_cache.clear(); self._vw.clear()
+        self._tw = None
+        return self
+
+    # --- text tower ---
+    def _get_tokenizer(self):
+        if self._tokenizer is None:
+            from transformers import AutoTokenizer
+            name = self.model_cfg["backbone"]["text_model"]["model_name"]
+            self._tokenizer = AutoTokenizer.from_pretrained(name)
+        return self._tokenizer
+
+    def encode_tokens(self, ids, mask):
+        """ids / mask: int [S, L] (CPU or device).  Returns L2-normalised embeddings [S, 768] on the device."""
+        if self._sd is None:
+            raise RuntimeError("load_state_dict first")
+        if self._tw is None:
+            self._tw = weights.prepare_text(self._sd, self.size, self.device, precise=self.precise)
+        S, Lt = ids.shape
+        key = (S, Lt)
+        if key not in self._text_plans:
+            self._text_plans[key] = plan.TextPlan(self._tw, self.size, S, Lt, device=self.device)
+        tp = self._text_plans[key]
+        return tp.run(ids.to(self.device, torch.int32), mask.to(self.device, torch.int32)).clone()
+
+    def forward_text(self, texts):
+        """texts: List[List[str]] (one list of class prompts per image); mm_backbone.py:376-390."""
+        num = [len(t) for t in texts]
+        assert max(num) == min(num), "number of sequences not equal in batch"
+        flat = list(itertools.chain(*texts))
+        key = tuple(flat)
+        if key not in self._text_cache:
+            tok = self._get_tokenizer()(text=flat, return_tensors="pt", padding=True)
+            self._text_cache[key] = self.encode_tokens(tok["input_ids"], tok["attention_mask"])
+        f = self._text_cache[key]
+        return f.reshape(-1, num[0], f.shape[-1])
+
+    def reparameterize(self, texts):
+        self.texts = texts
+        # infer_wedetect.py passes [[t1], [t2], ...]: one "image" per class; flatten to a single class list
+        self.text_feats = self.forward_text([list(itertools.chain(*texts))])
+
+    def set_text_features(self, feats):
+        """Directly install class embeddings [K, 768] (e.g. cached or synthetic), un-normalised is fine."""
+        self.texts = None
+        self.text_feats = feats.to(self.device, torch.float32).reshape(1, -1, schema.EMBED_DIM)
+
+    # --- vision ---
+    def _plan(self, B, H, W, K, dtype):
+        key = (B, H, W, K, dtype)
+        if key not in self._plans:
+            fmt = "u8_bgr" if dtype == torch.uint8 else "f32_rgb"
+            if fmt not in self._vw:
+                self._vw[fmt] = weights.prepare_vision(self._sd, self.size, self.device, input_format=fmt, precise=self.precise)
+            tc = self.test_cfg
+            if tc.get("nms", {}).get("type", "nms") != "nms":
+                raise NotImplementedError(f"nms type {tc['nms']['type']}")
+            p = plan.VisionPlan(self._vw[fmt], self.size, B, H, W, K=K, uni=False, input_dtype=dtype, score_thr=float(tc.get("score_thr", -1)),
+                                nms_pre=int(tc.get("nms_pre", 100000)), iou_thr=float(tc["nms"]["iou_threshold"]),
+                                max_per_img=int(tc["max_per_img"]), nms_mode=0, device=self.device)
+            p._text_key = None
+            self._plans[key] = p
+        return self._plans[key]
+
+    def predict(self, batch_inputs, batch_data_samples, rescale=True):
+        if self._sd is None:
+            raise RuntimeError("load_state_dict first")
+        if isinstance(batch_inputs, (list, tuple)):
+            batch_inputs = torch.stack(list(batch_inputs))
+        B, _, H, W = batch_inputs.shape
+        # text features: per-sample `texts` metainfo wins (yolo_world.py:94-96), else the reparameterized cache
+        if isinstance(batch_data_samples, list) and batch_data_samples and batch_data_samples[0].get("texts") is not None:
+            texts = [s.texts for s in batch_data_samples]
+            if any(t != texts[0] for t in texts):
+                raise NotImplementedError("per-image text sets that differ inside one batch are not supported")
+            flat = [t[0] if isinstance(t, (list, tuple)) else t for t in texts[0]]
+            feats = self.forward_text([flat])
+        elif self.text_feats is not None:
+            feats = self.text_feats
+        else:
+            raise TypeError("batch_data_samples should be dict or list.")
+        feats = feats.reshape(-1, schema.EMBED_DIM)
+        K = feats.shape[0]
+        p = self._plan(B, H, W, K, batch_inputs.dtype)
+        if p._text_key is not feats:
+            p.set_text(feats.contiguous())
+            p._text_key = feats
+        meta = torch.zeros(B, 8)
+        meta[:, 2:4] = 1.0
+        meta[:, 6] = 1.0
+        clamp = torch.empty(B, 2)
+        for b, s in enumerate(batch_data_samples or [None] * B):
+            mi = s.metainfo if s is not None else {}
+            oh, ow = mi.get("ori_shape", (H, W))[:2]
+            clamp[b, 0], clamp[b, 1] = float(ow), float(oh)
+            if rescale:
+                pad = mi.get("pad_param")
+                if pad is not None:
+                    meta[b, 0], meta[b, 1] = float(pad[2]), float(pad[0])
+                sf = mi.get("scale_factor", (1.0, 1.0))
+                meta[b, 2], meta[b, 3] = float(sf[0]), float(sf[1])
+        p.set_meta(meta.to(self.device, non_blocking=True), clamp.to(self.device, non_blocking=True))
+        p.image.copy_(batch_inputs, non_blocking=True)
+        p.run()
+        r = p.results()
+        counts = r["counts"].cpu().tolist()   # the one host sync of the step (the reference has >= 3 per image)
+        out = []
+        for b in range(B):
+            n = counts[b]
+            inst = InstanceData(bboxes=r["boxes"][b, :n], scores=r["scores"][b, :n], labels=r["labels"][b, :n].long())
+            s = batch_data_samples[b] if batch_data_samples else DetDataSample()
+            s.pred_instances = inst
+            out.append(s)
+        return out
+
+    def test_step(self, data):
+        return self.predict(data["inputs"], data.get("data_samples"), rescale=True)
+
+    __call__ = test_step
+
+
+def letterbox_params(w, h, new_shape):
+    """Scale / offsets of generate_proposal.py:17-82 (scale_up=True) without touching pixels."""
+    nw, nh = new_shape[1], new_shape[0]
+    r = min(nw / w, nh / h)
+    unpad = (int(round(w * r)), int(round(h * r)))
+    dw, dh = nw - unpad[0], nh - unpad[1]
+    return r, unpad, (dw // 2, dh // 2), (dw / 2, dh / 2)
+
+
+class SimpleYOLOWorldDetector:
+    """WeDetect-Uni proposal generator facade (generate_proposal.py:1052-1218)."""
+
+    def __init__(self, backbone_size, prompt_dim=768, num_prompts=512, num_proposals=300, *, device="cuda:0", precise=False):
+        L.load(require_gpu=True)
+        if backbone_size not in ("base", "large", "tiny"):
+            raise ValueError(backbone_size)
+        assert prompt_dim == schema.EMBED_DIM
+        self.size, self.num_prompts, self.num_proposals = backbone_size, num_prompts, num_proposals
+        self.img_size = (1280, 1280) if backbone_size == "large" else (640, 640)
+        self.device, self.precise = torch.device(device), precise
+        self._sd, self._vw, self._plans = None, None, {}
+
+    def eval(self):
+        return self
+
+    def cuda(self):
+        return self
+
+    def load_state_dict(self, sd, strict=False):
+        sd = schema.normalize_state_dict(sd)
+        need = schema.param_shapes(self.size, uni=True, num_prompts=self.num_prompts)
+        missing = [k for k in need if k not in sd]
+        if missing and strict:
+            raise RuntimeError(f"missing keys: {missing[:4]} ...")
+        if missing:
+            raise RuntimeError(f"checkpoint lacks {len(missing)} tensors needed for inference, e.g. {missing[:3]}")
+        self._sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+        self._vw, self._plans = None, {}
+        return "<All keys matched successfully>"
+
+    def _plan(self, B, H, W):
+        key = (B, H, W)
+        if key not in self._plans:
+            if self._vw is None:
+                self._vw = weights.prepare_vision(self._sd, self.size, self.device, input_format="f32_rgb", precise=self.precise)
+            self._plans[key] = plan.VisionPlan(self._vw, self.size, B, H, W, K=self.num_prompts, uni=True, score_thr=0.0, nms_pre=30000,
+                                               iou_thr=0.7, max_per_img=self.num_proposals, nms_mode=1, device=self.device)
+        return self._plans[key]
+
+    def forward_tensor(self, inputs, ratios=None, offsets=None, ori_shapes=None, rescale=True):
+        """inputs: fp32 [B,3,H,W] RGB in [0,1] (already letterboxed).  Returns the reference's list of dicts."""
+        B, _, H, W = inputs.shape
+        p = self._plan(B, H, W)
+        meta = torch.zeros(B, 8)
+        meta[:, 2:4] = 1.0
+        meta[:, 6] = 1.0
+        clamp = torch.tensor([[float(W), float(H)]] * B)
+        for b in range(B):
+            if offsets is not None:
+                meta[b, 4], meta[b, 5] = float(offsets[b][0]), float(offsets[b][1])
+            if ratios is not None and rescale:
+                meta[b, 6] = float(ratios[b])
+            if ori_shapes is not None:
+                clamp[b, 0], clamp[b, 1] = float(ori_shapes[b][1]), float(ori_shapes[b][0])
+        p.set_meta(meta.to(self.device), clamp.to(self.device))
+        p.image.copy_(inputs, non_blocking=True)
+        p.run()
+        r = p.results()
+        counts = r["counts"].cpu().tolist()
+        return [dict(bboxes=r["boxes"][b, :counts[b]], embeddings=r["embeddings"][b, :counts[b]], scores=r["scores"][b, :counts[b]])
+                for b in range(B)]
+
+    def forward(self, image_paths, rescale=True):
+        from PIL import Image
+        inputs, ratios, offsets, ori_shapes = [], [], [], []
+        for ip in image_paths:
+            img = Image.open(ip).convert("RGB") if isinstance(ip, str) else ip
+            w, h = img.size
+            ori_shapes.append((h, w))
+            r, unpad, (left, top), off = letterbox_params(w, h, self.img_size)
+            canvas = Image.new("RGB", (self.img_size[1], self.img_size[0]), (114, 114, 114))
+            canvas.paste(img.resize(unpad, Image.Resampling.BILINEAR), (left, top))
+            inputs.append(torch.from_numpy(np.array(canvas)).permute(2, 0, 1).float() / 255.0)
+            ratios.append(r)
+            offsets.append(off)
+        return self.forward_tensor(torch.stack(inputs), ratios, offsets, ori_shapes, rescale)
+
+    __call__ = forward

@@ -1,0 +1,84 @@
+"""Minimal stand-ins for mmengine.structures.InstanceData / mmdet DetDataSample.
+
+Only the surface that the reference's entry points touch (infer_wedetect.py:113-126): attribute access,
+boolean / index `__getitem__` applied to every field, `.cpu()`, `.numpy()`, `len()`; a data sample exposes
+its metainfo keys as attributes (yolo_world.py:94 relies on `hasattr(sample, 'texts')`).
+If the real mmengine is installed the detector converts to the real classes instead (api.to_mm_samples).
+"""
+import torch
+
+
+class InstanceData:
+    def __init__(self, **fields):
+        object.__setattr__(self, "_fields", {})
+        for k, v in fields.items():
+            setattr(self, k, v)
+
+    def __setattr__(self, k, v):
+        self._fields[k] = v
+
+    def __getattr__(self, k):
+        f = object.__getattribute__(self, "_fields")
+        if k in f:
+            return f[k]
+        raise AttributeError(k)
+
+    def __contains__(self, k):
+        return k in self._fields
+
+    def keys(self):
+        return list(self._fields)
+
+    def __len__(self):
+        for v in self._fields.values():
+            return len(v)
+        return 0
+
+    def __getitem__(self, idx):
+        return InstanceData(**{k: v[idx] for k, v in self._fields.items()})
+
+    def _map(self, fn):
+        return InstanceData(**{k: fn(v) if isinstance(v, torch.Tensor) else v for k, v in self._fields.items()})
+
+    def cpu(self):
+        return self._map(lambda t: t.cpu())
+
+    def to(self, *a, **kw):
+        return self._map(lambda t: t.to(*a, **kw))
+
+    def numpy(self):
+        return InstanceData(**{k: v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v for k, v in self._fields.items()})
+
+    def __repr__(self):
+        return "InstanceData(" + ", ".join(f"{k}={tuple(v.shape) if hasattr(v, 'shape') else v}" for k, v in self._fields.items()) + ")"
+
+
+class DetDataSample:
+    def __init__(self, metainfo=None):
+        object.__setattr__(self, "_meta", dict(metainfo or {}))
+        object.__setattr__(self, "_data", {})
+
+    @property
+    def metainfo(self):
+        return dict(self._meta)
+
+    def set_metainfo(self, meta):
+        self._meta.update(meta)
+
+    def __setattr__(self, k, v):
+        self._data[k] = v
+
+    def __getattr__(self, k):
+        d = object.__getattribute__(self, "_data")
+        if k in d:
+            return d[k]
+        m = object.__getattribute__(self, "_meta")
+        if k in m:
+            return m[k]
+        raise AttributeError(k)
+
+    def get(self, k, default=None):
+        try:
+            return getattr(self, k)
+        except AttributeError:
+            return default
