@@ -5,6 +5,8 @@
  * reference function(s) whose arithmetic it replaces (paths relative to the reference checkout).
  *
  * Conventions
+ *   - bf16 tensors may be "3-plane" (precise bf16x3 mode): value = p0 + p1 + p2, planes `plane_stride`
+ *     elements apart starting at the given pointer; a plane stride of 0 means an ordinary bf16 tensor;
  *   - plain C types only; all pointers in `wd_op.p[]` are DEVICE pointers owned by the caller;
  *   - every call enqueues work on the caller's `cudaStream_t` (passed as void*), never syncs;
  *   - return 0 on success, negative on failure; `wd_last_error()` returns a thread-local message;
@@ -52,57 +54,58 @@ enum wd_op_kind {
      *    25 tap_w (3 for 3x3)  26 pad (1 for 3x3)  27 group_valid (columns of a group present in memory, 0 = group_cols)
      *    28 K_valid (channels of A present in memory, 0 = Kc; TMA zero-fills up to Kc)
      *    29 BK_valid (columns of B present in memory, 0 = ntaps*Kc)
+     *    30 planes (0|1 fast, 3 precise)  31 A plane stride  32 B plane stride  33 C plane stride  34 resid plane stride
      * f: 0 resid_alpha
      * p: 0 A (bf16)  1 B (bf16 [N, ntaps*Kc])  2 C  3 bias f32[N]  4 gamma f32[N]  5 resid
-     *    6 A_lo  7 B_lo  8 C_lo   (bf16x3 "split" precise mode; null in fast mode)
      * out = resid*alpha + gamma * act(acc + bias)        (each term optional) */
     WD_OP_GEMM = 1,
     /* Row LayerNorm over C (biased variance, eps inside sqrt): mm_backbone.py:145-155, F.layer_norm.
-     * i: 0 rows 1 C 2 in_dtype(1 bf16? no: 2 f32) 3 out_dtype (0 bf16, 1 f32)
+     * i: 0 rows 1 C
      *    4 s2d (0 | 1: write 2x2 space-to-depth layout for the stride-2 patchify conv, :193-198)
-     *    5 W 6 H (only for s2d) 7 ld_in 8 ld_out 9 has_resid (out = LN(in + resid)) 10 ld_res
-     * f: 0 eps   p: 0 in f32  1 out  2 weight f32[C]  3 bias f32[C]  4 resid f32  5 out_lo  6 out2 f32 */
+     *    5 W 6 H (only for s2d) 7 ld_in 8 ld_out
+     *    30 out plane stride
+     * f: 0 eps   p: 0 in f32  1 out bf16 (nullable)  2 weight f32[C]  3 bias f32[C]  6 out f32 (nullable) */
     WD_OP_LN_ROWS = 2,
     /* Depthwise 7x7 (pad 3) + bias + LayerNorm(C) on an NHWC fp32 tensor -> bf16 rows.
      * mm_backbone.py:114-116 (Block.forward dwconv/permute/norm).
-     * i: 0 B 1 H 2 W 3 C 4 ld_out (0 = C)   f: 0 eps
-     * p: 0 in f32 [B,H,W,C]  1 out bf16 [B*H*W,ld_out]  2 w f32[49,C]  3 b f32[C]  4 ln_w  5 ln_b  6 out_lo */
+     * i: 0 B 1 H 2 W 3 C 4 ld_out (0 = C) 30 out plane stride   f: 0 eps
+     * p: 0 in f32 [B,H,W,C]  1 out bf16 [B*H*W,ld_out]  2 w f32[49,C]  3 b f32[C]  4 ln_w  5 ln_b */
     WD_OP_DWCONV_LN = 3,
     /* Stem patchify: image -> bf16 rows [B*(H/4)*(W/4), 64] (48 valid = (dy,dx,c), rest 0).
      * mm_backbone.py:188-191 (Conv2d k4 s4 input gather); data_preprocessor.py:35-36 (mean/std are
      * folded into the stem weights by the host).
-     * i: 0 B 1 H 2 W 3 in_dtype (0 u8, 2 f32) 4 layout (0 NCHW, 1 NHWC)   f: 0 scale
-     * p: 0 in  1 out bf16  2 out_lo */
+     * i: 0 B 1 H 2 W 3 in_dtype (0 u8, 2 f32) 4 layout (0 NCHW) 30 out plane stride   f: 0 scale
+     * p: 0 in  1 out bf16 */
     WD_OP_STEM_PATCH = 4,
     /* im2col for 3x3 stride-2 pad-1 conv on NHWC bf16: rows [B*Ho*Wo, 9*C] (tap-major).
      * yolo_world_pafpn.py:704-709,1062-1082 (downsample ConvBNReLU k3 s2).
-     * i: 0 B 1 H 2 W 3 C 4 ld_in   p: 0 in bf16  1 out bf16  2 in_lo  3 out_lo */
+     * i: 0 B 1 H 2 W 3 C 4 ld_in 30 out plane stride 31 in plane stride   p: 0 in bf16  1 out bf16 */
     WD_OP_IM2COL_S2 = 5,
-    /* f32 -> bf16 row cast (backbone outputs c1..c4 to neck operands). i: 0 rows 1 C 2 ld_in 3 ld_out
-     * p: 0 in f32  1 out bf16  2 out_lo */
+    /* f32 -> bf16 row cast (backbone outputs c1..c4 to neck operands). i: 0 rows 1 C 2 ld_in 3 ld_out 30 out plane stride
+     * p: 0 in f32  1 out bf16 */
     WD_OP_CAST_BF16 = 6,
     /* XLM-R embeddings: word + position + token_type, LayerNorm (transformers
      * modeling_xlm_roberta.py embeddings; position ids = cumsum(mask)*mask + pad_idx).
-     * i: 0 S (sequences) 1 L (tokens/seq) 2 Hd 3 pad_idx   f: 0 eps
+     * i: 0 S (sequences) 1 L (tokens/seq) 2 Hd 3 pad_idx 30 out plane stride   f: 0 eps
      * p: 0 ids i32[S,L] 1 mask i32[S,L] 2 word f32[V,Hd] 3 pos f32[P,Hd] 4 type f32[Hd] 5 ln_w 6 ln_b
-     *    7 out f32 [S*L,Hd]  8 out bf16  9 out_lo */
+     *    7 out f32 [S*L,Hd]  8 out bf16 */
     WD_OP_TEXT_EMBED = 7,
     /* Short-sequence multi-head self-attention (L <= 32), one warp per (sequence, head).
-     * i: 0 S 1 L 2 heads 3 head_dim 4 ld_qkv (= 3*Hd)   f: 0 scale
-     * p: 0 qkv f32 [S*L, 3*Hd]  1 mask i32[S,L]  2 out bf16 [S*L,Hd]  3 out_lo */
+     * i: 0 S 1 L 2 heads 3 head_dim 4 ld_qkv (= 3*Hd) 30 out plane stride   f: 0 scale
+     * p: 0 qkv f32 [S*L, 3*Hd]  1 mask i32[S,L]  2 out bf16 [S*L,Hd] */
     WD_OP_ATTN_SMALL = 8,
     /* CLS pooling + L2 normalise: out[s,:] = x[s,:] / max(||x[s,:]||, 1e-12)  (F.normalize,
      * mm_backbone.py:387).  i: 0 S 1 C 2 ld_in   p: 0 in f32  1 out f32 */
     WD_OP_L2NORM_ROWS = 9,
     /* gather rows: out[s,:] = in[idx0 + s*stride,:] as bf16 (CLS token rows, mm_backbone.py:385).
-     * i: 0 S 1 C 2 row_stride 3 ld_in  p: 0 in f32  1 out bf16  2 out_lo */
+     * i: 0 S 1 C 2 row_stride 3 ld_in 30 out plane stride  p: 0 in f32  1 out bf16 */
     WD_OP_GATHER_ROWS = 10,
     /* Fold BNContrastiveHead into a GEMM weight: W'[k,c] = t[k,c]/max(||t[k]||,eps) * g[c] * exp(s),
      * b'[k] = exp(s) * sum_c h[c]*tn[k,c] + bias (yolo_world_head.py:90-108; Uni variant without
      * text normalisation: generate_proposal.py:1129-1131).
-     * i: 0 K 1 C 2 normalize (0|1) 3 K_pad
+     * i: 0 K 1 C 2 normalize (0|1) 3 K_pad 30 W' plane stride
      * p: 0 text f32[K,C] 1 bn_g f32[C] 2 bn_h f32[C] 3 logit_scale f32[1] 4 bias f32[1]
-     *    5 W' bf16 [K_pad,C]  6 b' f32[K_pad]  7 W'_lo */
+     *    5 W' bf16 [K_pad,C]  6 b' f32[K_pad] */
     WD_OP_FOLD_TEXT = 11,
     /* Detection post-process for a batch: sigmoid, score threshold, top-k (nms_pre), box decode,
      * rescale, class-aware greedy NMS, keep max_per_img.  Bit-exact integer/index semantics.
@@ -112,8 +115,9 @@ enum wd_op_kind {
     WD_OP_POSTPROCESS = 12,
     /* Gather kept proposals' embedding rows: out[b, j, :] = BN(embed[b, anchor(b,j), :]) f32.
      * generate_proposal.py:1129,1209-1212.  i: 0 B 1 A 2 C 3 max_keep  4 nlevels 5..7 level sizes
+     *    30..32 embed plane strides
      * p: 0..2 embed bf16 per level [B*HW_l, C]  3 keep_anchor i32[B,max]  4 counts i32[B]
-     *    5 bn_g f32[3*C] 6 bn_h f32[3*C] 7 out f32 [B,max,C]  8..10 embed_lo per level */
+     *    5 bn_g f32[3*C] 6 bn_h f32[3*C] 7 out f32 [B,max,C] */
     WD_OP_GATHER_EMBED = 13,
 };
 

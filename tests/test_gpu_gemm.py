@@ -144,38 +144,59 @@ def test_dfl_epilogue():
 
 
 def test_linear_split_precise():
-    """bf16x3 split mode reproduces an fp32 GEMM to ~1e-5 relative."""
+    """bf16x3 three-plane mode reproduces an fp32 GEMM to fp32-level accuracy."""
     from wedetect_b200 import ops
+    from wedetect_b200.ops import P3
     M, K, N = 515, 256, 192
     g = torch.Generator().manual_seed(23)
     A, Wt = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
     bias = torch.randn(N, generator=g)
-    Ah, Al = R.split_hi_lo(A)
-    Wh, Wl = R.split_hi_lo(Wt)
+    resid = torch.randn(M, N, generator=g)
     d = _dev()
+    Ap, Wp, Rp = P3.from_f32(A, d), P3.from_f32(Wt, d), P3.from_f32(resid, d)
     C = torch.zeros(M, N, dtype=torch.float32, device=d)
-    _run(ops.linear(Ah.to(d), Wh.to(d), C, bias=bias.to(d), act=3, A_lo=Al.to(d), W_lo=Wl.to(d)))
+    _run(ops.linear(Ap, Wp, C, bias=bias.to(d), act=3))
     ref = R.act_ref(A.double() @ Wt.double().t() + bias.double(), 3).float()
-    report_close("linear split f32", C, ref, rtol=2e-5, atol=2e-5)
-    # bf16 hi/lo outputs
-    Ch = torch.zeros(M, N, dtype=torch.bfloat16, device=d)
-    Cl = torch.zeros(M, N, dtype=torch.bfloat16, device=d)
-    _run(ops.linear(Ah.to(d), Wh.to(d), Ch, bias=bias.to(d), act=2, A_lo=Al.to(d), W_lo=Wl.to(d), C_lo=Cl))
-    ref2 = R.act_ref(A.double() @ Wt.double().t() + bias.double(), 2).float()
-    report_close("linear split hi+lo", Ch.float() + Cl.float(), ref2, rtol=3e-5, atol=3e-5)
+    report_close("linear precise f32", C, ref, rtol=2e-6, atol=2e-6)
+    # three-plane bf16 output + three-plane bf16 residual
+    Cp = P3.zeros((M, N), d, True)
+    _run(ops.linear(Ap, Wp, Cp, bias=bias.to(d), act=2, resid=Rp, alpha=0.5))
+    ref2 = (R.act_ref(A.double() @ Wt.double().t() + bias.double(), 2) + 0.5 * resid.double()).float()
+    report_close("linear precise 3-plane out", Cp.value(), ref2, rtol=2e-6, atol=2e-6)
 
 
 def test_conv3x3_split_precise():
     from wedetect_b200 import ops
-    B, H, W, Cin, N = 2, 20, 20, 64, 128
+    from wedetect_b200.ops import P3
+    B, H, W, Cin, N = 2, 20, 20, 96, 128
     g = torch.Generator().manual_seed(24)
     A, Wt = torch.randn(B, H, W, Cin, generator=g), torch.randn(N, 9 * Cin, generator=g) * 0.04
-    Ah, Al = R.split_hi_lo(A)
-    Wh, Wl = R.split_hi_lo(Wt)
     d = _dev()
-    Ch = torch.zeros(B, H, W, N, dtype=torch.bfloat16, device=d)
-    Cl = torch.zeros_like(Ch)
-    _run(ops.conv3x3(Ah.to(d), _pad_taps(Wh, Cin).to(d), Ch, A_lo=Al.to(d), W_lo=_pad_taps(Wl, Cin).to(d), C_lo=Cl))
+    Cp = P3.zeros((B, H, W, N), d, True)
+    _run(ops.conv3x3(P3.from_f32(A, d), P3.from_f32(_pad_taps(Wt, Cin), d), Cp))
     w = Wt.view(N, 3, 3, Cin).permute(0, 3, 1, 2).double()
     ref = torch.nn.functional.conv2d(A.permute(0, 3, 1, 2).double(), w, padding=1).permute(0, 2, 3, 1).float()
-    report_close("conv3x3 split", (Ch.float() + Cl.float()).reshape(-1, N), ref.reshape(-1, N), rtol=3e-5, atol=3e-5)
+    report_close("conv3x3 precise", Cp.value().reshape(-1, N), ref.reshape(-1, N), rtol=2e-6, atol=2e-6)
+
+
+def test_deconv_and_im2col_precise():
+    from wedetect_b200 import ops
+    from wedetect_b200.ops import P3
+    B, H, W, Cin, Co = 1, 10, 10, 96, 96
+    g = torch.Generator().manual_seed(25)
+    A, Wt, bias = torch.randn(B, H, W, Cin, generator=g), torch.randn(4 * Co, Cin, generator=g) * 0.06, torch.randn(Co, generator=g)
+    d = _dev()
+    Cg = 128
+    Wp = torch.zeros(4, Cg, Cin)
+    Wp[:, :Co] = Wt.view(4, Co, Cin)
+    bp = torch.zeros(2, Cg)
+    bp[:, :Co] = bias
+    buf = P3.zeros((B, 2 * H, 2 * W, 2 * Co), d, True)
+    Cs = buf.view(lambda t: t[..., Co:])
+    Ap = P3.from_f32(A, d)
+    _run(ops.deconv2x2(Ap, P3.from_f32(Wp.view(4 * Cg, Cin), d), Cs, bp.view(-1).to(d)))
+    ref = (A.double().reshape(-1, Cin) @ Wt.double().t()).view(B, H, W, 2, 2, Co).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, Co) + bias.double()
+    report_close("deconv precise", Cs.value().reshape(-1, Co), ref.float().reshape(-1, Co), rtol=2e-6, atol=2e-6)
+    col = P3.zeros((B * 5 * 5, 9 * Cin), d, True)
+    _run(ops.im2col_s2(Ap, col))
+    report_close("im2col precise", col.value(), R.im2col_s2_ref(A), rtol=1e-6, atol=1e-7)

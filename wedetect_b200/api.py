@@ -1,0 +1,28 @@
+"""Entry-point shims with the names the reference's scripts import.
+
+    infer_wedetect.py:      from mmdet.apis import init_detector        ->  from wedetect_b200.api import init_detector
+                            from mmengine.config import Config          ->  from wedetect_b200.api import Config
+    generate_proposal.py:   SimpleYOLOWorldDetector(...)                ->  from wedetect_b200.api import SimpleYOLOWorldDetector
+See INTEGRATION.md for the exact diffs.
+"""
+import torch
+
+from .config import Config, parse_cfg_options  # noqa: F401
+from .detector import SimpleYOLOWorldDetector, YOLOWorldDetector  # noqa: F401
+from .structures import DetDataSample, InstanceData  # noqa: F401
+
+
+def init_detector(config, checkpoint=None, palette="none", device="cuda:0", cfg_options=None, precise=False):
+    """mmdet.apis.init_detector look-alike (infer_wedetect.py:156): config path or Config, checkpoint path."""
+    cfg = Config.fromfile(config) if isinstance(config, str) else config
+    if cfg_options:
+        cfg.merge_from_dict(cfg_options)
+    model_cfg = cfg["model"]
+    if model_cfg["type"] != "YOLOWorldDetector":
+        raise NotImplementedError(model_cfg["type"])
+    model = YOLOWorldDetector(model_cfg, device=device, precise=precise)
+    if checkpoint is not None:
+        sd = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, str) else checkpoint
+        model.load_state_dict(sd)
+    model.cfg = cfg
+    return model.eval()

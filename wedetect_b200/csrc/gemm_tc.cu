@@ -14,8 +14,9 @@
 //   apply bias / activation / LayerScale / residual (or DFL), stage the tile in swizzled smem and
 //   write it back with TMA stores (which clip partial tiles and scatter into concat / upsample
 //   layouts through a rank-5 tensor map).
-// * kSplit = bf16x3 "precise" mode: every fp32 operand is carried as hi + lo bf16 planes and each
-//   k-step issues A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, giving ~2^-16 relative operand error.
+// * kSplit = bf16x3 "precise" mode: every fp32 operand is carried as three bf16 planes p0 + p1 + p2
+//   (8 + 8 + 8 mantissa bits) and each k-step issues the six products whose weight is >= 2^-16
+//   (a0b0, a1b0, a0b1, a2b0, a1b1, a0b2), i.e. fp32-grade operands on the bf16 tensor pipe.
 //
 // Reference arithmetic replaced: see include/wedetect_b200.h (WD_OP_GEMM).
 #include "internal.h"
@@ -30,7 +31,7 @@ constexpr int kTileM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle atom
 
 struct GemmParams {
-    CUtensorMap tmA, tmB, tmC, tmA_lo, tmB_lo, tmC_lo;
+    CUtensorMap tmA[3], tmB[3], tmC[3];   // plane 0 (+ planes 1, 2 in the bf16x3 "precise" mode)
     int D0, D1, D2, E0, E1, E2, nt0, nt1, nt2;
     int kc_iters, ntaps, tap_w, pad;
     int N, num_m_tiles, num_n_tiles, num_tiles;
@@ -39,7 +40,7 @@ struct GemmParams {
     const float* bias;
     const float* gamma;
     const void* resid;
-    const void* resid_lo;
+    long long resid_ps;  // plane stride (elements) of a 3-plane bf16 residual, 0 = single plane
     float* dfl_out;
 };
 
@@ -47,10 +48,10 @@ template <int BN, bool kSplit>
 struct Cfg {
     static constexpr int A_BYTES = kTileM * 128;
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = (kSplit ? 2 : 1) * (A_BYTES + B_BYTES);
-    static constexpr int kStages = kSplit ? (BN >= 128 ? 2 : 3) : (BN == 256 ? 4 : (BN == 128 ? 5 : 6));
+    static constexpr int STAGE_BYTES = (kSplit ? 3 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int kStages = kSplit ? 2 : (BN == 256 ? 4 : (BN == 128 ? 5 : 6));
     static constexpr int EPI_BUFS = (!kSplit && BN <= 128) ? 2 : 1;
-    static constexpr int EPI_BUF_BYTES = 16384 * (kSplit ? 2 : 1);
+    static constexpr int EPI_BUF_BYTES = 16384;
     static constexpr int EPI_BYTES = kNumEpiWG * EPI_BUFS * EPI_BUF_BYTES;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
@@ -85,9 +86,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tmA);
-        tma_prefetch_desc(&p.tmB);
-        tma_prefetch_desc(&p.tmC);
+        tma_prefetch_desc(&p.tmA[0]);
+        tma_prefetch_desc(&p.tmB[0]);
+        tma_prefetch_desc(&p.tmC[0]);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (kSplit ? 2u : 1u) * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
+            const uint32_t tx_bytes = (kSplit ? 3u : 1u) * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
                 const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
@@ -125,16 +126,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     const int tap = kit / p.kc_iters, kc = kit - tap * p.kc_iters;
                     const int dx = tap % p.tap_w - p.pad, dy = tap / p.tap_w - p.pad;
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    uint8_t* sA = smem + stage * C::STAGE_BYTES;
-                    uint8_t* sB = sA + C::A_BYTES;
                     mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
-                    tma_load_4d(&p.tmA, &bar_full[stage], sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
-                    tma_load_2d(&p.tmB, &bar_full[stage], sB, kit * kBlockK, n_blk * BN);
-                    if (kSplit) {
-                        uint8_t* sA2 = sB + C::B_BYTES;
-                        uint8_t* sB2 = sA2 + C::A_BYTES;
-                        tma_load_4d(&p.tmA_lo, &bar_full[stage], sA2, kc * kBlockK, o0 + dx, o1 + dy, o2);
-                        tma_load_2d(&p.tmB_lo, &bar_full[stage], sB2, kit * kBlockK, n_blk * BN);
+#pragma unroll
+                    for (int pl = 0; pl < (kSplit ? 3 : 1); ++pl) {
+                        uint8_t* sA = smem + stage * C::STAGE_BYTES + pl * (C::A_BYTES + C::B_BYTES);
+                        tma_load_4d(&p.tmA[pl], &bar_full[stage], sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
+                        tma_load_2d(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES, kit * kBlockK, n_blk * BN);
                     }
                     if (++stage == C::kStages) {
                         stage = 0;
@@ -158,19 +155,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 for (int kit = 0; kit < k_iters; ++kit) {
                     mbar_wait(&bar_full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sA = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint32_t sB = sA + C::A_BYTES;
-                    const uint64_t adesc = umma_desc_sw128(sA);
-                    const uint64_t bdesc = umma_desc_sw128(sB);
+                    const uint32_t s0 = smem_u32(smem + stage * C::STAGE_BYTES);
+                    constexpr uint32_t PL = C::A_BYTES + C::B_BYTES;
+                    const uint64_t a0 = umma_desc_sw128(s0), b0 = umma_desc_sw128(s0 + C::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-                        umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
                         if (kSplit) {
-                            const uint64_t adesc2 = umma_desc_sw128(sB + C::B_BYTES);
-                            const uint64_t bdesc2 = umma_desc_sw128(sB + C::B_BYTES + C::A_BYTES);
-                            umma_bf16(tmem_d, adesc2 + 2 * k, bdesc + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, adesc + 2 * k, bdesc2 + 2 * k, idesc, 1u);
+                            const uint64_t a1 = umma_desc_sw128(s0 + PL), b1 = umma_desc_sw128(s0 + PL + C::A_BYTES);
+                            const uint64_t a2 = umma_desc_sw128(s0 + 2 * PL), b2 = umma_desc_sw128(s0 + 2 * PL + C::A_BYTES);
+                            umma_bf16(tmem_d, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a2 + 2 * k, b0 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a1 + 2 * k, b1 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a0 + 2 * k, b2 + 2 * k, idesc, 1u);
                         }
                     }
                     umma_commit(&bar_empty[stage]);  // frees the smem slot when these MMAs retire
@@ -286,7 +285,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                                 }
                             } else {
                                 const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix * p.ld_res + n_base;
-                                const __nv_bfloat16* rl = p.resid_lo ? reinterpret_cast<const __nv_bfloat16*>(p.resid_lo) + pix * p.ld_res + n_base : nullptr;
+                                const __nv_bfloat16* rl = p.resid_ps ? rp + p.resid_ps : nullptr;
 #pragma unroll
                                 for (int j = 0; j < CH; j += 8) {
                                     if (n_base + j < p.N) {
@@ -294,11 +293,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                                         float xs[8] = {bf16_lo(x.x), bf16_hi(x.x), bf16_lo(x.y), bf16_hi(x.y),
                                                        bf16_lo(x.z), bf16_hi(x.z), bf16_lo(x.w), bf16_hi(x.w)};
                                         if (rl) {
-                                            const uint4 y = *reinterpret_cast<const uint4*>(rl + j);
-                                            xs[0] += bf16_lo(y.x); xs[1] += bf16_hi(y.x);
-                                            xs[2] += bf16_lo(y.y); xs[3] += bf16_hi(y.y);
-                                            xs[4] += bf16_lo(y.z); xs[5] += bf16_hi(y.z);
-                                            xs[6] += bf16_lo(y.w); xs[7] += bf16_hi(y.w);
+#pragma unroll
+                                            for (int pl = 0; pl < 2; ++pl) {
+                                                const uint4 y = *reinterpret_cast<const uint4*>(rl + pl * p.resid_ps + j);
+                                                xs[0] += bf16_lo(y.x); xs[1] += bf16_hi(y.x);
+                                                xs[2] += bf16_lo(y.y); xs[3] += bf16_hi(y.y);
+                                                xs[4] += bf16_lo(y.z); xs[5] += bf16_hi(y.z);
+                                                xs[6] += bf16_lo(y.w); xs[7] += bf16_hi(y.w);
+                                            }
                                         }
 #pragma unroll
                                         for (int q = 0; q < 8; ++q) v[j + q] += p.alpha * xs[q];
@@ -306,43 +308,44 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                                 }
                             }
                         }
-                        // ---- stage into swizzled smem, then TMA store ----
+                        // ---- stage into swizzled smem, then TMA store (precise bf16 output: one pass per plane) ----
                         uint8_t* sbuf = wg_bufs + buf * C::EPI_BUF_BYTES;
-                        if (issuer) tma_store_wait_read<C::EPI_BUFS - 1>();  // buffer `buf` no longer being read
-                        named_bar_sync(1 + wg, 128);
                         uint8_t* srow = sbuf + r * 128;
-                        if constexpr (kOutBf16) {
+                        const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
+                        constexpr int kOutPlanes = (kSplit && kOutBf16) ? 3 : 1;
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                uint4 w;
-                                w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                                w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                                w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                                w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                                *reinterpret_cast<uint4*>(srow + ((q ^ (r & 7)) << 4)) = w;
-                                if constexpr (kSplit) {
-                                    uint4 l;
-                                    l.x = pack_bf16x2(v[q * 8 + 0] - bf16_lo(w.x), v[q * 8 + 1] - bf16_hi(w.x));
-                                    l.y = pack_bf16x2(v[q * 8 + 2] - bf16_lo(w.y), v[q * 8 + 3] - bf16_hi(w.y));
-                                    l.z = pack_bf16x2(v[q * 8 + 4] - bf16_lo(w.z), v[q * 8 + 5] - bf16_hi(w.z));
-                                    l.w = pack_bf16x2(v[q * 8 + 6] - bf16_lo(w.w), v[q * 8 + 7] - bf16_hi(w.w));
-                                    *reinterpret_cast<uint4*>(srow + 16384 + ((q ^ (r & 7)) << 4)) = l;
+                        for (int pl = 0; pl < kOutPlanes; ++pl) {
+                            if (issuer) tma_store_wait_read<C::EPI_BUFS - 1>();  // buffer `buf` no longer being read
+                            named_bar_sync(1 + wg, 128);
+                            if constexpr (kOutBf16) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    uint4 w;
+                                    w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                                    w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                                    w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                                    w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                                    *reinterpret_cast<uint4*>(srow + ((q ^ (r & 7)) << 4)) = w;
+                                    if constexpr (kSplit) {  // keep the remainder for the next plane
+                                        v[q * 8 + 0] -= bf16_lo(w.x); v[q * 8 + 1] -= bf16_hi(w.x);
+                                        v[q * 8 + 2] -= bf16_lo(w.y); v[q * 8 + 3] -= bf16_hi(w.y);
+                                        v[q * 8 + 4] -= bf16_lo(w.z); v[q * 8 + 5] -= bf16_hi(w.z);
+                                        v[q * 8 + 6] -= bf16_lo(w.w); v[q * 8 + 7] -= bf16_hi(w.w);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 w = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                                    *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = w;
                                 }
                             }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 w = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                                *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = w;
+                            fence_proxy_async_smem();
+                            named_bar_sync(1 + wg, 128);
+                            if (issuer) {
+                                tma_store_5d(&p.tmC[pl], sbuf, c0, o0, o1, o2, g);
+                                tma_store_commit();
                             }
-                        }
-                        fence_proxy_async_smem();
-                        named_bar_sync(1 + wg, 128);
-                        if (issuer) {
-                            const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
-                            tma_store_5d(&p.tmC, sbuf, c0, o0, o1, o2, g);
-                            if (kSplit && kOutBf16) tma_store_5d(&p.tmC_lo, sbuf + 16384, c0, o0, o1, o2, g);
-                            tma_store_commit();
                         }
                         buf = (buf + 1) % C::EPI_BUFS;
                     }
@@ -432,8 +435,11 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     P.bias = (const float*)op.p[3];
     P.gamma = (const float*)op.p[4];
     P.resid = op.p[5];
-    P.resid_lo = op.p[9];
-    g->split = (op.p[6] != nullptr && op.p[7] != nullptr) ? 1 : 0;
+    g->split = I[30] == 3 ? 1 : 0;
+    WD_REQUIRE(I[30] == 0 || I[30] == 1 || I[30] == 3, "gemm: planes must be 1 or 3");
+    const long long a_ps = I[31], b_ps = I[32], c_ps = I[33];
+    P.resid_ps = g->split ? I[34] : 0;
+    WD_REQUIRE(!g->split || (a_ps > 0 && b_ps > 0), "gemm: precise mode needs plane strides for A and B");
 
     WD_REQUIRE(P.D0 > 0 && P.D1 > 0 && P.D2 > 0, "gemm: bad dims %d %d %d", P.D0, P.D1, P.D2);
     WD_REQUIRE(P.E0 > 0 && P.E1 > 0 && P.E2 > 0 && P.E0 * P.E1 * P.E2 <= kTileM, "gemm: bad tile %d %d %d", P.E0, P.E1, P.E2);
@@ -467,8 +473,8 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         uint64_t dims[4] = {(uint64_t)k_valid, (uint64_t)P.D0, (uint64_t)P.D1, (uint64_t)P.D2};
         uint64_t str[3] = {(uint64_t)sa0 * 2, (uint64_t)sa1 * 2, (uint64_t)sa2 * 2};
         uint32_t box[4] = {kBlockK, (uint32_t)P.E0, (uint32_t)P.E1, (uint32_t)P.E2};
-        if (encode_tmap(&P.tmA, op.p[0], 2, 4, dims, str, box, true)) return -1;
-        if (g->split && encode_tmap(&P.tmA_lo, op.p[6], 2, 4, dims, str, box, true)) return -1;
+        for (int pl = 0; pl < (g->split ? 3 : 1); ++pl)
+            if (encode_tmap(&P.tmA[pl], (const __nv_bfloat16*)op.p[0] + pl * a_ps, 2, 4, dims, str, box, true)) return -1;
     }
     // --- B: rank-2 (k_total, n)
     {
@@ -476,8 +482,8 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         uint64_t dims[2] = {(uint64_t)bk_valid, (uint64_t)P.N};
         uint64_t str[1] = {(uint64_t)ldb * 2};
         uint32_t box[2] = {kBlockK, (uint32_t)g->block_n};
-        if (encode_tmap(&P.tmB, op.p[1], 2, 2, dims, str, box, true)) return -1;
-        if (g->split && encode_tmap(&P.tmB_lo, op.p[7], 2, 2, dims, str, box, true)) return -1;
+        for (int pl = 0; pl < (g->split ? 3 : 1); ++pl)
+            if (encode_tmap(&P.tmB[pl], (const __nv_bfloat16*)op.p[1] + pl * b_ps, 2, 2, dims, str, box, true)) return -1;
     }
     // --- C: rank-5 (c, d0, d1, d2, group), box (CH, E0, E1, E2, 1)
     if (P.epi_mode == 0) {
@@ -486,14 +492,15 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         uint64_t dims[5] = {(uint64_t)cols, (uint64_t)P.D0, (uint64_t)P.D1, (uint64_t)P.D2, (uint64_t)n_groups};
         uint64_t str[4] = {(uint64_t)sc0 * eb, (uint64_t)sc1 * eb, (uint64_t)sc2 * eb, (uint64_t)(n_groups == 1 ? sc2 * P.D2 : scg) * eb};
         uint32_t box[5] = {(uint32_t)CH, (uint32_t)P.E0, (uint32_t)P.E1, (uint32_t)P.E2, 1};
-        if (encode_tmap(&P.tmC, op.p[2], eb, 5, dims, str, box, true)) return -1;
+        if (encode_tmap(&P.tmC[0], op.p[2], eb, 5, dims, str, box, true)) return -1;
         if (g->split && !g->out_f32) {
-            WD_REQUIRE(op.p[8], "gemm: split mode with bf16 output needs C_lo");
-            if (encode_tmap(&P.tmC_lo, op.p[8], eb, 5, dims, str, box, true)) return -1;
+            WD_REQUIRE(c_ps > 0, "gemm: precise mode with bf16 output needs a C plane stride");
+            for (int pl = 1; pl < 3; ++pl)
+                if (encode_tmap(&P.tmC[pl], (__nv_bfloat16*)op.p[2] + pl * c_ps, eb, 5, dims, str, box, true)) return -1;
         }
         if (n_groups == 1) P.group_cols = 1 << 30;  // never wrap
     } else {
-        P.tmC = P.tmA;  // unused, keep a valid descriptor for the prefetch
+        P.tmC[0] = P.tmA[0];  // unused, keep a valid descriptor for the prefetch
     }
 
     const int sms = device_sm_count();

@@ -15,16 +15,32 @@ struct FnOp : CompiledOp {
     int launch(cudaStream_t s) override { return fn(s); }
 };
 
-__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, float a, float b, float c, float d) {
+// store 4 fp32 values as bf16; ps > 0 = precise mode: three planes p0 + p1 + p2 (plane stride ps elements)
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, long long ps, long long idx, float a, float b, float c, float d) {
     uint2 w;
     w.x = pack_bf16x2(a, b);
     w.y = pack_bf16x2(c, d);
     *reinterpret_cast<uint2*>(hi + idx) = w;
-    if (lo) {
-        uint2 l;
-        l.x = pack_bf16x2(a - bf16_lo(w.x), b - bf16_hi(w.x));
-        l.y = pack_bf16x2(c - bf16_lo(w.y), d - bf16_hi(w.y));
-        *reinterpret_cast<uint2*>(lo + idx) = l;
+    if (ps) {
+#pragma unroll
+        for (int pl = 1; pl < 3; ++pl) {
+            a -= bf16_lo(w.x); b -= bf16_hi(w.x); c -= bf16_lo(w.y); d -= bf16_hi(w.y);
+            w.x = pack_bf16x2(a, b);
+            w.y = pack_bf16x2(c, d);
+            *reinterpret_cast<uint2*>(hi + pl * ps + idx) = w;
+        }
+    }
+}
+__device__ __forceinline__ void store_bf16x1(__nv_bfloat16* hi, long long ps, long long idx, float a) {
+    __nv_bfloat16 h = __float2bfloat16_rn(a);
+    hi[idx] = h;
+    if (ps) {
+#pragma unroll
+        for (int pl = 1; pl < 3; ++pl) {
+            a -= __bfloat162float(h);
+            h = __float2bfloat16_rn(a);
+            hi[pl * ps + idx] = h;
+        }
     }
 }
 
@@ -35,7 +51,7 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, __nv_bfloat16* l
 constexpr int kLnMaxVec = 12;  // C <= 1536
 
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, int rows, int C, int ld_in, const float* __restrict__ w,
-                                                      const float* __restrict__ b, float eps, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                                                      const float* __restrict__ b, float eps, __nv_bfloat16* out_hi, long long out_ps,
                                                       float* out_f32, int ld_out, int s2d, int W, int H) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -79,7 +95,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
             const float y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
             const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z;
             const float y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
-            if (out_hi) store_bf16x4(out_hi, out_lo, orow * ld_out + coff + c, y0, y1, y2, y3);
+            if (out_hi) store_bf16x4(out_hi, out_ps, orow * ld_out + coff + c, y0, y1, y2, y3);
             if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * C + c) = make_float4(y0, y1, y2, y3);
         }
     }
@@ -94,7 +110,7 @@ constexpr int kDwTX = 8, kDwTY = 2;
 
 __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict__ in, int B, int H, int W, int C, const float* __restrict__ wt,
                                                          const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                                         float eps, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ld_out) {
+                                                         float eps, __nv_bfloat16* out_hi, long long out_ps, int ld_out) {
     __shared__ float red[kDwTY * kDwTX][12];
     const int cg = threadIdx.x;
     const int c = cg * 4;
@@ -198,7 +214,7 @@ __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict
             const float m = mean[oy][ox], r = rstd[oy][ox];
             const float4 a = acc[oy][ox];
             const long long idx = (((long long)bi * H + y) * W + x) * ld_out + c;
-            store_bf16x4(out_hi, out_lo, idx, (a.x - m) * r * w4.x + g4.x, (a.y - m) * r * w4.y + g4.y, (a.z - m) * r * w4.z + g4.z,
+            store_bf16x4(out_hi, out_ps, idx, (a.x - m) * r * w4.x + g4.x, (a.y - m) * r * w4.y + g4.y, (a.z - m) * r * w4.z + g4.z,
                          (a.w - m) * r * w4.w + g4.w);
         }
     }
@@ -208,7 +224,7 @@ __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict
 // stem patch gather: NCHW image -> rows [B*(H/4)*(W/4), 64], k = c*16 + dy*4 + dx (48 valid, 16 zero)
 // ------------------------------------------------------------------------------------------------
 template <typename InT>
-__global__ void stem_patch_kernel(const InT* __restrict__ in, int B, int H, int W, float scale, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+__global__ void stem_patch_kernel(const InT* __restrict__ in, int B, int H, int W, float scale, __nv_bfloat16* out_hi, long long out_ps) {
     const int Wo = W / 4, Ho = H / 4;
     const long long total = (long long)B * Ho * Wo * 16;  // 16 groups of 4 k-values per row
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -221,15 +237,15 @@ __global__ void stem_patch_kernel(const InT* __restrict__ in, int B, int H, int 
             const InT* src = in + (((long long)bi * 3 + ch) * H + (py * 4 + dy)) * W + px * 4;
             a = (float)src[0] * scale; b = (float)src[1] * scale; c = (float)src[2] * scale; d = (float)src[3] * scale;
         }
-        store_bf16x4(out_hi, out_lo, m * 64 + grp * 4, a, b, c, d);
+        store_bf16x4(out_hi, out_ps, m * 64 + grp * 4, a, b, c, d);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // im2col for 3x3 stride-2 pad-1 conv, bf16 NHWC -> rows [B*Ho*Wo, 9*C], k = (ky*3+kx)*C + c
 // ------------------------------------------------------------------------------------------------
-__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ in_lo, int B, int H, int W, int C, int ld_in,
-                                 __nv_bfloat16* out, __nv_bfloat16* out_lo) {
+__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, long long in_ps, int B, int H, int W, int C, int ld_in,
+                                 __nv_bfloat16* out, long long out_ps) {
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const int vec = C / 8;
     const long long total = (long long)B * Ho * Wo * 9 * vec;
@@ -240,26 +256,25 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, const __n
         r /= 9;
         const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho), bi = (int)(r / ((long long)Wo * Ho));
         const int iy = oy * 2 + tap / 3 - 1, ix = ox * 2 + tap % 3 - 1;
-        uint4 v = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-            const long long src = (((long long)bi * H + iy) * W + ix) * ld_in + cv * 8;
-            v = *reinterpret_cast<const uint4*>(in + src);
-            if (in_lo) l = *reinterpret_cast<const uint4*>(in_lo + src);
-        }
+        const bool inb = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const long long src = (((long long)bi * H + iy) * W + ix) * ld_in + cv * 8;
         const long long dst = r * (9LL * C) + (long long)tap * C + cv * 8;
-        *reinterpret_cast<uint4*>(out + dst) = v;
-        if (out_lo) *reinterpret_cast<uint4*>(out_lo + dst) = l;
+        for (int pl = 0; pl < (out_ps ? 3 : 1); ++pl) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (inb) v = *reinterpret_cast<const uint4*>(in + pl * in_ps + src);
+            *reinterpret_cast<uint4*>(out + pl * out_ps + dst) = v;
+        }
     }
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ in, long long rows, int C, int ld_in, int ld_out, __nv_bfloat16* out, __nv_bfloat16* out_lo) {
+__global__ void cast_bf16_kernel(const float* __restrict__ in, long long rows, int C, int ld_in, int ld_out, __nv_bfloat16* out, long long out_ps) {
     const int vec = C / 4;
     const long long total = rows * vec;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long r = t / vec;
         const int c = (int)(t % vec) * 4;
         const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
-        store_bf16x4(out, out_lo, r * ld_out + c, v.x, v.y, v.z, v.w);
+        store_bf16x4(out, out_ps, r * ld_out + c, v.x, v.y, v.z, v.w);
     }
 }
 
@@ -269,7 +284,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, long long rows, i
 __global__ void __launch_bounds__(256) text_embed_kernel(const int* __restrict__ ids, int S, int L, int Hd, int pad_idx, const float* __restrict__ word,
                                                          const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ lnw,
                                                          const float* __restrict__ lnb, float eps, float* out_f32, __nv_bfloat16* out_hi,
-                                                         __nv_bfloat16* out_lo) {
+                                                         long long out_ps) {
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tok >= S * L) return;
     const int lane = threadIdx.x & 31;
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const int* __restrict__
             const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z, y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
             const long long idx = (long long)tok * Hd + c;
             *reinterpret_cast<float4*>(out_f32 + idx) = make_float4(y0, y1, y2, y3);
-            store_bf16x4(out_hi, out_lo, idx, y0, y1, y2, y3);
+            store_bf16x4(out_hi, out_ps, idx, y0, y1, y2, y3);
         }
     }
 }
@@ -328,7 +343,7 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const int* __restrict__
 // softmax(q k^T * scale + mask) v, masked keys get -inf (== HF additive float-min mask after softmax)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attn_small_kernel(const float* __restrict__ qkv, const int* __restrict__ mask, int S, int L, int heads, int ld,
-                                                         float scale, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                                                         float scale, __nv_bfloat16* out_hi, long long out_ps) {
     extern __shared__ float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = blockIdx.x * 4 + warp;
@@ -366,13 +381,8 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const float* __restrict
             o1 = fmaf(pp, V[j * 65 + lane + 32], o1);
         }
         const long long idx = (long long)(s * L + i) * Hd + h * 64;
-        __nv_bfloat16 h0 = __float2bfloat16_rn(o0), h1 = __float2bfloat16_rn(o1);
-        out_hi[idx + lane] = h0;
-        out_hi[idx + lane + 32] = h1;
-        if (out_lo) {
-            out_lo[idx + lane] = __float2bfloat16_rn(o0 - __bfloat162float(h0));
-            out_lo[idx + lane + 32] = __float2bfloat16_rn(o1 - __bfloat162float(h1));
-        }
+        store_bf16x1(out_hi, out_ps, idx + lane, o0);
+        store_bf16x1(out_hi, out_ps, idx + lane + 32, o1);
     }
 }
 
@@ -389,14 +399,14 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ in, int S, int C, i
     for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = in[(long long)row * ld_in + c] / nrm;
 }
 
-__global__ void gather_rows_kernel(const float* __restrict__ in, int S, int C, int row_stride, int ld_in, __nv_bfloat16* out, __nv_bfloat16* out_lo) {
+__global__ void gather_rows_kernel(const float* __restrict__ in, int S, int C, int row_stride, int ld_in, __nv_bfloat16* out, long long out_ps) {
     const int vec = C / 4;
     const long long total = (long long)S * vec;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long r = t / vec;
         const int c = (int)(t % vec) * 4;
         const float4 v = *reinterpret_cast<const float4*>(in + r * row_stride * ld_in + c);
-        store_bf16x4(out, out_lo, r * C + c, v.x, v.y, v.z, v.w);
+        store_bf16x4(out, out_ps, r * C + c, v.x, v.y, v.z, v.w);
     }
 }
 
@@ -405,16 +415,13 @@ __global__ void gather_rows_kernel(const float* __restrict__ in, int S, int C, i
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fold_text_kernel(const float* __restrict__ text, int K, int C, int normalize, const float* __restrict__ g,
                                                         const float* __restrict__ hh, const float* __restrict__ logit_scale, const float* __restrict__ bias,
-                                                        __nv_bfloat16* W, __nv_bfloat16* W_lo, float* bprime) {
+                                                        __nv_bfloat16* W, long long W_ps, float* bprime) {
     __shared__ float red[8];
     __shared__ float bc;
     const int k = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= K) {  // zero padding rows
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            W[(long long)k * C + c] = __float2bfloat16_rn(0.f);
-            if (W_lo) W_lo[(long long)k * C + c] = __float2bfloat16_rn(0.f);
-        }
+        for (int c = threadIdx.x; c < C; c += blockDim.x) store_bf16x1(W, W_ps, (long long)k * C + c, 0.f);
         if (threadIdx.x == 0) bprime[k] = 0.f;
         return;
     }
@@ -440,9 +447,7 @@ __global__ void __launch_bounds__(256) fold_text_kernel(const float* __restrict_
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float tn = t[c] * inv;
         const float wv = tn * g[c] * es;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
-        W[(long long)k * C + c] = hi;
-        if (W_lo) W_lo[(long long)k * C + c] = __float2bfloat16_rn(wv - __bfloat162float(hi));
+        store_bf16x1(W, W_ps, (long long)k * C + c, wv);
         dot += hh[c] * tn;
     }
     dot = warp_sum(dot);
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(256) fold_text_kernel(const float* __restrict_
 // kept proposals -> BN'd embedding rows (generate_proposal.py:1129, 1209-1212)
 struct GatherEmbedArgs {
     const __nv_bfloat16* emb[3];
-    const __nv_bfloat16* emb_lo[3];
+    long long emb_ps[3];
     int lvl_size[3];
     int nlevels, B, C, max_keep;
 };
@@ -478,10 +483,10 @@ __global__ void gather_embed_kernel(GatherEmbedArgs a, const int* __restrict__ k
     }
     const long long row = (long long)b * a.lvl_size[lvl] + anchor;
     const __nv_bfloat16* e = a.emb[lvl] + row * a.C;
-    const __nv_bfloat16* el = a.emb_lo[lvl] ? a.emb_lo[lvl] + row * a.C : nullptr;
+    const long long eps_ = a.emb_ps[lvl];
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
         float v = __bfloat162float(e[c]);
-        if (el) v += __bfloat162float(el[c]);
+        if (eps_) v += __bfloat162float(e[eps_ + c]) + __bfloat162float(e[2 * eps_ + c]);
         o[c] = v * g[lvl * a.C + c] + hh[lvl * a.C + c];
     }
 }
@@ -511,7 +516,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             WD_REQUIRE(ld_in % 4 == 0 && ld_out % 4 == 0, "ln_rows: ld must be a multiple of 4");
             const float* in = (const float*)P[0];
             const float *w = (const float*)P[2], *b = (const float*)P[3];
-            __nv_bfloat16 *oh = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[5];
+            __nv_bfloat16* oh = (__nv_bfloat16*)P[1];
+            const long long ol = I[30];
             float* of = (float*)P[6];
             f->fn = [=](cudaStream_t s) {
                 ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
@@ -527,7 +533,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             WD_REQUIRE(B > 0 && H > 0 && W > 0 && C % 4 == 0 && C / 4 <= 384, "dwconv_ln: bad shape");
             WD_REQUIRE(P[0] && P[1] && P[2] && P[3] && P[4] && P[5], "dwconv_ln: null pointer");
             const float* in = (const float*)P[0];
-            __nv_bfloat16 *oh = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[6];
+            __nv_bfloat16* oh = (__nv_bfloat16*)P[1];
+            const long long ol = I[30];
             const float *wt = (const float*)P[2], *bs = (const float*)P[3], *lw = (const float*)P[4], *lb = (const float*)P[5];
             const int threads = ((C / 4 + 31) / 32) * 32;
             const int ld_out = I[4] > 0 ? I[4] : C;
@@ -547,7 +554,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             WD_REQUIRE(B > 0 && H % 4 == 0 && W % 4 == 0 && layout == 0 && (dt == 0 || dt == 2), "stem_patch: bad arguments");
             WD_REQUIRE(P[0] && P[1], "stem_patch: null pointer");
             const void* in = P[0];
-            __nv_bfloat16 *oh = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[2];
+            __nv_bfloat16* oh = (__nv_bfloat16*)P[1];
+            const long long ol = I[30];
             const long long total = (long long)B * (H / 4) * (W / 4) * 16;
             f->fn = [=](cudaStream_t s) {
                 if (dt == 0) stem_patch_kernel<uint8_t><<<grid_for(total, 256), 256, 0, s>>>((const uint8_t*)in, B, H, W, scale, oh, ol);
@@ -561,8 +569,10 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         case WD_OP_IM2COL_S2: {
             const int B = I[0], H = I[1], W = I[2], C = I[3], ld_in = I[4];
             WD_REQUIRE(B > 0 && H > 0 && W > 0 && C % 8 == 0 && ld_in % 8 == 0 && P[0] && P[1], "im2col_s2: bad arguments");
-            const __nv_bfloat16 *in = (const __nv_bfloat16*)P[0], *inl = (const __nv_bfloat16*)P[2];
-            __nv_bfloat16 *o = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[3];
+            const __nv_bfloat16* in = (const __nv_bfloat16*)P[0];
+            __nv_bfloat16* o = (__nv_bfloat16*)P[1];
+            const long long inl = I[31], ol = I[30];
+            WD_REQUIRE((inl == 0) == (ol == 0), "im2col_s2: both or neither plane stride");
             const long long total = (long long)B * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * 9 * (C / 8);
             f->fn = [=](cudaStream_t s) {
                 im2col_s2_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, inl, B, H, W, C, ld_in, o, ol);
@@ -576,7 +586,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const int rows = I[0], C = I[1], ld_in = I[2], ld_out = I[3];
             WD_REQUIRE(rows > 0 && C % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && P[0] && P[1], "cast_bf16: bad arguments");
             const float* in = (const float*)P[0];
-            __nv_bfloat16 *o = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[2];
+            __nv_bfloat16* o = (__nv_bfloat16*)P[1];
+            const long long ol = I[30];
             f->fn = [=](cudaStream_t s) {
                 cast_bf16_kernel<<<grid_for((long long)rows * (C / 4), 256), 256, 0, s>>>(in, rows, C, ld_in, ld_out, o, ol);
                 WD_CHECK_CUDA(cudaGetLastError());
@@ -593,7 +604,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const int* ids = (const int*)P[0];
             const float *word = (const float*)P[2], *pos = (const float*)P[3], *type = (const float*)P[4], *lw = (const float*)P[5], *lb = (const float*)P[6];
             float* of = (float*)P[7];
-            __nv_bfloat16 *oh = (__nv_bfloat16*)P[8], *ol = (__nv_bfloat16*)P[9];
+            __nv_bfloat16* oh = (__nv_bfloat16*)P[8];
+            const long long ol = I[30];
             f->fn = [=](cudaStream_t s) {
                 text_embed_kernel<<<(S * L + 7) / 8, 256, 0, s>>>(ids, S, L, Hd, pad_idx, word, pos, type, lw, lb, eps, of, oh, ol);
                 WD_CHECK_CUDA(cudaGetLastError());
@@ -608,7 +620,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             WD_REQUIRE(S > 0 && L > 0 && L <= 32 && hd == 64 && heads > 0 && P[0] && P[1] && P[2], "attn_small: needs L <= 32 and head_dim == 64");
             const float* qkv = (const float*)P[0];
             const int* mask = (const int*)P[1];
-            __nv_bfloat16 *oh = (__nv_bfloat16*)P[2], *ol = (__nv_bfloat16*)P[3];
+            __nv_bfloat16* oh = (__nv_bfloat16*)P[2];
+            const long long ol = I[30];
             const int smem = 4 * 3 * L * 65 * (int)sizeof(float);
             f->fn = [=](cudaStream_t s) {
                 static bool attr = false;
@@ -640,7 +653,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const int S = I[0], C = I[1], rs = I[2], ld_in = I[3];
             WD_REQUIRE(S > 0 && C % 4 == 0 && ld_in % 4 == 0 && P[0] && P[1], "gather_rows: bad arguments");
             const float* in = (const float*)P[0];
-            __nv_bfloat16 *o = (__nv_bfloat16*)P[1], *ol = (__nv_bfloat16*)P[2];
+            __nv_bfloat16* o = (__nv_bfloat16*)P[1];
+            const long long ol = I[30];
             f->fn = [=](cudaStream_t s) {
                 gather_rows_kernel<<<grid_for((long long)S * (C / 4), 256), 256, 0, s>>>(in, S, C, rs, ld_in, o, ol);
                 WD_CHECK_CUDA(cudaGetLastError());
@@ -654,7 +668,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             WD_REQUIRE(K > 0 && C > 0 && Kpad >= K, "fold_text: bad shape");
             for (int k = 0; k <= 6; ++k) WD_REQUIRE(P[k], "fold_text: null pointer %d", k);
             const float *t = (const float*)P[0], *g = (const float*)P[1], *hh = (const float*)P[2], *ls = (const float*)P[3], *bi = (const float*)P[4];
-            __nv_bfloat16 *Wd = (__nv_bfloat16*)P[5], *Wl = (__nv_bfloat16*)P[7];
+            __nv_bfloat16* Wd = (__nv_bfloat16*)P[5];
+            const long long Wl = I[30];
             float* bp = (float*)P[6];
             f->fn = [=](cudaStream_t s) {
                 fold_text_kernel<<<Kpad, 256, 0, s>>>(t, K, C, normalize, g, hh, ls, bi, Wd, Wl, bp);
@@ -671,7 +686,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             for (int l = 0; l < 3; ++l) {
                 a.lvl_size[l] = I[5 + l];
                 a.emb[l] = (const __nv_bfloat16*)P[l];
-                a.emb_lo[l] = (const __nv_bfloat16*)P[8 + l];
+                a.emb_ps[l] = I[30 + l];
             }
             WD_REQUIRE(P[0] && P[3] && P[4] && P[5] && P[6] && P[7], "gather_embed: null pointer");
             const int* ka = (const int*)P[3];

@@ -12,6 +12,50 @@ from . import _lib as L
 from ._lib import WdOp
 
 
+class P3:
+    """A bf16 tensor view `t` that is plane 0 of a 3-plane precise tensor (value = p0 + p1 + p2); the other
+    planes live `ps` elements further in the same allocation.  ps == 0: an ordinary single-plane tensor."""
+
+    def __init__(self, t, ps=0):
+        self.t, self.ps = t, int(ps)
+
+    @staticmethod
+    def from_f32(x, device=None):
+        """Split an fp32 tensor into three bf16 planes (test / weight-upload helper)."""
+        x = x.float()
+        base = torch.empty((3,) + tuple(x.shape), dtype=torch.bfloat16)
+        r = x.clone()
+        for i in range(3):
+            base[i] = r.to(torch.bfloat16)
+            r = r - base[i].float()
+        if device is not None:
+            base = base.to(device)
+        return P3(base[0], base.stride(0))
+
+    @staticmethod
+    def zeros(shape, device, planes3):
+        if planes3:
+            base = torch.zeros((3,) + tuple(shape), dtype=torch.bfloat16, device=device)
+            return P3(base[0], base.stride(0))
+        return P3(torch.zeros(shape, dtype=torch.bfloat16, device=device), 0)
+
+    def value(self):
+        """fp32 reconstruction (sum of planes)."""
+        if not self.ps:
+            return self.t.float()
+        planes = [self.t.as_strided(self.t.shape, self.t.stride(), self.t.storage_offset() + i * self.ps) for i in range(3)]
+        return planes[0].float() + planes[1].float() + planes[2].float()
+
+    def view(self, fn):
+        return P3(fn(self.t), self.ps)
+
+
+def _tp(x):
+    if x is None:
+        return None, 0
+    return (x.t, x.ps) if isinstance(x, P3) else (x, 0)
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -50,10 +94,11 @@ def pick_block_n(N, out_f32=False, split=False):
 
 def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, block_n=None, out_f32=False,
              act=L.ACT_NONE, bias=None, gamma=None, resid=None, ld_res=0, alpha=1.0, group_cols=None, n_groups=1,
-             c_gstride=0, dfl=False, A_lo=None, W_lo=None, C_lo=None, resid_lo=None, group_valid=0, k_valid=0, bk_valid=0):
+             c_gstride=0, dfl=False, a_ps=0, w_ps=0, c_ps=0, r_ps=0, group_valid=0, k_valid=0, bk_valid=0):
     op = WdOp()
     op.kind = L.OP_GEMM
-    split = A_lo is not None and W_lo is not None
+    split = bool(a_ps) and bool(w_ps)
+    assert bool(a_ps) == bool(w_ps), "precise mode needs 3-plane A and W"
     if block_n is None:
         block_n = 64 if dfl else pick_block_n(N, out_f32, split)
     I = op.i
@@ -72,8 +117,10 @@ def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, 
     I[24] = 1 if dfl else 0
     I[25], I[26] = (3, 1) if ntaps == 9 else (1, 0)
     I[27], I[28], I[29] = group_valid, k_valid, bk_valid
+    I[30] = 3 if split else 1
+    I[31], I[32], I[33], I[34] = a_ps, w_ps, c_ps, r_ps
     op.f[0] = alpha
-    for k, t in enumerate((A, W, C, bias, gamma, resid, A_lo, W_lo, C_lo, resid_lo)):
+    for k, t in enumerate((A, W, C, bias, gamma, resid)):
         op.p[k] = _ptr(t)
     return op
 
@@ -83,9 +130,10 @@ def _flat_strides(ld, rows):
     return (ld, big, big)
 
 
-def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, dfl=False,
-           A_lo=None, W_lo=None, C_lo=None, resid_lo=None):
-    """C[M, N] = epi(A[M, K] @ W[N, K]^T); A / C / resid may be column slices of wider row-major buffers."""
+def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, dfl=False):
+    """C[M, N] = epi(A[M, K] @ W[N, K]^T); A / C / resid may be column slices of wider row-major buffers.
+    A, W (and bf16 C / resid) may be P3 three-plane tensors (precise mode)."""
+    (A, a_ps), (W, w_ps), (C, c_ps), (resid, r_ps) = _tp(A), _tp(W), _tp(C), _tp(resid)
     _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
     M, K = A.shape
     N = W.shape[0]
@@ -104,13 +152,13 @@ def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_N
         ld_res = resid.stride(0)
     return gemm_raw(A=A, W=W, C=C, dims=(M, 1, 1), tile=(128, 1, 1), Kc=Kc, N=N, a_strides=_flat_strides(A.stride(0), M),
                     ldb=W.stride(0), c_strides=c_str, block_n=block_n, out_f32=out_f32, act=act, bias=bias, gamma=gamma,
-                    resid=resid, ld_res=ld_res, alpha=alpha, dfl=dfl, A_lo=A_lo, W_lo=W_lo, C_lo=C_lo, resid_lo=resid_lo,
+                    resid=resid, ld_res=ld_res, alpha=alpha, dfl=dfl, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps, r_ps=r_ps,
                     k_valid=K, bk_valid=K)
 
 
-def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, A_lo=None, W_lo=None,
-            C_lo=None, resid_lo=None):
-    """3x3 stride-1 pad-1 convolution as 9 shifted TMA brick loads.  A [B,H,W,Cin], W [N, 9*Cin] (tap-major)."""
+def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None):
+    """3x3 stride-1 pad-1 convolution as 9 shifted TMA brick loads.  A [B,H,W,Cin], W [N, 9*pad64(Cin)] (tap-major)."""
+    (A, a_ps), (W, w_ps), (C, c_ps), (resid, r_ps) = _tp(A), _tp(W), _tp(C), _tp(resid)
     _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
     B, H, Wd, Cin = A.shape
     N = W.shape[0]
@@ -125,14 +173,14 @@ def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_
     return gemm_raw(A=A, W=W, C=C, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Kc, k_valid=Cin, ntaps=9, N=N,
                     a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
                     c_strides=(C.stride(2), C.stride(1), C.stride(0)), block_n=block_n, out_f32=C.dtype == torch.float32,
-                    act=act, bias=bias, resid=resid, ld_res=ld_res, alpha=alpha, A_lo=A_lo, W_lo=W_lo, C_lo=C_lo,
-                    resid_lo=resid_lo)
+                    act=act, bias=bias, resid=resid, ld_res=ld_res, alpha=alpha, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps, r_ps=r_ps)
 
 
-def deconv2x2(A, W, C, bias2, *, A_lo=None, W_lo=None, C_lo=None):
+def deconv2x2(A, W, C, bias2):
     """ConvTranspose2d(k=2, s=2) as two GEMMs (dy = 0, 1) whose TMA stores scatter into the 2x upsampled map.
     A [B,H,W,Cin]; W [4*Co, Cin] rows ordered (dy, dx, co); C [B,2H,2W,Co] (may be a channel slice);
-    bias2 f32 [2*Co] = bias repeated for dx = 0, 1."""
+    bias2 f32 [2*Cg] = bias repeated for dx = 0, 1."""
+    (A, a_ps), (W, w_ps), (C, c_ps) = _tp(A), _tp(W), _tp(C)
     _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
     B, H, Wd, Cin = A.shape
     Co = C.shape[3]
@@ -147,13 +195,12 @@ def deconv2x2(A, W, C, bias2, *, A_lo=None, W_lo=None, C_lo=None):
         ops.append(gemm_raw(A=A, W=Wdy, C=Cdy, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Kc, k_valid=Cin, bk_valid=Cin,
                             N=2 * Cg, a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
                             c_strides=(2 * C.stride(2), 2 * C.stride(1), C.stride(0)), group_cols=Cg, group_valid=Co,
-                            n_groups=2, c_gstride=C.stride(2), bias=bias2, out_f32=False,
-                            A_lo=A_lo, W_lo=None if W_lo is None else W_lo[dy * 2 * Cg:(dy + 1) * 2 * Cg],
-                            C_lo=None if C_lo is None else C_lo[:, dy]))
+                            n_groups=2, c_gstride=C.stride(2), bias=bias2, out_f32=False, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps))
     return ops
 
 
-def ln_rows(x, w, b, eps, *, out_bf16=None, out_lo=None, out_f32=None, s2d_hw=None):
+def ln_rows(x, w, b, eps, *, out_bf16=None, out_f32=None, s2d_hw=None):
+    out_bf16, o_ps = _tp(out_bf16)
     _chk(x, torch.float32, "x")
     rows, C = x.shape
     op = WdOp()
@@ -165,28 +212,32 @@ def ln_rows(x, w, b, eps, *, out_bf16=None, out_lo=None, out_f32=None, s2d_hw=No
         op.i[4], op.i[5], op.i[6] = 1, W, H
         assert out_bf16 is not None and out_bf16.shape == (rows // 4, 4 * C)
     op.i[8] = out_bf16.stride(0) if out_bf16 is not None else C
+    op.i[30] = o_ps
     op.f[0] = eps
     if out_f32 is not None:
         assert out_f32.is_contiguous() and out_f32.shape == (rows, C)
-    for k, t in ((0, x), (1, out_bf16), (2, w), (3, b), (5, out_lo), (6, out_f32)):
+    for k, t in ((0, x), (1, out_bf16), (2, w), (3, b), (6, out_f32)):
         op.p[k] = _ptr(t)
     return op
 
 
-def dwconv_ln(x, out, w49, bias, ln_w, ln_b, eps, out_lo=None):
+def dwconv_ln(x, out, w49, bias, ln_w, ln_b, eps):
+    out, o_ps = _tp(out)
     _chk(x, torch.float32, "x")
     B, H, W, C = x.shape
     assert x.is_contiguous() and out.shape == (B * H * W, C) and out.stride(1) == 1 and w49.shape == (49, C)
     op = WdOp()
     op.kind = L.OP_DWCONV_LN
     op.i[0], op.i[1], op.i[2], op.i[3], op.i[4] = B, H, W, C, out.stride(0)
+    op.i[30] = o_ps
     op.f[0] = eps
-    for k, t in enumerate((x, out, w49, bias, ln_w, ln_b, out_lo)):
+    for k, t in enumerate((x, out, w49, bias, ln_w, ln_b)):
         op.p[k] = _ptr(t)
     return op
 
 
-def stem_patch(img, out, scale=1.0, out_lo=None):
+def stem_patch(img, out, scale=1.0):
+    out, o_ps = _tp(out)
     B, C3, H, W = img.shape
     assert C3 == 3 and img.is_contiguous() and out.shape == (B * (H // 4) * (W // 4), 64) and out.is_contiguous()
     op = WdOp()
@@ -195,12 +246,14 @@ def stem_patch(img, out, scale=1.0, out_lo=None):
     op.i[3] = 0 if img.dtype == torch.uint8 else 2
     assert img.dtype in (torch.uint8, torch.float32)
     op.f[0] = scale
-    for k, t in enumerate((img, out, out_lo)):
+    op.i[30] = o_ps
+    for k, t in enumerate((img, out)):
         op.p[k] = _ptr(t)
     return op
 
 
-def im2col_s2(x, out, x_lo=None, out_lo=None):
+def im2col_s2(x, out):
+    (x, x_ps), (out, o_ps) = _tp(x), _tp(out)
     _chk(x, torch.bfloat16, "x")
     B, H, W, C = x.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
@@ -209,23 +262,27 @@ def im2col_s2(x, out, x_lo=None, out_lo=None):
     op = WdOp()
     op.kind = L.OP_IM2COL_S2
     op.i[0], op.i[1], op.i[2], op.i[3], op.i[4] = B, H, W, C, x.stride(2)
-    for k, t in enumerate((x, out, x_lo, out_lo)):
+    op.i[30], op.i[31] = o_ps, x_ps
+    for k, t in enumerate((x, out)):
         op.p[k] = _ptr(t)
     return op
 
 
-def cast_bf16(x, out, out_lo=None):
+def cast_bf16(x, out):
+    out, o_ps = _tp(out)
     _chk(x, torch.float32, "x")
     rows, C = x.shape
     op = WdOp()
     op.kind = L.OP_CAST_BF16
     op.i[0], op.i[1], op.i[2], op.i[3] = rows, C, x.stride(0), out.stride(0)
-    for k, t in enumerate((x, out, out_lo)):
+    op.i[30] = o_ps
+    for k, t in enumerate((x, out)):
         op.p[k] = _ptr(t)
     return op
 
 
-def text_embed(ids, word, pos, typ, ln_w, ln_b, eps, pad_idx, out_f32, out_bf16, out_lo=None):
+def text_embed(ids, word, pos, typ, ln_w, ln_b, eps, pad_idx, out_f32, out_bf16):
+    out_bf16, o_ps = _tp(out_bf16)
     S, Lt = ids.shape
     assert ids.dtype == torch.int32 and ids.is_contiguous()
     Hd = word.shape[1]
@@ -233,19 +290,22 @@ def text_embed(ids, word, pos, typ, ln_w, ln_b, eps, pad_idx, out_f32, out_bf16,
     op.kind = L.OP_TEXT_EMBED
     op.i[0], op.i[1], op.i[2], op.i[3] = S, Lt, Hd, pad_idx
     op.f[0] = eps
-    for k, t in ((0, ids), (2, word), (3, pos), (4, typ), (5, ln_w), (6, ln_b), (7, out_f32), (8, out_bf16), (9, out_lo)):
+    op.i[30] = o_ps
+    for k, t in ((0, ids), (2, word), (3, pos), (4, typ), (5, ln_w), (6, ln_b), (7, out_f32), (8, out_bf16)):
         op.p[k] = _ptr(t)
     return op
 
 
-def attn_small(qkv, mask, out, heads, scale, out_lo=None):
+def attn_small(qkv, mask, out, heads, scale):
+    out, o_ps = _tp(out)
     S, Lt = mask.shape
     assert mask.dtype == torch.int32 and qkv.dtype == torch.float32 and qkv.is_contiguous()
     op = WdOp()
     op.kind = L.OP_ATTN_SMALL
     op.i[0], op.i[1], op.i[2], op.i[3], op.i[4] = S, Lt, heads, 64, qkv.shape[1]
     op.f[0] = scale
-    for k, t in enumerate((qkv, mask, out, out_lo)):
+    op.i[30] = o_ps
+    for k, t in enumerate((qkv, mask, out)):
         op.p[k] = _ptr(t)
     return op
 
@@ -258,36 +318,40 @@ def l2norm_rows(x, out):
     return op
 
 
-def gather_rows(x, out, S, row_stride, out_lo=None):
+def gather_rows(x, out, S, row_stride):
+    out, o_ps = _tp(out)
     op = WdOp()
     op.kind = L.OP_GATHER_ROWS
     op.i[0], op.i[1], op.i[2], op.i[3] = S, x.shape[1], row_stride, x.stride(0)
-    for k, t in enumerate((x, out, out_lo)):
+    op.i[30] = o_ps
+    for k, t in enumerate((x, out)):
         op.p[k] = _ptr(t)
     return op
 
 
-def fold_text(text, bn_g, bn_h, logit_scale, bias, Wout, bout, normalize, Wout_lo=None):
+def fold_text(text, bn_g, bn_h, logit_scale, bias, Wout, bout, normalize):
+    Wout, w_ps = _tp(Wout)
     K, C = text.shape
     assert text.dtype == torch.float32 and text.is_contiguous() and Wout.shape[1] == C and Wout.is_contiguous()
     op = WdOp()
     op.kind = L.OP_FOLD_TEXT
     op.i[0], op.i[1], op.i[2], op.i[3] = K, C, 1 if normalize else 0, Wout.shape[0]
-    for k, t in enumerate((text, bn_g, bn_h, logit_scale, bias, Wout, bout, Wout_lo)):
+    op.i[30] = w_ps
+    for k, t in enumerate((text, bn_g, bn_h, logit_scale, bias, Wout, bout)):
         op.p[k] = _ptr(t)
     return op
 
 
-def gather_embed(embeds, keep_anchor, counts, bn_g, bn_h, out, embeds_lo=None):
+def gather_embed(embeds, keep_anchor, counts, bn_g, bn_h, out):
     B, max_keep, C = out.shape
     op = WdOp()
     op.kind = L.OP_GATHER_EMBED
     op.i[0], op.i[2], op.i[3], op.i[4] = B, C, max_keep, len(embeds)
     for l, e in enumerate(embeds):
+        e, e_ps = _tp(e)
         op.i[5 + l] = e.shape[0] // B
+        op.i[30 + l] = e_ps
         op.p[l] = _ptr(e)
-        if embeds_lo is not None:
-            op.p[8 + l] = _ptr(embeds_lo[l])
     for k, t in ((3, keep_anchor), (4, counts), (5, bn_g), (6, bn_h), (7, out)):
         op.p[k] = _ptr(t)
     return op

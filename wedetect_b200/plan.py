@@ -19,34 +19,37 @@ import torch
 
 from . import _lib as L
 from . import ops, schema
+from .ops import P3
 
 BF16, F32 = torch.bfloat16, torch.float32
 
 
 class Act:
-    """A bf16 activation [rows, C] (+ optional low plane) with NHWC geometry."""
+    """A bf16 activation [rows, C] with NHWC geometry; `ps` > 0 = three-plane precise tensor (ops.P3)."""
 
-    def __init__(self, hi, lo, B, H, W):
-        self.hi, self.lo, self.B, self.H, self.W = hi, lo, B, H, W
+    def __init__(self, t, ps, B, H, W):
+        self.t, self.ps, self.B, self.H, self.W = t, ps, B, H, W
 
     @property
     def C(self):
-        return self.hi.shape[1]
+        return self.t.shape[1]
 
     def cols(self, c0, c1):
-        return Act(self.hi[:, c0:c1], None if self.lo is None else self.lo[:, c0:c1], self.B, self.H, self.W)
+        return Act(self.t[:, c0:c1], self.ps, self.B, self.H, self.W)
 
-    def _v4(self, t):
+    @property
+    def p3(self):
+        return P3(self.t, self.ps)
+
+    @property
+    def p3_4d(self):
+        t = self.t
         ld = t.stride(0)
-        return t.as_strided((self.B, self.H, self.W, t.shape[1]), (self.H * self.W * ld, self.W * ld, ld, 1), t.storage_offset())
+        v = t.as_strided((self.B, self.H, self.W, t.shape[1]), (self.H * self.W * ld, self.W * ld, ld, 1), t.storage_offset())
+        return P3(v, self.ps)
 
-    @property
-    def hi4(self):
-        return self._v4(self.hi)
-
-    @property
-    def lo4(self):
-        return None if self.lo is None else self._v4(self.lo)
+    def value(self):
+        return self.p3.value()
 
 
 class VisionPlan:
@@ -80,42 +83,33 @@ class VisionPlan:
         return t
 
     def _act(self, name, B, H, W, C):
-        hi = torch.zeros(B * H * W, C, dtype=BF16, device=self.dev)
-        lo = torch.zeros_like(hi) if self.precise else None
-        a = Act(hi, lo, B, H, W)
+        q = P3.zeros((B * H * W, C), self.dev, self.precise)
+        a = Act(q.t, q.ps, B, H, W)
         self.bufs[name] = a
         return a
 
-    def _view_act(self, base_hi, base_lo, rows, C, B, H, W):
-        hi = base_hi.view(-1)[: rows * C].view(rows, C)
-        lo = None if base_lo is None else base_lo.view(-1)[: rows * C].view(rows, C)
-        return Act(hi, lo, B, H, W)
+    def _view_act(self, scratch, rows, C, B, H, W):
+        """A [rows, C] activation carved out of a flat scratch P3 (all planes keep the scratch's plane stride)."""
+        return Act(scratch.t[: rows * C].view(rows, C), scratch.ps, B, H, W)
 
     def _mat(self, name):
         return self.Wt.mat(name)
 
     # ------------------------------------------------------------------ op helpers
     def _linear(self, a, wname, out, *, bias=None, act=L.ACT_NONE, gamma=None, resid=None, alpha=1.0, dfl=False):
-        w, wlo = self._mat(wname)
-        if isinstance(out, Act):
-            C, Clo = out.hi, out.lo
-        else:
-            C, Clo = out, None
-        r, rlo = (resid.hi, resid.lo) if isinstance(resid, Act) else (resid, None)
-        self.ops.append(ops.linear(a.hi, w, C, bias=bias, gamma=gamma, resid=r, alpha=alpha, act=act, dfl=dfl,
-                                   A_lo=a.lo, W_lo=wlo if self.precise else None, C_lo=Clo, resid_lo=rlo))
+        C = out.p3 if isinstance(out, Act) else out
+        r = resid.p3 if isinstance(resid, Act) else resid
+        self.ops.append(ops.linear(a.p3, self._mat(wname), C, bias=bias, gamma=gamma, resid=r, alpha=alpha, act=act, dfl=dfl))
 
     def _conv3x3(self, a, wname, out, *, bias, act, resid=None, alpha=1.0):
-        w, wlo = self._mat(wname)
-        self.ops.append(ops.conv3x3(a.hi4, w, out.hi4, bias=bias, act=act, resid=None if resid is None else resid.hi4, alpha=alpha,
-                                    A_lo=a.lo4, W_lo=wlo if self.precise else None, C_lo=out.lo4,
-                                    resid_lo=None if resid is None else resid.lo4))
+        self.ops.append(ops.conv3x3(a.p3_4d, self._mat(wname), out.p3_4d, bias=bias, act=act,
+                                    resid=None if resid is None else resid.p3_4d, alpha=alpha))
 
     def _conv3x3_s2(self, a, wname, out, *, bias, act):
         """3x3 stride-2: im2col gather then a plain GEMM (4 small sites in the neck)."""
         Ho, Wo = (a.H - 1) // 2 + 1, (a.W - 1) // 2 + 1
         col = self._act(f"im2col.{wname}", a.B, Ho, Wo, 9 * a.C)
-        self.ops.append(ops.im2col_s2(a.hi4, col.hi, a.lo4, col.lo))
+        self.ops.append(ops.im2col_s2(a.p3_4d, col.p3))
         self._linear(col, wname, out, bias=bias, act=act)
 
     def _cba1x1(self, a, name, out, act):
@@ -129,14 +123,12 @@ class VisionPlan:
         ws = [self.W // 4, self.W // 8, self.W // 16, self.W // 32]
         rows = [B * h * w for h, w in zip(hs, ws)]
         # scratch shared by all stages (stage 0 is the largest)
-        scratch_ln = torch.zeros(max(r * d for r, d in zip(rows, dims)), dtype=BF16, device=self.dev)
-        scratch_hid = torch.zeros(max(r * 4 * d for r, d in zip(rows, dims)), dtype=BF16, device=self.dev)
-        scratch_ln_lo = torch.zeros_like(scratch_ln) if self.precise else None
-        scratch_hid_lo = torch.zeros_like(scratch_hid) if self.precise else None
-        self.keep += [scratch_ln, scratch_hid, scratch_ln_lo, scratch_hid_lo]
+        scratch_ln = P3.zeros((max(r * d for r, d in zip(rows, dims)),), self.dev, self.precise)
+        scratch_hid = P3.zeros((max(r * 4 * d for r, d in zip(rows, dims)),), self.dev, self.precise)
+        self.keep += [scratch_ln, scratch_hid]
         # stem
         patch = self._act("stem.patch", B, hs[0], ws[0], 64)
-        self.ops.append(ops.stem_patch(self.image, patch.hi, 1.0, patch.lo))
+        self.ops.append(ops.stem_patch(self.image, patch.p3, 1.0))
         x = self._f32("x0", rows[0], dims[0])
         self._linear(patch, "stem.w", x, bias=W_["stem.b"])
         self.ops.append(ops.ln_rows(x, W_["stem.ln_w"], W_["stem.ln_b"], schema.LN_EPS, out_f32=x))
@@ -144,21 +136,21 @@ class VisionPlan:
         for s in range(4):
             C, M = dims[s], rows[s]
             if s > 0:
-                s2d = self._view_act(scratch_hid, scratch_hid_lo, M, 4 * dims[s - 1], B, hs[s], ws[s])
-                self.ops.append(ops.ln_rows(x, W_[f"down{s}.ln_w"], W_[f"down{s}.ln_b"], schema.LN_EPS, out_bf16=s2d.hi, out_lo=s2d.lo,
+                s2d = self._view_act(scratch_hid, M, 4 * dims[s - 1], B, hs[s], ws[s])
+                self.ops.append(ops.ln_rows(x, W_[f"down{s}.ln_w"], W_[f"down{s}.ln_b"], schema.LN_EPS, out_bf16=s2d.p3,
                                             s2d_hw=(hs[s - 1], ws[s - 1])))
                 x = self._f32(f"x{s}", M, C)
                 self._linear(s2d, f"down{s}.w", x, bias=W_[f"down{s}.b"])
-            t_ln = self._view_act(scratch_ln, scratch_ln_lo, M, C, B, hs[s], ws[s])
-            t_hid = self._view_act(scratch_hid, scratch_hid_lo, M, 4 * C, B, hs[s], ws[s])
+            t_ln = self._view_act(scratch_ln, M, C, B, hs[s], ws[s])
+            t_hid = self._view_act(scratch_hid, M, 4 * C, B, hs[s], ws[s])
             x4 = x.view(B, hs[s], ws[s], C)
             for j in range(depths[s]):
                 q = f"s{s}.b{j}."
-                self.ops.append(ops.dwconv_ln(x4, t_ln.hi, W_[q + "dw_w"], W_[q + "dw_b"], W_[q + "ln_w"], W_[q + "ln_b"], schema.LN_EPS, t_ln.lo))
+                self.ops.append(ops.dwconv_ln(x4, t_ln.p3, W_[q + "dw_w"], W_[q + "dw_b"], W_[q + "ln_w"], W_[q + "ln_b"], schema.LN_EPS))
                 self._linear(t_ln, q + "w1", t_hid, bias=W_[q + "b1"], act=L.ACT_GELU)
                 self._linear(t_hid, q + "w2", x, bias=W_[q + "b2"], gamma=W_[q + "gamma"], resid=x, alpha=1.0)
             c = self._act(f"c{s + 1}", B, hs[s], ws[s], C)
-            self.ops.append(ops.cast_bf16(x, c.hi, c.lo))
+            self.ops.append(ops.cast_bf16(x, c.p3))
             self.c_feats.append(c)
         self.stage_x = [self.bufs[f"x{s}"] for s in range(4)]
 
@@ -166,7 +158,7 @@ class VisionPlan:
     def _bepc3(self, name, x, out, n):
         """CSPStackRep (yolo_world_pafpn.py:631-647): cv3(cat(m(cv1 x), cv2 x)); out is the destination Act."""
         W_ = self.Wt
-        c_ = W_.mat(f"neck.{name}.cv1.w")[0].shape[0]
+        c_ = W_.mat(f"neck.{name}.cv1.w").t.shape[0]
         cat = self._act(f"{name}.cat", x.B, x.H, x.W, 2 * c_)
         a = self._act(f"{name}.a0", x.B, x.H, x.W, c_)
         b = self._act(f"{name}.a1", x.B, x.H, x.W, c_)
@@ -185,11 +177,10 @@ class VisionPlan:
     def _bifusion(self, name, top, mid, low, out):
         """BiFusion (yolo_world_pafpn.py:692-715): cv3(cat(up(top), cv1(mid), down(cv2(low))))."""
         W_ = self.Wt
-        co = W_.mat(f"neck.{name}.cv1.w")[0].shape[0]
+        co = W_.mat(f"neck.{name}.cv1.w").t.shape[0]
         cat = self._act(f"{name}.cat", mid.B, mid.H, mid.W, 3 * co)
-        w, wlo = self._mat(f"neck.{name}.upsample.w")
         up = cat.cols(0, co)
-        self.ops += ops.deconv2x2(top.hi4, w, up.hi4, W_[f"neck.{name}.upsample.b"], A_lo=top.lo4, W_lo=wlo if self.precise else None, C_lo=up.lo4)
+        self.ops += ops.deconv2x2(top.p3_4d, self._mat(f"neck.{name}.upsample.w"), up.p3_4d, W_[f"neck.{name}.upsample.b"])
         self._cba1x1(mid, f"{name}.cv1", cat.cols(co, 2 * co), L.ACT_RELU)
         t = self._act(f"{name}.t", low.B, low.H, low.W, co)
         self._cba1x1(low, f"{name}.cv2", t, L.ACT_RELU)
@@ -237,11 +228,10 @@ class VisionPlan:
             self._conv3x3(h1, q + "1.w", h2, bias=W_[q + "1.b"], act=L.ACT_SILU)
             self._linear(h2, q + "2.w", emb, bias=W_[q + "2.b"])
             # similarity GEMM against the folded (BN * normalised text * exp(logit_scale)) matrix
-            sw = torch.zeros(self.K_pad, schema.EMBED_DIM, dtype=BF16, device=self.dev)
-            swl = torch.zeros_like(sw) if self.precise else None
+            sw = P3.zeros((self.K_pad, schema.EMBED_DIM), self.dev, self.precise)
             sb = torch.zeros(self.K_pad, dtype=F32, device=self.dev)
             lg = self._f32(f"head{l}.logits", M, self.K_pad)
-            self.ops.append(ops.linear(emb.hi, sw, lg, bias=sb, A_lo=emb.lo, W_lo=swl))
+            self.ops.append(ops.linear(emb.p3, sw, lg, bias=sb))
             r1 = self._act(f"head{l}.r1", B, p.H, p.W, schema.HEAD_REG_CH)
             r2 = self._act(f"head{l}.r2", B, p.H, p.W, schema.HEAD_REG_CH)
             q = f"head.reg_preds.{l}."
@@ -252,7 +242,7 @@ class VisionPlan:
             self.embeds.append(emb)
             self.logits.append(lg)
             self.dists.append(dist)
-            self.sim_w.append((sw, swl))
+            self.sim_w.append(sw)
             self.sim_b.append(sb)
 
     def _build_post(self, score_thr, nms_pre, iou_thr, max_per_img, nms_mode, tv_numel_thr):
@@ -270,9 +260,8 @@ class VisionPlan:
         self.max_per_img = max_per_img
         if self.uni:
             self.kept_embed = torch.zeros(B, max_per_img, schema.EMBED_DIM, dtype=F32, device=self.dev)
-            self.ops.append(ops.gather_embed([e.hi for e in self.embeds], self.post.anchors, self.post.counts, self.Wt["head.contrast.g_all"],
-                                             self.Wt["head.contrast.h_all"], self.kept_embed,
-                                             embeds_lo=[e.lo for e in self.embeds] if self.precise else None))
+            self.ops.append(ops.gather_embed([e.p3 for e in self.embeds], self.post.anchors, self.post.counts, self.Wt["head.contrast.g_all"],
+                                             self.Wt["head.contrast.h_all"], self.kept_embed))
 
     # ------------------------------------------------------------------ run-time API
     def set_text(self, text_feats, normalize=True):
@@ -282,9 +271,8 @@ class VisionPlan:
         fold = []
         for l in range(3):
             c = f"head.contrast.{l}."
-            sw, swl = self.sim_w[l]
-            fold.append(ops.fold_text(self._text, self.Wt[c + "g"], self.Wt[c + "h"], self.Wt[c + "logit_scale"], self.Wt[c + "bias"], sw,
-                                      self.sim_b[l], normalize, Wout_lo=swl))
+            fold.append(ops.fold_text(self._text, self.Wt[c + "g"], self.Wt[c + "h"], self.Wt[c + "logit_scale"], self.Wt[c + "bias"], self.sim_w[l],
+                                      self.sim_b[l], normalize))
         self._fold_program = L.Program(fold)
         self._fold_program.run(torch.cuda.current_stream().cuda_stream)
 
@@ -340,8 +328,7 @@ class TextPlan:
         pr = weights.precise
 
         def bf(rows, cols):
-            hi = torch.zeros(rows, cols, dtype=BF16, device=dev)
-            return Act(hi, torch.zeros_like(hi) if pr else None, 1, 1, rows)
+            return P3.zeros((rows, cols), dev, pr)
 
         self.ids = torch.zeros(S, Lt, dtype=torch.int32, device=dev)
         self.mask = torch.zeros(S, Lt, dtype=torch.int32, device=dev)
@@ -355,22 +342,20 @@ class TextPlan:
         o = []
 
         def lin(a, wname, out, **kw):
-            w, wlo = W_.mat(wname)
-            C, Clo = (out.hi, out.lo) if isinstance(out, Act) else (out, None)
-            o.append(ops.linear(a.hi, w, C, A_lo=a.lo, W_lo=wlo if pr else None, C_lo=Clo, **kw))
+            o.append(ops.linear(a, W_.mat(wname), out, **kw))
 
         o.append(ops.text_embed(self.ids, W_["emb.word"], W_["emb.pos"], W_["emb.type"], W_["emb.ln_w"], W_["emb.ln_b"], schema.TEXT_EPS,
-                                schema.TEXT_PAD, x, xb.hi, xb.lo))
+                                schema.TEXT_PAD, x, xb))
         for i in range(t["layers"]):
             q = f"l{i}."
             lin(xb, q + "qkv.w", qkv, bias=W_[q + "qkv.b"])
-            o.append(ops.attn_small(qkv, self.mask, att.hi, nh, 0.125, att.lo))
+            o.append(ops.attn_small(qkv, self.mask, att, nh, 0.125))
             lin(att, q + "o.w", y, bias=W_[q + "o.b"], resid=x, alpha=1.0)
-            o.append(ops.ln_rows(y, W_[q + "ln1_w"], W_[q + "ln1_b"], schema.TEXT_EPS, out_bf16=xb.hi, out_lo=xb.lo, out_f32=x))
+            o.append(ops.ln_rows(y, W_[q + "ln1_w"], W_[q + "ln1_b"], schema.TEXT_EPS, out_bf16=xb, out_f32=x))
             lin(xb, q + "f1.w", hid, bias=W_[q + "f1.b"], act=L.ACT_GELU)
             lin(hid, q + "f2.w", y, bias=W_[q + "f2.b"], resid=x, alpha=1.0)
-            o.append(ops.ln_rows(y, W_[q + "ln2_w"], W_[q + "ln2_b"], schema.TEXT_EPS, out_bf16=xb.hi, out_lo=xb.lo, out_f32=x))
-        o.append(ops.gather_rows(x, cls.hi, S, Lt, cls.lo))
+            o.append(ops.ln_rows(y, W_[q + "ln2_w"], W_[q + "ln2_b"], schema.TEXT_EPS, out_bf16=xb, out_f32=x))
+        o.append(ops.gather_rows(x, cls, S, Lt))
         lin(cls, "head.w", ho, bias=W_["head.b"])
         o.append(ops.l2norm_rows(ho, self.feats))
         self.program = L.Program(o)

@@ -16,12 +16,7 @@ device tensors consumed by plan.py.  Transformations (all exact algebra, done in
 import torch
 
 from . import schema
-
-
-def _hi_lo(t32):
-    hi = t32.to(torch.bfloat16)
-    lo = (t32 - hi.float()).to(torch.bfloat16)
-    return hi, lo
+from .ops import P3
 
 
 class DeviceWeights:
@@ -31,18 +26,15 @@ class DeviceWeights:
         self.t = {}
 
     def put_mat(self, name, w64):
-        """GEMM B operand: bf16 (+ lo plane in precise mode)."""
+        """GEMM B operand: bf16, or three bf16 planes (p0 + p1 + p2 ~ fp32) in precise mode."""
         w32 = w64.float().contiguous()
-        hi, lo = _hi_lo(w32)
-        self.t[name] = hi.to(self.device)
-        if self.precise:
-            self.t[name + "#lo"] = lo.to(self.device)
+        self.t[name] = P3.from_f32(w32, self.device) if self.precise else P3(w32.to(torch.bfloat16).to(self.device), 0)
 
     def put_f32(self, name, v):
         self.t[name] = v.float().contiguous().to(self.device)
 
     def mat(self, name):
-        return self.t[name], self.t.get(name + "#lo")
+        return self.t[name]
 
     def __getitem__(self, k):
         return self.t[k]
