@@ -1,0 +1,60 @@
+"""world_size-2 gloo test of the multi-GPU host logic (sharding + single all-gather of padded detections)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wedetect_b200 import dist as wd
+    idx = list(wd.shard_indices(total, world, rank))
+    B, M = len(idx), 5
+    g = torch.Generator().manual_seed(100)
+    allb = torch.rand(total, M, 4, generator=g)
+    alls = torch.rand(total, M, generator=g)
+    alll = torch.randint(0, 80, (total, M), generator=g)
+    allc = torch.randint(0, M + 1, (total,), generator=g)
+    blk = wd.pack_detections(allb[idx], alls[idx], alll[idx], allc[idx])
+    out = wd.gather_detections(blk)
+    b, s, l, c = wd.unpack_detections(out)
+    ok = torch.equal(b, allb) and torch.equal(s, alls) and torch.equal(l, alll) and torch.equal(c, allc)
+    q.put((rank, idx, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_indices_match_reference_sampler():
+    from wedetect_b200.dist import shard_indices
+    for total in (0, 1, 7, 64, 100000):
+        for world in (1, 2, 8):
+            parts = [list(shard_indices(total, world, r)) for r in range(world)]
+            assert sum(parts, []) == list(range(total))
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+def test_all_gather_detections_world2():
+    world, total = 2, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    assert all(r[2] for r in res)

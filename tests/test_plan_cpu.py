@@ -1,0 +1,64 @@
+"""Host-side lowering logic on the CPU: tile pickers, weight folding algebra, op wiring (no kernels run)."""
+import types
+
+import pytest
+import torch
+
+
+def test_pick_tile_and_block_n():
+    from wedetect_b200.ops import pick_block_n, pick_tile
+    for (W, H, B) in [(80, 80, 32), (40, 40, 32), (20, 20, 32), (100, 100, 16), (25, 25, 16), (20, 20, 1), (160, 160, 1)]:
+        e0, e1, e2 = pick_tile(W, H, B)
+        assert e0 * e1 * e2 <= 128 and e0 <= W and e1 <= H and e2 <= max(B, 1)
+        tiles = -(-W // e0) * -(-H // e1) * -(-B // e2)
+        assert W * H * B / (tiles * 128) > 0.6
+    assert pick_block_n(2048) == 256 and pick_block_n(384) == 128 and pick_block_n(64) == 64 and pick_block_n(1208) == 256
+    assert pick_block_n(512, split=True) == 128
+
+
+def test_bn_fold_and_layouts_match_conv_semantics():
+    """Folded + re-laid-out weights reproduce Conv+BN / ConvTranspose / patchify exactly (fp64 algebra)."""
+    import torch.nn.functional as F
+    from wedetect_b200 import weights as Wp
+    g = torch.Generator().manual_seed(0)
+    Cin, Cout = 24, 16
+    sd = {"c.weight": torch.randn(Cout, Cin, 3, 3, generator=g), "bn.weight": torch.rand(Cout, generator=g) + 0.5, "bn.bias": torch.randn(Cout, generator=g),
+          "bn.running_mean": torch.randn(Cout, generator=g), "bn.running_var": torch.rand(Cout, generator=g) + 0.5}
+    w, b = Wp._fold_bn(sd, "c.weight", "bn", 1e-3)
+    x = torch.randn(2, Cin, 9, 9, generator=g).double()
+    ref = F.batch_norm(F.conv2d(x, sd["c.weight"].double(), padding=1), sd["bn.running_mean"].double(), sd["bn.running_var"].double(),
+                       sd["bn.weight"].double(), sd["bn.bias"].double(), False, 0.0, 1e-3)
+    torch.testing.assert_close(F.conv2d(x, w, b, padding=1), ref, rtol=1e-10, atol=1e-10)
+    taps = Wp._taps(w)                                   # [Cout, 9*64]
+    Kc = 64
+    cols = F.unfold(x, 3, padding=1).view(2, Cin, 9, 81).permute(0, 3, 2, 1)          # [B, L, tap, c]
+    colp = torch.zeros(2, 81, 9, Kc, dtype=torch.float64)
+    colp[..., :Cin] = cols
+    y = colp.reshape(2 * 81, 9 * Kc) @ taps.t() + b
+    torch.testing.assert_close(y.view(2, 9, 9, Cout).permute(0, 3, 1, 2), ref, rtol=1e-10, atol=1e-10)
+
+
+def test_plan_builds_for_all_sizes_on_cpu(monkeypatch):
+    import wedetect_b200._lib as L
+    from oracle import synth
+
+    class FakeProg:
+        def __init__(self, ops_, keepalive=()):
+            self.ops, self.num_launches = ops_, len(ops_)
+
+        def run(self, s):
+            pass
+
+    monkeypatch.setattr(L, "Program", FakeProg)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda: types.SimpleNamespace(cuda_stream=0))
+    from wedetect_b200 import plan, weights
+    for size, res, K, precise in (("tiny", 320, 5, False), ("base", 320, 80, True), ("large", 160, 16, False)):
+        sd = synth.synth_state_dict(size, seed=0, uni=True, num_prompts=K, with_text=False, calibrate=False)
+        Wt = weights.prepare_vision(sd, size, "cpu", precise=precise)
+        p = plan.VisionPlan(Wt, size, 2, res, res, K=K, uni=True, nms_mode=1, score_thr=0.0, device="cpu")
+        kinds = [op.kind for op in p.ops]
+        assert kinds.count(L.OP_DWCONV_LN) == sum({"tiny": (3, 3, 9, 3)}.get(size, (3, 3, 27, 3)))
+        assert kinds[-2:] == [L.OP_POSTPROCESS, L.OP_GATHER_EMBED]
+        for op in p.ops:
+            if op.kind == L.OP_GEMM:
+                assert op.i[30] == (3 if precise else 1) and op.i[6] % 64 == 0 and op.i[8] % 8 == 0
