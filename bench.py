@@ -83,6 +83,19 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(self.rows))
 
 
+def host_threads():
+    """CPU threads we may actually use: affinity mask, capped by the cgroup quota (a 128-core box with an 8-core
+    quota thrashes if torch spawns 128 workers) and by 32."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 def op_flops(op):
     """Algorithmic FLOPs of one GEMM-op record (2*M*N*K over real, unpadded extents)."""
     I = op.i
@@ -122,7 +135,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     n = args.cpu_sample or 2
     step = cpu_reference_arm(args, n, threads)
     for _ in range(max(1, min(args.warmup, 1))):
@@ -151,6 +164,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.set_num_threads(max(1, host_threads() // world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -284,7 +298,7 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         n = args.cpu_sample or 2
         step = cpu_reference_arm(args, n, threads)
         step(1)
@@ -305,7 +319,7 @@ def run_ours(args):
                 e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h // args.steps,
                          api="YOLOWorldDetector.test_step(pinned uint8 BGR batch) + pred_instances.cpu()"),
                 gpu_launches=int(launches), clocks=clk.summary(), roofline=roofline, cpu_baseline=cpu)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -23,6 +23,11 @@ import torch
 from wedetect_b200 import schema
 
 
+import os
+
+CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_cache")
+
+
 def synth_state_dict(size, *, seed=0, uni=False, num_prompts=256, with_text=True, cls_bias=0.0, text_vocab=None,
                      calibrate=True, regime="dense"):
     g = torch.Generator().manual_seed(seed)
@@ -63,7 +68,20 @@ def synth_state_dict(size, *, seed=0, uni=False, num_prompts=256, with_text=True
             raise KeyError(name)
         sd[name] = t
     if calibrate:
-        _calibrate(sd, size, seed, regime)
+        # the calibrated statistics (~100 KB) are cached on disk so that another machine (the GPU box) reproduces
+        # bit-identical weights without re-running the CPU calibration pass
+        path = os.path.join(CACHE_DIR, f"calib_{size}_s{seed}_{regime}.pt")
+        if os.path.exists(path):
+            sd.update(torch.load(path))
+        else:
+            before = {k: v for k, v in sd.items()}
+            _calibrate(sd, size, seed, regime)
+            changed = {k: v for k, v in sd.items() if v is not before[k]}
+            try:
+                os.makedirs(CACHE_DIR, exist_ok=True)
+                torch.save(changed, path)
+            except OSError:
+                pass
     return sd
 
 

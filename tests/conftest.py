@@ -9,7 +9,24 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+def _cap_threads():
+    """Never let torch spawn one worker per visible core: GPU boxes expose 128 cores behind a small cgroup quota."""
+    try:
+        import torch
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        try:
+            q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if q != "max":
+                n = min(n, max(1, int(int(q) / int(p))))
+        except Exception:
+            pass
+        torch.set_num_threads(max(1, min(n, 16)))
+    except Exception:
+        pass
+
+
 def pytest_configure(config):
+    _cap_threads()
     config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 device (run with -m gpu on the B200 box)")
 
 

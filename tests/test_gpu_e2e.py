@@ -28,7 +28,6 @@ def run_case(size, B, H, W, K, *, uni, precise, regime, seed=0):
     from oracle import functional as Fn, synth
     from oracle.postprocess import postprocess_ref, identity_meta
     from wedetect_b200 import plan, schema, weights
-    torch.set_num_threads(min(16, os.cpu_count() or 1))
     sd = synth.synth_state_dict(size, seed=seed, uni=uni, num_prompts=K, with_text=False, regime=regime)
     imgs = synth.synth_images(B, H, W, seed=seed + 2)
     g = torch.Generator().manual_seed(seed + 5)

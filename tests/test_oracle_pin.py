@@ -25,7 +25,6 @@ def _digest_close(t, g, rtol=2e-4, atol=2e-4):
 def test_functional_oracle_matches_reference_goldens():
     from oracle import functional as Fn, synth
     gold = torch.load(GOLD)["base_320"]
-    torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.synth_state_dict("base", seed=0, uni=True, regime="sparse")
     x = synth.synth_images(2, 320, 320, seed=2)
     with torch.no_grad():

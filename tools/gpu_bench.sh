@@ -2,7 +2,7 @@
 # First measurement pass: bench line + per-op table + ncu launch list + one full ncu capture of the top GEMM.
 mkdir -p gpurun_out
 nproc > gpurun_out/nproc.txt
-timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 --profile-ops gpurun_out/ops_profile.json > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 420 python bench.py --gpus 1 --steps 10 --warmup 3 --profile-ops gpurun_out/ops_profile.json > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit $?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" = "ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 330 --csv --log-file gpurun_out/launches.csv \
