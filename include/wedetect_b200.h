@@ -176,6 +176,8 @@ int wd_program_num_launches(const wd_program* prog);
 int wd_program_num_ops(const wd_program* prog);
 /* measurement helper: eager run with CUDA events between ops; ms_per_op has wd_program_num_ops entries. */
 int wd_program_run_timed(wd_program* prog, void* stream, float* ms_per_op);
+/* debug helper: run op by op; *stuck_op = index of the first op not finished after timeout_ms (-1: none). */
+int wd_program_find_stuck_op(wd_program* prog, void* stream, int timeout_ms, int* stuck_op);
 void wd_program_destroy(wd_program* prog);
 
 /* workspace size needed by WD_OP_POSTPROCESS for (B, anchors, K). */

@@ -32,6 +32,8 @@ def _rand_bf16(*shape, scale=1.0, seed=0):
     (300, 192, 80, None),    # N not a multiple of the chunk/tile (80), K = 3 iterations
     (128 * 400, 128, 512, 256),  # many tiles per CTA: barrier phases wrap, TMEM double buffering
     (640, 2048, 256, 256),   # long K loop
+    (128 * 700, 64, 64, 64),     # BN=64 bf16: one column chunk -> the second epilogue warpgroup idles; many tiles per CTA
+    (128 * 500, 128, 128, 128),  # BN=128, many tiles per CTA
     (500, 96, 384, None),    # K = 96: second k-chunk half zero-filled by TMA
     (260, 864, 96, None),    # im2col of a 96-channel 3x3 s2 conv (K = 9*96)
 ])
@@ -57,6 +59,18 @@ def test_linear_epilogue_f32(act):
     _run(ops.linear(A.to(d), W.to(d), C, bias=bias.to(d), gamma=gamma.to(d), resid=resid.to(d), alpha=0.75, act=act))
     ref = R.linear_ref(A, W, bias=bias, act=act, gamma=gamma, resid=resid, alpha=0.75)
     report_close(f"linear epilogue act={act}", C, ref, rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("N,block_n", [(64, 64), (128, 128), (32, 64)])
+def test_linear_f32_many_tiles(N, block_n):
+    """fp32 output, every tile width, several tiles per CTA (accumulator hand-back of both epilogue warpgroups)."""
+    from wedetect_b200 import ops
+    M, K = 128 * 450, 64
+    A, W = _rand_bf16(M, K, seed=31), _rand_bf16(N, K, seed=32, scale=0.1)
+    d = _dev()
+    C = torch.zeros(M, N, dtype=torch.float32, device=d)
+    _run(ops.linear(A.to(d), W.to(d), C, block_n=block_n))
+    report_close(f"linear f32 many tiles N={N}", C, R.linear_ref(A, W), rtol=1e-4, atol=1e-4)
 
 
 def test_linear_inplace_residual_f32():

@@ -20,6 +20,7 @@ EXPORTS = [
     "wd_last_error", "wd_version", "wd_launch_count", "wd_device_info", "wd_op_run", "wd_program_create",
     "wd_program_run", "wd_program_capture", "wd_program_replay", "wd_program_num_launches",
     "wd_program_destroy", "wd_pp_workspace_bytes", "wd_program_num_ops", "wd_program_run_timed",
+    "wd_program_find_stuck_op",
 ]
 
 
@@ -76,6 +77,7 @@ def load(require_gpu=True):
         lib.wd_program_num_launches.argtypes = [ctypes.c_void_p]
         lib.wd_program_num_ops.argtypes = [ctypes.c_void_p]
         lib.wd_program_run_timed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        lib.wd_program_find_stuck_op.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         lib.wd_program_destroy.argtypes = [ctypes.c_void_p]
         lib.wd_program_destroy.restype = None
         lib.wd_pp_workspace_bytes.argtypes = [ctypes.c_int] * 4
@@ -136,6 +138,12 @@ class Program:
         ms = (ctypes.c_float * n)()
         check(self._lib.wd_program_run_timed(self._h, ctypes.c_void_p(stream), ms), "wd_program_run_timed")
         return list(ms)
+
+    def find_stuck_op(self, stream=0, timeout_ms=5000):
+        """Debug: index of the first op that does not complete within timeout_ms (-1 if the program finishes)."""
+        stuck = ctypes.c_int(-1)
+        check(self._lib.wd_program_find_stuck_op(self._h, ctypes.c_void_p(stream), timeout_ms, ctypes.byref(stuck)), "wd_program_find_stuck_op")
+        return stuck.value
 
     def capture(self, stream):
         check(self._lib.wd_program_capture(self._h, ctypes.c_void_p(stream)), "wd_program_capture")

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <time.h>
 
 namespace wd {
 
@@ -211,6 +212,42 @@ int wd_program_run_timed(wd_program* prog, void* stream, float* ms_per_op) {
     for (auto& x : ev) cudaEventDestroy(x);
     if (rc) return rc;
     WD_CHECK_CUDA(e);
+    return 0;
+}
+
+// Debug helper: run op by op, polling the stream after each launch; returns the index of the first op that does
+// not finish within timeout_ms (-1 if all finish).  A stuck kernel is left running: the caller should exit.
+int wd_program_find_stuck_op(wd_program* prog, void* stream, int timeout_ms, int* stuck_op) {
+    if (!prog || !stuck_op) {
+        wd::set_last_error("wd_program_find_stuck_op: bad arguments");
+        return -1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    *stuck_op = -1;
+    for (size_t i = 0; i < prog->ops.size(); ++i) {
+        int rc = prog->ops[i]->launch(s);
+        if (rc) return rc;
+        cudaEvent_t ev;
+        WD_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        WD_CHECK_CUDA(cudaEventRecord(ev, s));
+        int waited = 0;
+        cudaError_t q;
+        while ((q = cudaEventQuery(ev)) == cudaErrorNotReady && waited < timeout_ms) {
+            struct timespec ts = {0, 1000000};
+            nanosleep(&ts, nullptr);
+            ++waited;
+        }
+        cudaEventDestroy(ev);
+        if (q == cudaErrorNotReady) {
+            *stuck_op = (int)i;
+            return 0;
+        }
+        if (q != cudaSuccess) {
+            wd::set_last_error("op %zu failed: %s", i, cudaGetErrorString(q));
+            *stuck_op = (int)i;
+            return -2;
+        }
+    }
     return 0;
 }
 

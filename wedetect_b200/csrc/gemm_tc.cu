@@ -243,6 +243,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[as]);
             } else {
+                if (wg >= n_chunks) {
+                    // this warpgroup owns no column chunk of the tile (BN == CH): still hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tempty[as]);
+                }
                 for (int c = wg; c < n_chunks; c += kNumEpiWG) {
                     float v[CH];
 #pragma unroll
