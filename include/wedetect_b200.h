@@ -68,8 +68,10 @@ enum wd_op_kind {
     WD_OP_LN_ROWS = 2,
     /* Depthwise 7x7 (pad 3) + bias + LayerNorm(C) on an NHWC fp32 tensor -> bf16 rows.
      * mm_backbone.py:114-116 (Block.forward dwconv/permute/norm).
-     * i: 0 B 1 H 2 W 3 C 4 ld_out (0 = C) 30 out plane stride   f: 0 eps
-     * p: 0 in f32 [B,H,W,C]  1 out bf16 [B*H*W,ld_out]  2 w f32[49,C]  3 b f32[C]  4 ln_w  5 ln_b */
+     * i: 0 B 1 H 2 W 3 C 4 ld_out (0 = C) 5 tx 6 ty (block = 8tx x 4ty pixels; used with the scratch) 30 out plane stride
+     * f: 0 eps
+     * p: 0 in f32 [B,H,W,C]  1 out bf16 [B*H*W,ld_out]  2 w f32[49,C]  3 b f32[C]  4 ln_w  5 ln_b
+     *    7 scratch f32 [B*H*W, C] (non-null selects the shared-memory tiled kernel) */
     WD_OP_DWCONV_LN = 3,
     /* Stem patchify: image -> bf16 rows [B*(H/4)*(W/4), 64] (48 valid = (dy,dx,c), rest 0).
      * mm_backbone.py:188-191 (Conv2d k4 s4 input gather); data_preprocessor.py:35-36 (mean/std are

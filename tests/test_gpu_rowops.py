@@ -47,8 +47,9 @@ def test_ln_rows_s2d():
     report_close("ln s2d", ob, ref, rtol=8e-3, atol=1e-3)
 
 
-@pytest.mark.parametrize("B,H,W,C", [(2, 20, 20, 128), (1, 40, 36, 256), (1, 10, 10, 1024), (1, 9, 13, 96), (1, 6, 6, 1536)])
-def test_dwconv_ln(B, H, W, C):
+@pytest.mark.parametrize("tiled", [False, True])
+@pytest.mark.parametrize("B,H,W,C", [(2, 20, 20, 128), (1, 40, 36, 256), (1, 10, 10, 1024), (1, 9, 13, 96), (1, 6, 6, 1536), (2, 160, 160, 128), (3, 40, 40, 512)])
+def test_dwconv_ln(B, H, W, C, tiled):
     from wedetect_b200 import ops
     g = _g(3)
     x = torch.randn(B, H, W, C, generator=g)
@@ -56,7 +57,8 @@ def test_dwconv_ln(B, H, W, C):
     bias, lw, lb = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
     from wedetect_b200.ops import P3
     out = P3.zeros((B * H * W, C), D, True)
-    _run(ops.dwconv_ln(x.to(D), out, w49.to(D), bias.to(D), lw.to(D), lb.to(D), 1e-6))
+    scratch = torch.zeros(x.numel(), dtype=torch.float32, device=D) if tiled else None
+    _run(ops.dwconv_ln(x.to(D), out, w49.to(D), bias.to(D), lw.to(D), lb.to(D), 1e-6, scratch=scratch))
     ref = R.dwconv_ln_ref(x, w49, bias, lw, lb, 1e-6)
     report_close("dwconv_ln bf16", out.t, ref, rtol=8e-3, atol=2e-3)
     report_close("dwconv_ln 3-plane", out.value(), ref, rtol=2e-5, atol=2e-5)

@@ -221,7 +221,25 @@ def ln_rows(x, w, b, eps, *, out_bf16=None, out_f32=None, s2d_hw=None):
     return op
 
 
-def dwconv_ln(x, out, w49, bias, ln_w, ln_b, eps):
+@functools.lru_cache(maxsize=None)
+def pick_dw_tile(W, H):
+    """(tx, ty): block tile = 8tx x 4ty output pixels for the tiled depthwise kernel (<= 16 thread tiles, <= 100 KB smem)."""
+    best = None
+    for tx in range(1, 7):
+        for ty in range(1, 9):
+            if tx * ty > 12 or ((8 * tx + 6) * (4 * ty + 6) + 49) * 128 > 100 * 1024:
+                continue
+            bx, by = -(-W // (8 * tx)), -(-H // (4 * ty))
+            compute = bx * by * 32 * tx * ty
+            halo = bx * by * (8 * tx + 6) * (4 * ty + 6)
+            cost = compute + 0.4 * halo + (0.05 * compute if (tx * ty) % 2 else 0)
+            if best is None or cost < best[0]:
+                best = (cost, (tx, ty))
+    return best[1]
+
+
+def dwconv_ln(x, out, w49, bias, ln_w, ln_b, eps, scratch=None):
+    """scratch: fp32 tensor with >= B*H*W*C elements -> shared-memory tiled kernel; None -> register-only kernel."""
     out, o_ps = _tp(out)
     _chk(x, torch.float32, "x")
     B, H, W, C = x.shape
@@ -233,6 +251,10 @@ def dwconv_ln(x, out, w49, bias, ln_w, ln_b, eps):
     op.f[0] = eps
     for k, t in enumerate((x, out, w49, bias, ln_w, ln_b)):
         op.p[k] = _ptr(t)
+    if scratch is not None:
+        assert scratch.dtype == torch.float32 and scratch.numel() >= x.numel() and scratch.is_contiguous()
+        op.i[5], op.i[6] = pick_dw_tile(W, H)
+        op.p[7] = _ptr(scratch)
     return op
 
 

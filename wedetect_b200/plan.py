@@ -125,7 +125,8 @@ class VisionPlan:
         # scratch shared by all stages (stage 0 is the largest)
         scratch_ln = P3.zeros((max(r * d for r, d in zip(rows, dims)),), self.dev, self.precise)
         scratch_hid = P3.zeros((max(r * 4 * d for r, d in zip(rows, dims)),), self.dev, self.precise)
-        self.keep += [scratch_ln, scratch_hid]
+        scratch_dw = torch.zeros(max(r * d for r, d in zip(rows, dims)), dtype=F32, device=self.dev)   # depthwise conv output, pre-LN
+        self.keep += [scratch_ln, scratch_hid, scratch_dw]
         # stem
         patch = self._act("stem.patch", B, hs[0], ws[0], 64)
         self.ops.append(ops.stem_patch(self.image, patch.p3, 1.0))
@@ -146,7 +147,7 @@ class VisionPlan:
             x4 = x.view(B, hs[s], ws[s], C)
             for j in range(depths[s]):
                 q = f"s{s}.b{j}."
-                self.ops.append(ops.dwconv_ln(x4, t_ln.p3, W_[q + "dw_w"], W_[q + "dw_b"], W_[q + "ln_w"], W_[q + "ln_b"], schema.LN_EPS))
+                self.ops.append(ops.dwconv_ln(x4, t_ln.p3, W_[q + "dw_w"], W_[q + "dw_b"], W_[q + "ln_w"], W_[q + "ln_b"], schema.LN_EPS, scratch=scratch_dw))
                 self._linear(t_ln, q + "w1", t_hid, bias=W_[q + "b1"], act=L.ACT_GELU)
                 self._linear(t_hid, q + "w2", x, bias=W_[q + "b2"], gamma=W_[q + "gamma"], resid=x, alpha=1.0)
             c = self._act(f"c{s + 1}", B, hs[s], ws[s], C)
