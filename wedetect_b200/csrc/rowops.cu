@@ -221,21 +221,18 @@ __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 7x7 + LayerNorm, shared-memory tiled version (the production path).
-//   block  = (8*tx) x (4*ty) output pixels of one image, all channels, 32 channels at a time
-//   thread = 2 channels x (8 wide x 4 tall) outputs: 64 fp32 accumulators, a sliding window of 4 weight rows
-//            (56 registers); every halo value is read from smem once per thread and feeds up to 28 FMAs
-//   phase 1: per 32-channel chunk: halo (+3 px, zero padded) and 49 weights -> smem, 3136 FMAs / thread, conv
-//            result (+bias, fp32) -> a scratch tensor (stays L2 resident)
-//   phase 2: the same block re-reads its pixels from the scratch (L2 hits), LayerNorm over C, bf16 out
+// depthwise 7x7 (pad 3) + bias, shared-memory tiled (the production path; LayerNorm follows as ln_rows on the
+// L2-resident fp32 result).
+//   block  = (8*tx) x (4*ty) output pixels x 32 channels of one image  (grid.z = image x channel chunk)
+//   thread = 2 channels x (8 wide x 4 tall) outputs: 64 fp32 accumulators + a sliding window of 4 weight rows;
+//            every halo value is read from smem once per thread and feeds up to 28 FMAs (FMA-pipe bound)
 // L2->SM traffic is (1 + 6/(8tx))(1 + 6/(4ty)) x the input instead of 7x for the register-only kernel above.
 // ------------------------------------------------------------------------------------------------
 constexpr int kDw2CK = 32;
 
-__global__ void __launch_bounds__(192, 2) dwconv7_ln_tiled_kernel(const float* __restrict__ in, int B, int H, int W, int C, const float* __restrict__ wt,
-                                                               const float* __restrict__ bias, float* __restrict__ yscr, const float* __restrict__ lnw,
-                                                               const float* __restrict__ lnb, float eps, __nv_bfloat16* out_hi, long long out_ps,
-                                                               int ld_out, int tx, int ty) {
+__global__ void __launch_bounds__(192, 2) dwconv7_tiled_kernel(const float* __restrict__ in, int H, int W, int C, int nchunks,
+                                                               const float* __restrict__ wt, const float* __restrict__ bias,
+                                                               float* __restrict__ yscr, int tx, int ty) {
     extern __shared__ float dsm[];
     const int HW_ = 8 * tx + 6, HH_ = 4 * ty + 6;
     float* halo = dsm;                                // [HH_][HW_][32]
@@ -244,122 +241,79 @@ __global__ void __launch_bounds__(192, 2) dwconv7_ln_tiled_kernel(const float* _
     const int pair = tid & 15, tile = tid >> 4;
     const bool active = tile < tx * ty;
     const int tix = tile % tx, tiy = tile / tx;
-    const int x0 = blockIdx.x * 8 * tx, y0 = blockIdx.y * 4 * ty, bi = blockIdx.z;
+    const int x0 = blockIdx.x * 8 * tx, y0 = blockIdx.y * 4 * ty;
+    const int bi = blockIdx.z / nchunks, c0 = (blockIdx.z % nchunks) * kDw2CK;
     const float* inb = in + (long long)bi * H * W * C;
 
-    for (int c0 = 0; c0 < C; c0 += kDw2CK) {
-        // ---- cooperative loads (float4, channel-contiguous) ----
-        const int nh4 = HH_ * HW_ * (kDw2CK / 4);
-        for (int i = tid; i < nh4; i += nthr) {
-            const int c4 = i & 7, pix = i >> 3;
-            const int py = pix / HW_, px = pix - py * HW_;
-            const int gy = y0 - 3 + py, gx = x0 - 3 + px;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + c4 * 4 < C)
-                v = __ldg(reinterpret_cast<const float4*>(inb + ((long long)gy * W + gx) * C + c0 + c4 * 4));
-            *reinterpret_cast<float4*>(halo + pix * kDw2CK + c4 * 4) = v;
+    // ---- cooperative loads (float4, channel-contiguous); out-of-image pixels are the conv's zero padding ----
+    const int nh4 = HH_ * HW_ * (kDw2CK / 4);
+    for (int i = tid; i < nh4; i += nthr) {
+        const int c4 = i & 7, pix = i >> 3;
+        const int py = pix / HW_, px = pix - py * HW_;
+        const int gy = y0 - 3 + py, gx = x0 - 3 + px;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + c4 * 4 < C)
+            v = __ldg(reinterpret_cast<const float4*>(inb + ((long long)gy * W + gx) * C + c0 + c4 * 4));
+        *reinterpret_cast<float4*>(halo + pix * kDw2CK + c4 * 4) = v;
+    }
+    for (int i = tid; i < 49 * 8; i += nthr) {
+        const int c4 = i & 7, tap = i >> 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c4 * 4 < C) v = __ldg(reinterpret_cast<const float4*>(wt + (long long)tap * C + c0 + c4 * 4));
+        *reinterpret_cast<float4*>(wsm + tap * kDw2CK + c4 * 4) = v;
+    }
+    __syncthreads();
+    if (!active || c0 + pair * 2 >= C) return;
+    float2 acc[4][8];
+#pragma unroll
+    for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 8; ++ox) acc[oy][ox] = make_float2(0.f, 0.f);
+    float2 wrow[4][7];
+#pragma unroll
+    for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx) wrow[oy][dx] = make_float2(0.f, 0.f);
+    const float* hbase = halo + ((tiy * 4) * HW_ + tix * 8) * kDw2CK + pair * 2;
+#pragma unroll
+    for (int iy = 0; iy < 10; ++iy) {
+        // wrow[oy] holds the weight row dy = iy - oy
+#pragma unroll
+        for (int oy = 3; oy > 0; --oy)
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) wrow[oy][dx] = wrow[oy - 1][dx];
+        if (iy < 7) {
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) wrow[0][dx] = *reinterpret_cast<const float2*>(wsm + (iy * 7 + dx) * kDw2CK + pair * 2);
         }
-        for (int i = tid; i < 49 * 8; i += nthr) {
-            const int c4 = i & 7, tap = i >> 3;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c0 + c4 * 4 < C) v = __ldg(reinterpret_cast<const float4*>(wt + (long long)tap * C + c0 + c4 * 4));
-            *reinterpret_cast<float4*>(wsm + tap * kDw2CK + c4 * 4) = v;
-        }
-        __syncthreads();
-        if (active && c0 + pair * 2 < C) {
-            float2 acc[4][8];
+        const float* hrow = hbase + iy * HW_ * kDw2CK;
 #pragma unroll
-            for (int oy = 0; oy < 4; ++oy)
+        for (int ix = 0; ix < 14; ++ix) {
+            const float2 v = *reinterpret_cast<const float2*>(hrow + ix * kDw2CK);
 #pragma unroll
-                for (int ox = 0; ox < 8; ++ox) acc[oy][ox] = make_float2(0.f, 0.f);
-            float2 wrow[4][7];
+            for (int oy = 0; oy < 4; ++oy) {
+                if (iy - oy >= 0 && iy - oy < 7) {
 #pragma unroll
-            for (int oy = 0; oy < 4; ++oy)
-#pragma unroll
-                for (int dx = 0; dx < 7; ++dx) wrow[oy][dx] = make_float2(0.f, 0.f);
-            const float* hbase = halo + ((tiy * 4) * HW_ + tix * 8) * kDw2CK + pair * 2;
-#pragma unroll
-            for (int iy = 0; iy < 10; ++iy) {
-                // wrow[oy] holds the weight row dy = iy - oy
-#pragma unroll
-                for (int oy = 3; oy > 0; --oy)
-#pragma unroll
-                    for (int dx = 0; dx < 7; ++dx) wrow[oy][dx] = wrow[oy - 1][dx];
-                if (iy < 7) {
-#pragma unroll
-                    for (int dx = 0; dx < 7; ++dx) wrow[0][dx] = *reinterpret_cast<const float2*>(wsm + (iy * 7 + dx) * kDw2CK + pair * 2);
-                }
-                const float* hrow = hbase + iy * HW_ * kDw2CK;
-#pragma unroll
-                for (int ix = 0; ix < 14; ++ix) {
-                    const float2 v = *reinterpret_cast<const float2*>(hrow + ix * kDw2CK);
-#pragma unroll
-                    for (int oy = 0; oy < 4; ++oy) {
-                        if (iy - oy >= 0 && iy - oy < 7) {
-#pragma unroll
-                            for (int ox = 0; ox < 8; ++ox) {
-                                if (ix - ox >= 0 && ix - ox < 7) {
-                                    acc[oy][ox].x = fmaf(v.x, wrow[oy][ix - ox].x, acc[oy][ox].x);
-                                    acc[oy][ox].y = fmaf(v.y, wrow[oy][ix - ox].y, acc[oy][ox].y);
-                                }
-                            }
+                    for (int ox = 0; ox < 8; ++ox) {
+                        if (ix - ox >= 0 && ix - ox < 7) {
+                            acc[oy][ox].x = fmaf(v.x, wrow[oy][ix - ox].x, acc[oy][ox].x);
+                            acc[oy][ox].y = fmaf(v.y, wrow[oy][ix - ox].y, acc[oy][ox].y);
                         }
                     }
                 }
             }
-            const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c0 + pair * 2));
-#pragma unroll
-            for (int oy = 0; oy < 4; ++oy) {
-                const int y = y0 + tiy * 4 + oy;
-#pragma unroll
-                for (int ox = 0; ox < 8; ++ox) {
-                    const int x = x0 + tix * 8 + ox;
-                    if (y < H && x < W)
-                        *reinterpret_cast<float2*>(yscr + (((long long)bi * H + y) * W + x) * C + c0 + pair * 2) =
-                            make_float2(acc[oy][ox].x + b2.x, acc[oy][ox].y + b2.y);
-                }
-            }
         }
-        __syncthreads();
     }
-    // ---- phase 2: LayerNorm of this block's pixels (written above by this block; visible after the barrier) ----
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-    const int tw = 8 * tx, npx = tw * 4 * ty;
-    for (int pidx = warp; pidx < npx; pidx += nwarps) {
-        const int y = y0 + pidx / tw, x = x0 + pidx % tw;
-        if (y >= H || x >= W) continue;
-        const long long row = ((long long)bi * H + y) * W + x;
-        const float* yr = yscr + row * C;
-        float4 v[kLnMaxVec];
-        float sum = 0.f;
+    const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c0 + pair * 2));
 #pragma unroll
-        for (int i = 0; i < kLnMaxVec; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < C) {
-                v[i] = *reinterpret_cast<const float4*>(yr + c);
-                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-            }
-        }
-        const float mean = warp_sum(sum) / (float)C;
-        float sq = 0.f;
+    for (int oy = 0; oy < 4; ++oy) {
+        const int y = y0 + tiy * 4 + oy;
 #pragma unroll
-        for (int i = 0; i < kLnMaxVec; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < C) {
-                const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-                sq += (a * a + bb * bb) + (cc * cc + d * d);
-            }
-        }
-        const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)C + eps);
-#pragma unroll
-        for (int i = 0; i < kLnMaxVec; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < C) {
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(lnw + c));
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(lnb + c));
-                store_bf16x4(out_hi, out_ps, row * ld_out + c, (v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y,
-                             (v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
-            }
+        for (int ox = 0; ox < 8; ++ox) {
+            const int x = x0 + tix * 8 + ox;
+            if (y < H && x < W)
+                *reinterpret_cast<float2*>(yscr + (((long long)bi * H + y) * W + x) * C + c0 + pair * 2) =
+                    make_float2(acc[oy][ox].x + b2.x, acc[oy][ox].y + b2.y);
         }
     }
 }
@@ -684,25 +638,35 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const int ld_out = I[4] > 0 ? I[4] : C;
             WD_REQUIRE(ld_out >= C && ld_out % 4 == 0, "dwconv_ln: bad ld_out");
             float* yscr = (float*)P[7];
-            if (yscr) {  // shared-memory tiled kernel (needs an fp32 scratch [B*H*W, C])
+            if (yscr) {  // shared-memory tiled conv -> fp32 scratch (L2 resident), then LayerNorm rows -> bf16
                 const int tx = I[5], ty = I[6];
                 WD_REQUIRE(tx >= 1 && ty >= 1 && tx * ty <= 12 && C % 4 == 0 && C <= kLnMaxVec * 128, "dwconv_ln: bad tile %d x %d", tx, ty);
                 const int thr = ((16 * tx * ty + 31) / 32) * 32;
                 const int smem = ((8 * tx + 6) * (4 * ty + 6) + 49) * kDw2CK * (int)sizeof(float);
-                WD_REQUIRE(thr <= 192 && smem <= 220 * 1024, "dwconv_ln: tile too large");
-                f->fn = [=](cudaStream_t s) {
-                    static int attr_smem = 0;
-                    if (smem > attr_smem) {
-                        WD_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_ln_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                        attr_smem = 220 * 1024;
+                const int nchunks = (C + kDw2CK - 1) / kDw2CK;
+                WD_REQUIRE(thr <= 192 && smem <= 220 * 1024 && (long long)B * nchunks <= 65535, "dwconv_ln: tile / grid too large");
+                const int rows = B * H * W;
+                struct DwOp : CompiledOp {
+                    std::function<int(cudaStream_t)> fn;
+                    int launch(cudaStream_t s) override { return fn(s); }
+                    int num_kernels() const override { return 2; }
+                };
+                auto d = std::make_unique<DwOp>();
+                d->fn = [=](cudaStream_t s) {
+                    static bool attr = false;
+                    if (!attr) {
+                        WD_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                        attr = true;
                     }
-                    dim3 grid((W + 8 * tx - 1) / (8 * tx), (H + 4 * ty - 1) / (4 * ty), B);
-                    dwconv7_ln_tiled_kernel<<<grid, thr, smem, s>>>(in, B, H, W, C, wt, bs, yscr, lw, lb, eps, oh, ol, ld_out, tx, ty);
+                    dim3 grid((W + 8 * tx - 1) / (8 * tx), (H + 4 * ty - 1) / (4 * ty), B * nchunks);
+                    dwconv7_tiled_kernel<<<grid, thr, smem, s>>>(in, H, W, C, nchunks, wt, bs, yscr, tx, ty);
+                    ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(yscr, rows, C, C, lw, lb, eps, oh, ol, nullptr, ld_out, 0, 0, 0);
                     WD_CHECK_CUDA(cudaGetLastError());
-                    count_launch();
+                    count_launch(2);
                     return 0;
                 };
-                break;
+                out = std::move(d);
+                return 0;
             }
             f->fn = [=](cudaStream_t s) {
                 dim3 grid((W + kDwTX - 1) / kDwTX, (H + kDwTY - 1) / kDwTY, B);
