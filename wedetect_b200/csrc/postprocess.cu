@@ -22,6 +22,8 @@
 //   7 pp_finalize     : first max_per_img kept candidates in rank order -> outputs
 #include "internal.h"
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace wd {
 
@@ -496,6 +498,17 @@ struct PostOp : CompiledOp {
         return 0;
     }
     int launch(cudaStream_t s) override {
+        // WD_PP_PROFILE=1: synchronous per-phase timing printed to stderr (debug / tuning aid, never in benchmarks)
+        static const bool prof = getenv("WD_PP_PROFILE") != nullptr;
+        cudaEvent_t ev[8];
+        int ne = 0;
+        auto mark = [&]() {
+            if (prof) {
+                cudaEventCreate(&ev[ne]);
+                cudaEventRecord(ev[ne++], s);
+            }
+        };
+        mark();
         pp_reset_kernel<<<(d.p.B + 255) / 256, 256, 0, s>>>(d);
         count_launch();
         for (int l = 0; l < d.p.nlevels; ++l) {
@@ -505,17 +518,36 @@ struct PostOp : CompiledOp {
             pp_candidates_kernel<<<(int)g, 256, 0, s>>>(d, l);
             count_launch();
         }
+        mark();
         if (sort(d.keys0, d.keys1, &d.ctrl->total, passes1, s)) return -2;
+        mark();
         const unsigned long long* sorted1 = (passes1 & 1) ? d.keys1 : d.keys0;
         pp_segments_kernel<<<1, 32, 0, s>>>(d);
         pp_decode_kernel<<<dim3(32, d.p.B), 256, 0, s>>>(d, sorted1);
         count_launch(2);
+        mark();
         if (sort(d.keys2a, d.keys2b, &d.ctrl->total2, passes2, s)) return -2;
+        mark();
         const unsigned long long* sorted2 = (passes2 & 1) ? d.keys2b : d.keys2a;
         pp_nms_kernel<<<dim3(d.p.K, d.p.B), 128, 0, s>>>(d, sorted2, kept);
+        mark();
         pp_finalize_kernel<<<d.p.B, 256, 0, s>>>(d);
         count_launch(2);
+        mark();
         WD_CHECK_CUDA(cudaGetLastError());
+        if (prof) {
+            cudaStreamSynchronize(s);
+            static const char* names[] = {"candidates", "sort1", "segments+decode", "sort2", "nms", "finalize"};
+            float tot = 0.f;
+            for (int i = 0; i + 1 < ne; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+                fprintf(stderr, "[pp] %-16s %.3f ms\n", names[i], ms);
+                tot += ms;
+            }
+            fprintf(stderr, "[pp] total %.3f ms (passes %d + %d)\n", tot, passes1, passes2);
+            for (int i = 0; i < ne; ++i) cudaEventDestroy(ev[i]);
+        }
         return 0;
     }
     float4* kept;

@@ -101,6 +101,89 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
     }
 }
 
+// Narrow rows (C <= 128*NV): R rows per warp in flight so that each warp keeps R*NV 16-byte loads outstanding
+// (the one-row kernel above is latency bound at C = 128: 512 B per warp per round trip).
+template <int NV, int R>
+__global__ void __launch_bounds__(256) ln_rows_multi_kernel(const float* __restrict__ in, int rows, int C, int ld_in, const float* __restrict__ w,
+                                                            const float* __restrict__ b, float eps, __nv_bfloat16* out_hi, long long out_ps,
+                                                            float* out_f32, int ld_out, int s2d, int W, int H) {
+    const int wrp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const long long row0 = (long long)wrp * R;
+    if (row0 >= rows) return;
+    float4 v[R][NV];
+    float sum[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        sum[r] = 0.f;
+        const long long row = row0 + r;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            v[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows && c < C) v[r][i] = *reinterpret_cast<const float4*>(in + row * ld_in + c);
+            sum[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+        }
+    }
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mean[r] = warp_sum(sum[r]) / (float)C;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < C) {
+                const float a = v[r][i].x - mean[r], bb = v[r][i].y - mean[r], cc = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
+                sq += (a * a + bb * bb) + (cc * cc + d * d);
+            }
+        }
+        rstd[r] = 1.f / sqrtf(warp_sum(sq) / (float)C + eps);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c >= C) continue;
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long row = row0 + r;
+            if (row >= rows) continue;
+            const float y0 = (v[r][i].x - mean[r]) * rstd[r] * ww.x + bb.x, y1 = (v[r][i].y - mean[r]) * rstd[r] * ww.y + bb.y;
+            const float y2 = (v[r][i].z - mean[r]) * rstd[r] * ww.z + bb.z, y3 = (v[r][i].w - mean[r]) * rstd[r] * ww.w + bb.w;
+            if (out_hi) {
+                long long orow = row;
+                int coff = 0;
+                if (s2d) {
+                    const int xx = (int)(row % W), yy = (int)((row / W) % H), bi = (int)(row / ((long long)W * H));
+                    orow = ((long long)bi * (H / 2) + yy / 2) * (W / 2) + xx / 2;
+                    coff = ((yy & 1) * 2 + (xx & 1)) * C;
+                }
+                store_bf16x4(out_hi, out_ps, orow * ld_out + coff + c, y0, y1, y2, y3);
+            }
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c) = make_float4(y0, y1, y2, y3);
+        }
+    }
+}
+
+static void launch_ln_rows(cudaStream_t s, const float* in, int rows, int C, int ld_in, const float* w, const float* b, float eps, __nv_bfloat16* oh,
+                           long long ol, float* of, int ld_out, int s2d, int W, int H) {
+    if (C <= 128) {
+        const int warps = (rows + 3) / 4;
+        ln_rows_multi_kernel<1, 4><<<(warps + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+    } else if (C <= 256) {
+        const int warps = (rows + 3) / 4;
+        ln_rows_multi_kernel<2, 4><<<(warps + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+    } else if (C <= 512) {
+        const int warps = (rows + 1) / 2;
+        ln_rows_multi_kernel<4, 2><<<(warps + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+    } else {
+        ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // depthwise 7x7 (pad 3) + bias + LayerNorm(C) -> bf16.   mm_backbone.py:114-116.
 // block = C/4 threads (rounded up to a warp multiple); a block owns a strip of TY x TX output pixels
@@ -245,23 +328,24 @@ __global__ void __launch_bounds__(192, 2) dwconv7_tiled_kernel(const float* __re
     const int bi = blockIdx.z / nchunks, c0 = (blockIdx.z % nchunks) * kDw2CK;
     const float* inb = in + (long long)bi * H * W * C;
 
-    // ---- cooperative loads (float4, channel-contiguous); out-of-image pixels are the conv's zero padding ----
+    // ---- cooperative async loads (cp.async 16 B, zero-fill = the conv's zero padding): all requests of a thread
+    //      are in flight together, one memory latency per block instead of one per loop iteration ----
     const int nh4 = HH_ * HW_ * (kDw2CK / 4);
     for (int i = tid; i < nh4; i += nthr) {
         const int c4 = i & 7, pix = i >> 3;
         const int py = pix / HW_, px = pix - py * HW_;
         const int gy = y0 - 3 + py, gx = x0 - 3 + px;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + c4 * 4 < C)
-            v = __ldg(reinterpret_cast<const float4*>(inb + ((long long)gy * W + gx) * C + c0 + c4 * 4));
-        *reinterpret_cast<float4*>(halo + pix * kDw2CK + c4 * 4) = v;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + c4 * 4 < C;
+        const float* src = ok ? inb + ((long long)gy * W + gx) * C + c0 + c4 * 4 : inb;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(halo + pix * kDw2CK + c4 * 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
     for (int i = tid; i < 49 * 8; i += nthr) {
         const int c4 = i & 7, tap = i >> 3;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + c4 * 4 < C) v = __ldg(reinterpret_cast<const float4*>(wt + (long long)tap * C + c0 + c4 * 4));
-        *reinterpret_cast<float4*>(wsm + tap * kDw2CK + c4 * 4) = v;
+        const bool ok = c0 + c4 * 4 < C;
+        const float* src = ok ? wt + (long long)tap * C + c0 + c4 * 4 : wt;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(wsm + tap * kDw2CK + c4 * 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (!active || c0 + pair * 2 >= C) return;
     float2 acc[4][8];
@@ -618,7 +702,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const long long ol = I[30];
             float* of = (float*)P[6];
             f->fn = [=](cudaStream_t s) {
-                ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+                launch_ln_rows(s, in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
                 return 0;
@@ -660,7 +744,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
                     }
                     dim3 grid((W + 8 * tx - 1) / (8 * tx), (H + 4 * ty - 1) / (4 * ty), B * nchunks);
                     dwconv7_tiled_kernel<<<grid, thr, smem, s>>>(in, H, W, C, nchunks, wt, bs, yscr, tx, ty);
-                    ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(yscr, rows, C, C, lw, lb, eps, oh, ol, nullptr, ld_out, 0, 0, 0);
+                    launch_ln_rows(s, yscr, rows, C, C, lw, lb, eps, oh, ol, nullptr, ld_out, 0, 0, 0);
                     WD_CHECK_CUDA(cudaGetLastError());
                     count_launch(2);
                     return 0;
