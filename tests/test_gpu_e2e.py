@@ -84,7 +84,7 @@ def test_e2e_fast(size, K):
         # bf16 operands: ~0.4 % per GEMM, amplified by this random-weight network (the fp32 oracle itself drifts
         # ~20x from backbone to P5 against an fp64 run); measured 3.5-9 % at the pyramid, see DESIGN.md §Precision
         assert errs[f"p{l + 3}"]["rel_rms"] < 0.15, errs[f"p{l + 3}"]
-        assert errs[f"logit{l}"]["max_abs"] < 0.6, errs[f"logit{l}"]
+        assert errs[f"logit{l}"]["max_abs"] < 1.0 and errs[f"logit{l}"]["rel_rms"] < 0.03, errs[f"logit{l}"]
         assert errs[f"dist{l}"]["max_abs"] < 2.0, errs[f"dist{l}"]
     assert min(errs["det_overlap"]) > 0.8, errs["det_overlap"]
 

@@ -24,6 +24,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 
 namespace wd {
 
@@ -45,6 +46,7 @@ struct PPDev {
     int lvl_off[5];         // anchor offset of each level
     unsigned long long cap; // key capacity
     int idx_bits, b_bits, cls_bits;
+    float logit_lo;
     // workspace pointers
     unsigned long long *keys0, *keys1, *keys2a, *keys2b;
     unsigned int* hist;
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(256) pp_candidates_kernel(PPDev d, int lvl) {
     const float* logits = d.p.logits[lvl];
     const int ld = d.p.ld_logit[lvl];
     const float thr = d.p.score_thr;
+    const float logit_lo = d.logit_lo;   // conservative float bound: x < logit_lo  =>  sigmoid(x) <= thr, skip the double evaluation
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long start = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -104,7 +107,8 @@ __global__ void __launch_bounds__(256) pp_candidates_kernel(PPDev d, int lvl) {
             const long long row = t / K;  // b*hw + a
             b = (int)(row / hw);
             const int a = (int)(row % hw);
-            const float s = sigmoid_dr(logits[row * ld + k]);
+            const float x = logits[row * ld + k];
+            const float s = x < logit_lo ? 0.f : sigmoid_dr(x);
             if (s > thr) {
                 pass = true;
                 const unsigned int inv = 0x3FFFFFFFu - (__float_as_uint(s) & 0x3FFFFFFFu);
@@ -340,6 +344,9 @@ __global__ void __launch_bounds__(128) pp_nms_kernel(PPDev d, const unsigned lon
     __syncthreads();
 
     for (int base = 0; base < n; base += 128) {
+        // a class can contribute at most max_per_img detections to the image's final top-max_per_img (its kept
+        // candidates are in score order), so the rest of the segment cannot matter: exact early exit
+        if (s_nk >= d.p.max_per_img) break;
         const int t = base + tid;
         const bool valid = t < n;
         float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -576,6 +583,14 @@ int compile_postprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     const unsigned long long cap = (unsigned long long)p.B * A * p.K;
     WD_REQUIRE(cap < (1ull << 32), "postprocess: B*A*K too large");
     o->d.cap = cap;
+    {
+        // sigmoid is monotone: scores > thr need logits > log(thr/(1-thr)); keep a safety margin far above any rounding
+        const double t = (double)p.score_thr;
+        double lo = -120.0;                                   // thr <= 0: every representable positive score passes
+        if (t >= 1.0) lo = 120.0;
+        else if (t > 0.0) { lo = log(t / (1.0 - t)); lo -= 1e-3 * (fabs(lo) > 1.0 ? fabs(lo) : 1.0); }
+        o->d.logit_lo = (float)lo;
+    }
     o->d.idx_bits = bits_for((unsigned long long)A * p.K);
     o->d.b_bits = bits_for(p.B);
     o->d.cls_bits = bits_for(p.K);

@@ -50,6 +50,7 @@ class YOLOWorldDetector:
         self._sd = None
         self.texts = None
         self.text_feats = None
+        self.last_batch_result = None
 
     # --- nn.Module-ish surface used by the entry points ---
     def eval(self):
@@ -99,11 +100,12 @@ class YOLOWorldDetector:
         assert max(num) == min(num), "number of sequences not equal in batch"
         flat = list(itertools.chain(*texts))
         key = tuple(flat)
-        if key not in self._text_cache:
+        key = (key, num[0])
+        if key not in self._text_cache:       # cached per text set: same tensor object on every call (predict relies on it)
             tok = self._get_tokenizer()(text=flat, return_tensors="pt", padding=True)
-            self._text_cache[key] = self.encode_tokens(tok["input_ids"], tok["attention_mask"])
-        f = self._text_cache[key]
-        return f.reshape(-1, num[0], f.shape[-1])
+            f = self.encode_tokens(tok["input_ids"], tok["attention_mask"])
+            self._text_cache[key] = f.reshape(-1, num[0], f.shape[-1])
+        return self._text_cache[key]
 
     def reparameterize(self, texts):
         self.texts = texts
@@ -149,12 +151,13 @@ class YOLOWorldDetector:
             feats = self.text_feats
         else:
             raise TypeError("batch_data_samples should be dict or list.")
+        src = feats
         feats = feats.reshape(-1, schema.EMBED_DIM)
         K = feats.shape[0]
         p = self._plan(B, H, W, K, batch_inputs.dtype)
-        if p._text_key is not feats:
+        if p._text_key is not src:            # fold BN * text * exp(scale) only when the text set changes
             p.set_text(feats.contiguous())
-            p._text_key = feats
+            p._text_key = src
         meta = torch.zeros(B, 8)
         meta[:, 2:4] = 1.0
         meta[:, 6] = 1.0
@@ -173,6 +176,7 @@ class YOLOWorldDetector:
         p.image.copy_(batch_inputs, non_blocking=True)
         p.run()
         r = p.results()
+        self.last_batch_result = r            # packed device tensors [B,max,...] + counts: bulk readers copy these once
         counts = r["counts"].cpu().tolist()   # the one host sync of the step (the reference has >= 3 per image)
         out = []
         for b in range(B):
