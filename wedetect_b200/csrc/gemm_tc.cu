@@ -92,6 +92,50 @@ __device__ __forceinline__ float act_fn(float x) {
     return x;
 }
 
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): two lanes of fp32 per instruction
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// fast activations on a pair (same formulas as act_fn<., true>)
+template <int ACT>
+__device__ __forceinline__ uint64_t act2_fast(uint64_t x) {
+    if constexpr (ACT == WD_ACT_GELU) {
+        const uint64_t s = mul2(x, x);
+        uint64_t p = fma2(s, pk2(-3.51516790e-4f, -3.51516790e-4f), pk2(3.70056460e-2f, 3.70056460e-2f));
+        p = fma2(s, p, pk2(7.97507884e-1f, 7.97507884e-1f));
+        float u0, u1;
+        upk2(mul2(x, p), u0, u1);
+        const uint64_t h = mul2(x, pk2(0.5f, 0.5f));
+        return fma2(h, pk2(tanh_approx(u0), tanh_approx(u1)), h);
+    } else if constexpr (ACT == WD_ACT_SILU) {
+        const uint64_t h = mul2(x, pk2(0.5f, 0.5f));
+        float h0, h1;
+        upk2(h, h0, h1);
+        return fma2(h, pk2(tanh_approx(h0), tanh_approx(h1)), h);
+    } else {
+        return x;
+    }
+}
+
 // v[j] = gamma[n] * act(v[j] + bias[n]) over one column chunk
 template <int CH, int ACT, bool kFast>
 __device__ __forceinline__ void epi_bias_act(float* v, const float* bias, const float* gamma, int n_base, int N) {
@@ -100,10 +144,15 @@ __device__ __forceinline__ void epi_bias_act(float* v, const float* bias, const 
         const int n = n_base + j;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
-        v[j + 0] = act_fn<ACT, kFast>(v[j + 0] + b4.x);
-        v[j + 1] = act_fn<ACT, kFast>(v[j + 1] + b4.y);
-        v[j + 2] = act_fn<ACT, kFast>(v[j + 2] + b4.z);
-        v[j + 3] = act_fn<ACT, kFast>(v[j + 3] + b4.w);
+        if constexpr (kFast && (ACT == WD_ACT_GELU || ACT == WD_ACT_SILU)) {
+            upk2(act2_fast<ACT>(add2(pk2(v[j + 0], v[j + 1]), pk2(b4.x, b4.y))), v[j + 0], v[j + 1]);
+            upk2(act2_fast<ACT>(add2(pk2(v[j + 2], v[j + 3]), pk2(b4.z, b4.w))), v[j + 2], v[j + 3]);
+        } else {
+            v[j + 0] = act_fn<ACT, kFast>(v[j + 0] + b4.x);
+            v[j + 1] = act_fn<ACT, kFast>(v[j + 1] + b4.y);
+            v[j + 2] = act_fn<ACT, kFast>(v[j + 2] + b4.z);
+            v[j + 3] = act_fn<ACT, kFast>(v[j + 3] + b4.w);
+        }
         if (gamma && n < N) {
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n));
             v[j + 0] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
@@ -193,10 +242,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             int as = 0;
             uint32_t aphase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                mbar_wait(&bar_tempty[as], aphase ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                if constexpr (!kSplit) {
+                    mbar_wait(&bar_tempty[as], aphase ^ 1);
+                    tc_fence_after();
+                }
                 for (int kit = 0; kit < k_iters; ++kit) {
+                    if constexpr (kSplit) {
+                        // precise mode: a fresh accumulator per 64-wide k-block; the epilogue sums the blocks in fp32
+                        // registers (round-to-nearest), keeping the tensor pipe's truncating accumulation chains short
+                        mbar_wait(&bar_tempty[as], aphase ^ 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
                     mbar_wait(&bar_full[stage], phase);
                     tc_fence_after();
                     const uint32_t s0 = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -205,15 +262,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-                        umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
-                        if (kSplit) {
+                        if constexpr (!kSplit) {
+                            umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
+                        } else {
                             const uint64_t a1 = umma_desc_sw128(s0 + PL), b1 = umma_desc_sw128(s0 + PL + C::A_BYTES);
                             const uint64_t a2 = umma_desc_sw128(s0 + 2 * PL), b2 = umma_desc_sw128(s0 + 2 * PL + C::A_BYTES);
-                            umma_bf16(tmem_d, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, a2 + 2 * k, b0 + 2 * k, idesc, 1u);
+                            // smallest products first so they are summed before the large term enters
+                            umma_bf16(tmem_d, a0 + 2 * k, b2 + 2 * k, idesc, k != 0 ? 1u : 0u);
                             umma_bf16(tmem_d, a1 + 2 * k, b1 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, a0 + 2 * k, b2 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a2 + 2 * k, b0 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, 1u);
                         }
                     }
                     umma_commit(&bar_empty[stage]);  // frees the smem slot when these MMAs retire
@@ -221,11 +281,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         stage = 0;
                         phase ^= 1;
                     }
+                    if constexpr (kSplit) {
+                        umma_commit(&bar_tfull[as]);
+                        if (++as == 2) {
+                            as = 0;
+                            aphase ^= 1;
+                        }
+                    }
                 }
-                umma_commit(&bar_tfull[as]);  // accumulator complete -> epilogue
-                if (++as == 2) {
-                    as = 0;
-                    aphase ^= 1;
+                if constexpr (!kSplit) {
+                    umma_commit(&bar_tfull[as]);  // accumulator complete -> epilogue
+                    if (++as == 2) {
+                        as = 0;
+                        aphase ^= 1;
+                    }
                 }
             }
         }
@@ -251,153 +320,249 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             const bool row_ok = (i2 < p.E2) && d0 < p.D0 && d1 < p.D1 && d2 < p.D2;
             const long long pix = ((long long)d2 * p.D1 + d1) * p.D0 + d0;
 
-            mbar_wait(&bar_tfull[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
-
-            if (p.epi_mode == 1) {
-                // ---- DFL epilogue (BN == 64): softmax over 16 bins x 4 sides, expectation ----
-                if constexpr (BN == 64) if (wg == 0) {
-                    float v[64];
-                    tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(v));
-                    tmem_ld_32x32(taddr + 32, reinterpret_cast<uint32_t*>(v + 32));
-                    tmem_ld_wait();
-                    float out4[4];
+            // ---- residual prefetch (single-plane residual of the output's dtype): the 8 x 16 B loads of a chunk are
+            //      issued before the accumulator is waited for / read, so their DRAM latency hides behind the MMAs ----
+            uint4 rq[8];
+            bool rq_valid = false;
+            const bool rq_ok = row_ok && p.resid_ps == 0 && p.resid_dtype == (kOutBf16 ? 1 : 2);
+            auto prefetch_resid = [&](int c) {
+                rq_valid = false;
+                const int n_base = n_blk * BN + c * CH;
+                if (!rq_ok || c >= n_chunks || n_base >= p.N) return;
+                const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.resid) + (pix * p.ld_res + n_base) * (long long)sizeof(OutT);
+                constexpr int EPV = 16 / (int)sizeof(OutT);   // elements per 16-byte vector
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        float mx = -INFINITY;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            v[s * 16 + j] += __ldg(p.bias + s * 16 + j);
-                            mx = fmaxf(mx, v[s * 16 + j]);
-                        }
-                        float den = 0.f, num = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float e = expf(v[s * 16 + j] - mx);
-                            den += e;
-                            num += e * (float)j;
-                        }
-                        out4[s] = num / den;
-                    }
-                    if (row_ok)
-                        *reinterpret_cast<float4*>(p.dfl_out + pix * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+                for (int q = 0; q < 8; ++q) {
+                    rq[q] = make_uint4(0u, 0u, 0u, 0u);
+                    if (n_base + q * EPV < p.N) rq[q] = *reinterpret_cast<const uint4*>(rp + q * 16);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_tempty[as]);
-            } else {
-                if (wg >= n_chunks) {
-                    // this warpgroup owns no column chunk of the tile (BN == CH): still hand the accumulator back
+                rq_valid = true;
+            };
+            // ---- per column chunk: v = resid*alpha + gamma * act(acc + bias) -> swizzled smem -> TMA store ----
+            auto finish_chunk = [&](float* v, int c) {
+                const int n_base = n_blk * BN + c * CH;
+                if (n_base < p.N) {  // warp-uniform: whole chunk beyond N is skipped (nothing to store)
+                    // ---- math: v = resid*alpha + gamma * act(acc + bias); the activation is uniform per launch ----
+                    constexpr bool kFast = kOutBf16 && !kSplit;
+                    switch (p.act) {
+                        case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                        case WD_ACT_SILU: epi_bias_act<CH, WD_ACT_SILU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                        case WD_ACT_GELU: epi_bias_act<CH, WD_ACT_GELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                        default: epi_bias_act<CH, WD_ACT_NONE, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                    }
+                    if (rq_valid) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if constexpr (kOutBf16) {
+                                v[q * 8 + 0] += p.alpha * bf16_lo(rq[q].x); v[q * 8 + 1] += p.alpha * bf16_hi(rq[q].x);
+                                v[q * 8 + 2] += p.alpha * bf16_lo(rq[q].y); v[q * 8 + 3] += p.alpha * bf16_hi(rq[q].y);
+                                v[q * 8 + 4] += p.alpha * bf16_lo(rq[q].z); v[q * 8 + 5] += p.alpha * bf16_hi(rq[q].z);
+                                v[q * 8 + 6] += p.alpha * bf16_lo(rq[q].w); v[q * 8 + 7] += p.alpha * bf16_hi(rq[q].w);
+                            } else {
+                                v[q * 4 + 0] += p.alpha * __uint_as_float(rq[q].x); v[q * 4 + 1] += p.alpha * __uint_as_float(rq[q].y);
+                                v[q * 4 + 2] += p.alpha * __uint_as_float(rq[q].z); v[q * 4 + 3] += p.alpha * __uint_as_float(rq[q].w);
+                            }
+                        }
+                        prefetch_resid(c + kNumEpiWG);   // next chunk of this warpgroup: overlaps staging, store and TMEM read
+                    } else if (p.resid_dtype != 0 && row_ok) {
+                        if (p.resid_dtype == 2) {
+                            const float* rp = reinterpret_cast<const float*>(p.resid) + pix * p.ld_res + n_base;
+#pragma unroll
+                            for (int j = 0; j < CH; j += 4) {
+                                if (n_base + j < p.N) {
+                                    const float4 x = *reinterpret_cast<const float4*>(rp + j);
+                                    v[j + 0] += p.alpha * x.x;
+                                    v[j + 1] += p.alpha * x.y;
+                                    v[j + 2] += p.alpha * x.z;
+                                    v[j + 3] += p.alpha * x.w;
+                                }
+                            }
+                        } else {
+                            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix * p.ld_res + n_base;
+                            const __nv_bfloat16* rl = p.resid_ps ? rp + p.resid_ps : nullptr;
+#pragma unroll
+                            for (int j = 0; j < CH; j += 8) {
+                                if (n_base + j < p.N) {
+                                    const uint4 x = *reinterpret_cast<const uint4*>(rp + j);
+                                    float xs[8] = {bf16_lo(x.x), bf16_hi(x.x), bf16_lo(x.y), bf16_hi(x.y),
+                                                   bf16_lo(x.z), bf16_hi(x.z), bf16_lo(x.w), bf16_hi(x.w)};
+                                    if (rl) {
+#pragma unroll
+                                        for (int pl = 0; pl < 2; ++pl) {
+                                            const uint4 y = *reinterpret_cast<const uint4*>(rl + pl * p.resid_ps + j);
+                                            xs[0] += bf16_lo(y.x); xs[1] += bf16_hi(y.x);
+                                            xs[2] += bf16_lo(y.y); xs[3] += bf16_hi(y.y);
+                                            xs[4] += bf16_lo(y.z); xs[5] += bf16_hi(y.z);
+                                            xs[6] += bf16_lo(y.w); xs[7] += bf16_hi(y.w);
+                                        }
+                                    }
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) v[j + q] += p.alpha * xs[q];
+                                }
+                            }
+                        }
+                    }
+                    // ---- stage into swizzled smem, then TMA store (precise bf16 output: one pass per plane) ----
+                    uint8_t* sbuf = wg_bufs + buf * C::EPI_BUF_BYTES;
+                    uint8_t* srow = sbuf + r * 128;
+                    const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
+                    constexpr int kOutPlanes = (kSplit && kOutBf16) ? 3 : 1;
+#pragma unroll
+                    for (int pl = 0; pl < kOutPlanes; ++pl) {
+                        if (issuer) tma_store_wait_read<C::EPI_BUFS - 1>();  // buffer `buf` no longer being read
+                        named_bar_sync(1 + wg, 128);
+                        if constexpr (kOutBf16) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                uint4 w;
+                                w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                                w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                                w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                                w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                                *reinterpret_cast<uint4*>(srow + ((q ^ (r & 7)) << 4)) = w;
+                                if constexpr (kSplit) {  // keep the remainder for the next plane
+                                    v[q * 8 + 0] -= bf16_lo(w.x); v[q * 8 + 1] -= bf16_hi(w.x);
+                                    v[q * 8 + 2] -= bf16_lo(w.y); v[q * 8 + 3] -= bf16_hi(w.y);
+                                    v[q * 8 + 4] -= bf16_lo(w.z); v[q * 8 + 5] -= bf16_hi(w.z);
+                                    v[q * 8 + 6] -= bf16_lo(w.w); v[q * 8 + 7] -= bf16_hi(w.w);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 w = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                                *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = w;
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + wg, 128);
+                        if (issuer) {
+                            tma_store_5d(&p.tmC[pl], sbuf, c0, o0, o1, o2, g);
+                            tma_store_commit();
+                        }
+                    }
+                    buf = (buf + 1) % C::EPI_BUFS;
+                }
+            };
+            auto finish_dfl = [&](float* v) {
+                float out4[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[s * 16 + j] += __ldg(p.bias + s * 16 + j);
+                        mx = fmaxf(mx, v[s * 16 + j]);
+                    }
+                    float den = 0.f, num = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float e = expf(v[s * 16 + j] - mx);
+                        den += e;
+                        num += e * (float)j;
+                    }
+                    out4[s] = num / den;
+                }
+                if (row_ok)
+                    *reinterpret_cast<float4*>(p.dfl_out + pix * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+            };
+            if constexpr (!kSplit) {
+                if (p.epi_mode == 0) prefetch_resid(wg);
+                mbar_wait(&bar_tfull[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+                if (p.epi_mode == 1) {
+                    // ---- DFL epilogue (BN == 64): softmax over 16 bins x 4 sides, expectation ----
+                    if constexpr (BN == 64) if (wg == 0) {
+                        float v[64];
+                        tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(v));
+                        tmem_ld_32x32(taddr + 32, reinterpret_cast<uint32_t*>(v + 32));
+                        tmem_ld_wait();
+                        finish_dfl(v);
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_tempty[as]);
-                }
-                for (int c = wg; c < n_chunks; c += kNumEpiWG) {
-                    float v[CH];
-#pragma unroll
-                    for (int j = 0; j < CH; j += 32) tmem_ld_32x32(taddr + c * CH + j, reinterpret_cast<uint32_t*>(v + j));
-                    tmem_ld_wait();
-                    if (c + kNumEpiWG >= n_chunks) {
-                        // last TMEM read of this warp for this tile: hand the accumulator back
+                } else {
+                    if (wg >= n_chunks) {
+                        // this warpgroup owns no column chunk of the tile (BN == CH): still hand the accumulator back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_tempty[as]);
                     }
-                    const int n_base = n_blk * BN + c * CH;
-                    if (n_base < p.N) {  // warp-uniform: whole chunk beyond N is skipped (nothing to store)
-                        // ---- math: v = resid*alpha + gamma * act(acc + bias); the activation is uniform per launch ----
-                        constexpr bool kFast = kOutBf16 && !kSplit;
-                        switch (p.act) {
-                            case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                            case WD_ACT_SILU: epi_bias_act<CH, WD_ACT_SILU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                            case WD_ACT_GELU: epi_bias_act<CH, WD_ACT_GELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                            default: epi_bias_act<CH, WD_ACT_NONE, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                    for (int c = wg; c < n_chunks; c += kNumEpiWG) {
+                        float v[CH];
+#pragma unroll
+                        for (int j = 0; j < CH; j += 32) tmem_ld_32x32(taddr + c * CH + j, reinterpret_cast<uint32_t*>(v + j));
+                        tmem_ld_wait();
+                        if (c + kNumEpiWG >= n_chunks) {
+                            // last TMEM read of this warp for this tile: hand the accumulator back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bar_tempty[as]);
                         }
-                        if (p.resid_dtype != 0 && row_ok) {
-                            if (p.resid_dtype == 2) {
-                                const float* rp = reinterpret_cast<const float*>(p.resid) + pix * p.ld_res + n_base;
-#pragma unroll
-                                for (int j = 0; j < CH; j += 4) {
-                                    if (n_base + j < p.N) {
-                                        const float4 x = *reinterpret_cast<const float4*>(rp + j);
-                                        v[j + 0] += p.alpha * x.x;
-                                        v[j + 1] += p.alpha * x.y;
-                                        v[j + 2] += p.alpha * x.z;
-                                        v[j + 3] += p.alpha * x.w;
-                                    }
-                                }
-                            } else {
-                                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix * p.ld_res + n_base;
-                                const __nv_bfloat16* rl = p.resid_ps ? rp + p.resid_ps : nullptr;
-#pragma unroll
-                                for (int j = 0; j < CH; j += 8) {
-                                    if (n_base + j < p.N) {
-                                        const uint4 x = *reinterpret_cast<const uint4*>(rp + j);
-                                        float xs[8] = {bf16_lo(x.x), bf16_hi(x.x), bf16_lo(x.y), bf16_hi(x.y),
-                                                       bf16_lo(x.z), bf16_hi(x.z), bf16_lo(x.w), bf16_hi(x.w)};
-                                        if (rl) {
-#pragma unroll
-                                            for (int pl = 0; pl < 2; ++pl) {
-                                                const uint4 y = *reinterpret_cast<const uint4*>(rl + pl * p.resid_ps + j);
-                                                xs[0] += bf16_lo(y.x); xs[1] += bf16_hi(y.x);
-                                                xs[2] += bf16_lo(y.y); xs[3] += bf16_hi(y.y);
-                                                xs[4] += bf16_lo(y.z); xs[5] += bf16_hi(y.z);
-                                                xs[6] += bf16_lo(y.w); xs[7] += bf16_hi(y.w);
-                                            }
-                                        }
-#pragma unroll
-                                        for (int q = 0; q < 8; ++q) v[j + q] += p.alpha * xs[q];
-                                    }
-                                }
-                            }
-                        }
-                        // ---- stage into swizzled smem, then TMA store (precise bf16 output: one pass per plane) ----
-                        uint8_t* sbuf = wg_bufs + buf * C::EPI_BUF_BYTES;
-                        uint8_t* srow = sbuf + r * 128;
-                        const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
-                        constexpr int kOutPlanes = (kSplit && kOutBf16) ? 3 : 1;
-#pragma unroll
-                        for (int pl = 0; pl < kOutPlanes; ++pl) {
-                            if (issuer) tma_store_wait_read<C::EPI_BUFS - 1>();  // buffer `buf` no longer being read
-                            named_bar_sync(1 + wg, 128);
-                            if constexpr (kOutBf16) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    uint4 w;
-                                    w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                                    w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                                    w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                                    w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                                    *reinterpret_cast<uint4*>(srow + ((q ^ (r & 7)) << 4)) = w;
-                                    if constexpr (kSplit) {  // keep the remainder for the next plane
-                                        v[q * 8 + 0] -= bf16_lo(w.x); v[q * 8 + 1] -= bf16_hi(w.x);
-                                        v[q * 8 + 2] -= bf16_lo(w.y); v[q * 8 + 3] -= bf16_hi(w.y);
-                                        v[q * 8 + 4] -= bf16_lo(w.z); v[q * 8 + 5] -= bf16_hi(w.z);
-                                        v[q * 8 + 6] -= bf16_lo(w.w); v[q * 8 + 7] -= bf16_hi(w.w);
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const float4 w = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                                    *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = w;
-                                }
-                            }
-                            fence_proxy_async_smem();
-                            named_bar_sync(1 + wg, 128);
-                            if (issuer) {
-                                tma_store_5d(&p.tmC[pl], sbuf, c0, o0, o1, o2, g);
-                                tma_store_commit();
-                            }
-                        }
-                        buf = (buf + 1) % C::EPI_BUFS;
+                        finish_chunk(v, c);
                     }
                 }
-            }
-            if (++as == 2) {
-                as = 0;
-                aphase ^= 1;
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            } else {
+                // ---- precise mode: sum the per-k-block accumulators in fp32 registers ----
+                constexpr int MY = (n_chunks + kNumEpiWG - 1) / kNumEpiWG;   // chunks a warpgroup can own
+                static_assert(MY * CH <= 64 && BN <= 128, "precise mode register budget");
+                float acc[64];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+                const bool dfl = p.epi_mode == 1;
+                for (int kit = 0; kit < k_iters; ++kit) {
+                    mbar_wait(&bar_tfull[as], aphase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+                    float t[32];
+                    if (dfl) {
+                        if constexpr (BN == 64) if (wg == 0) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                tmem_ld_32x32(taddr + h * 32, reinterpret_cast<uint32_t*>(t));
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) acc[h * 32 + j] += t[j];
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < MY; ++i) {
+                            const int c = wg + i * kNumEpiWG;
+                            if (c < n_chunks) {
+#pragma unroll
+                                for (int j0 = 0; j0 < CH; j0 += 32) {
+                                    tmem_ld_32x32(taddr + c * CH + j0, reinterpret_cast<uint32_t*>(t));
+                                    tmem_ld_wait();
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) acc[i * CH + j0 + j] += t[j];
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tempty[as]);
+                    if (++as == 2) {
+                        as = 0;
+                        aphase ^= 1;
+                    }
+                }
+                if (dfl) {
+                    if constexpr (BN == 64) if (wg == 0) finish_dfl(acc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < MY; ++i) {
+                        const int c = wg + i * kNumEpiWG;
+                        if (c < n_chunks) finish_chunk(acc + i * CH, c);
+                    }
+                }
             }
         }
         if (issuer) tma_store_wait_all<0>();

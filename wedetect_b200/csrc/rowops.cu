@@ -330,14 +330,25 @@ __global__ void __launch_bounds__(192, 2) dwconv7_tiled_kernel(const float* __re
 
     // ---- cooperative async loads (cp.async 16 B, zero-fill = the conv's zero padding): all requests of a thread
     //      are in flight together, one memory latency per block instead of one per loop iteration ----
-    const int nh4 = HH_ * HW_ * (kDw2CK / 4);
-    for (int i = tid; i < nh4; i += nthr) {
-        const int c4 = i & 7, pix = i >> 3;
-        const int py = pix / HW_, px = pix - py * HW_;
-        const int gy = y0 - 3 + py, gx = x0 - 3 + px;
-        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + c4 * 4 < C;
-        const float* src = ok ? inb + ((long long)gy * W + gx) * C + c0 + c4 * 4 : inb;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(halo + pix * kDw2CK + c4 * 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    {
+        const int npix = HH_ * HW_, pstep = nthr >> 3;   // nthr is a multiple of 32: 8 threads (one 128-byte row) per pixel
+        const int c4 = tid & 7;
+        const bool cok = c0 + c4 * 4 < C;
+        int pix = tid >> 3;
+        int py = pix / HW_, px = pix - py * HW_;           // one division per thread, then incremental stepping
+        const uint32_t sbase = smem_u32(halo + c4 * 4);
+        const float* gbase = inb + c0 + c4 * 4;
+        for (; pix < npix; pix += pstep) {
+            const int gy = y0 - 3 + py, gx = x0 - 3 + px;
+            const bool ok = cok && gy >= 0 && gy < H && gx >= 0 && gx < W;
+            const float* src = ok ? gbase + ((long long)gy * W + gx) * C : inb;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + pix * (kDw2CK * 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            px += pstep;
+            while (px >= HW_) {
+                px -= HW_;
+                ++py;
+            }
+        }
     }
     for (int i = tid; i < 49 * 8; i += nthr) {
         const int c4 = i & 7, tap = i >> 3;
