@@ -35,7 +35,7 @@ struct GemmParams {
     int D0, D1, D2, E0, E1, E2, nt0, nt1, nt2;
     int kc_iters, ntaps, tap_w, pad;
     int N, num_m_tiles, num_n_tiles, num_tiles;
-    int act, resid_dtype, ld_res, group_cols, epi_mode, rows_a;
+    int act, resid_dtype, ld_res, group_cols, epi_mode, rows_a, exact_act;
     float alpha;
     const float* bias;
     const float* gamma;
@@ -76,7 +76,7 @@ __device__ __forceinline__ float act_fn(float x) {
             const float h = 0.5f * x;
             return fmaf(h, tanh_approx(h), h);
         } else {
-            return __fdividef(x, 1.f + __expf(-x));
+            return x / (1.f + expf(-x));   // exact path (fp32 outputs / precise mode / exact_act)
         }
     }
     if constexpr (ACT == WD_ACT_GELU) {
@@ -344,11 +344,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 if (n_base < p.N) {  // warp-uniform: whole chunk beyond N is skipped (nothing to store)
                     // ---- math: v = resid*alpha + gamma * act(acc + bias); the activation is uniform per launch ----
                     constexpr bool kFast = kOutBf16 && !kSplit;
-                    switch (p.act) {
-                        case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                        case WD_ACT_SILU: epi_bias_act<CH, WD_ACT_SILU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                        case WD_ACT_GELU: epi_bias_act<CH, WD_ACT_GELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                        default: epi_bias_act<CH, WD_ACT_NONE, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                    if (kFast && !p.exact_act) {
+                        switch (p.act) {
+                            case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_SILU: epi_bias_act<CH, WD_ACT_SILU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_GELU: epi_bias_act<CH, WD_ACT_GELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                            default: epi_bias_act<CH, WD_ACT_NONE, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                        }
+                    } else {
+                        switch (p.act) {
+                            case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, false>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_SILU: epi_bias_act<CH, WD_ACT_SILU, false>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_GELU: epi_bias_act<CH, WD_ACT_GELU, false>(v, p.bias, p.gamma, n_base, p.N); break;
+                            default: epi_bias_act<CH, WD_ACT_NONE, false>(v, p.bias, p.gamma, n_base, p.N); break;
+                        }
                     }
                     if (rq_valid) {
 #pragma unroll
@@ -635,6 +644,7 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     const int n_groups = I[19];
     const long long sc0 = I[20], sc1 = I[21], sc2 = I[22], scg = I[23];
     P.epi_mode = I[24];
+    P.exact_act = I[35];
     P.tap_w = I[25] > 0 ? I[25] : 1;
     P.pad = I[26];
     const int group_valid = I[27] > 0 ? I[27] : I[18];   // columns of a group that exist in memory

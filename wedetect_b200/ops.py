@@ -92,6 +92,11 @@ def pick_block_n(N, out_f32=False, split=False):
     return best[1]
 
 
+# activations for which the fast path must use the exact formula (debug / accuracy studies): subset of {ACT_SILU, ACT_GELU}
+import os as _os
+EXACT_ACT = {dict(silu=L.ACT_SILU, gelu=L.ACT_GELU)[a] for a in _os.environ.get("WD_EXACT_ACT", "").split(",") if a in ("silu", "gelu")}
+
+
 def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, block_n=None, out_f32=False,
              act=L.ACT_NONE, bias=None, gamma=None, resid=None, ld_res=0, alpha=1.0, group_cols=None, n_groups=1,
              c_gstride=0, dfl=False, a_ps=0, w_ps=0, c_ps=0, r_ps=0, group_valid=0, k_valid=0, bk_valid=0):
@@ -117,6 +122,7 @@ def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, 
     I[24] = 1 if dfl else 0
     I[25], I[26] = (3, 1) if ntaps == 9 else (1, 0)
     I[27], I[28], I[29] = group_valid, k_valid, bk_valid
+    I[35] = 1 if act in EXACT_ACT else 0
     I[30] = 3 if split else 1
     I[31], I[32], I[33], I[34] = a_ps, w_ps, c_ps, r_ps
     op.f[0] = alpha
