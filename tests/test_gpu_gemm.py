@@ -32,6 +32,8 @@ def _rand_bf16(*shape, scale=1.0, seed=0):
     (300, 192, 80, None),    # N not a multiple of the chunk/tile (80), K = 3 iterations
     (128 * 400, 128, 512, 256),  # many tiles per CTA: barrier phases wrap, TMEM double buffering
     (640, 2048, 256, 256),   # long K loop
+    (128 * 301, 512, 512, 256),  # pair mode with an odd number of m-tiles (ghost tile) and 2 n-tiles
+    (128 * 3, 64, 256, 256),     # pair mode, 3 m-tiles, single k-iteration
     (128 * 700, 64, 64, 64),     # BN=64 bf16: one column chunk -> the second epilogue warpgroup idles; many tiles per CTA
     (128 * 500, 128, 128, 128),  # BN=128, many tiles per CTA
     (500, 96, 384, None),    # K = 96: second k-chunk half zero-filled by TMA

@@ -36,6 +36,7 @@ struct GemmParams {
     int kc_iters, ntaps, tap_w, pad;
     int N, num_m_tiles, num_n_tiles, num_tiles;
     int act, resid_dtype, ld_res, group_cols, epi_mode, rows_a, exact_act;
+    int clu, num_pair_tiles;   // clu == 2: clusters of two CTAs (same n-block, adjacent m-blocks) share B through TMA multicast
     float alpha;
     const float* bias;
     const float* gamma;
@@ -55,7 +56,9 @@ struct Cfg {
     static constexpr int EPI_BYTES = kNumEpiWG * EPI_BUFS * EPI_BUF_BYTES;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
-    static constexpr int TMEM_COLS = 2 * BN;
+    // precise mode keeps two accumulators per buffer: the a0*b0 products and the five small cross terms, so the
+    // small terms are not truncated against the large running sum inside the tensor pipe
+    static constexpr int TMEM_COLS = (kSplit ? 4 : 2) * BN;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols");
 };
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_empty[s], (uint32_t)p.clu);   // one tcgen05.commit arrival per CTA that reads this stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tfull[a], 1);
@@ -200,10 +203,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if (p.clu == 2) {
+        __syncwarp();
+        cluster_sync_all();   // peer barriers initialised before any multicast can signal them
+    }
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const int k_iters = p.kc_iters * p.ntaps;
+    // work distribution: plain persistent CTAs, or CTA pairs walking (m-pair, n) tiles in lock step
+    const int crank = p.clu == 2 ? (int)cluster_ctarank() : 0;
+    const int t_first = p.clu == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int t_step = p.clu == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int t_total = p.clu == 2 ? p.num_pair_tiles : p.num_tiles;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -211,10 +223,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = (kSplit ? 3u : 1u) * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+            for (int tile = t_first; tile < t_total; tile += t_step) {
+                const int m_blk = (tile / p.num_n_tiles) * p.clu + crank, n_blk = tile % p.num_n_tiles;
                 const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
-                const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
+                const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;   // beyond the tensor for the odd pair's ghost tile
                 for (int kit = 0; kit < k_iters; ++kit) {
                     const int tap = kit / p.kc_iters, kc = kit - tap * p.kc_iters;
                     const int dx = tap % p.tap_w - p.pad, dy = tap / p.tap_w - p.pad;
@@ -224,7 +236,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     for (int pl = 0; pl < (kSplit ? 3 : 1); ++pl) {
                         uint8_t* sA = smem + stage * C::STAGE_BYTES + pl * (C::A_BYTES + C::B_BYTES);
                         tma_load_4d(&p.tmA[pl], &bar_full[stage], sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
-                        tma_load_2d(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES, kit * kBlockK, n_blk * BN);
+                        if (p.clu == 2)   // this CTA fetches its half of B for both CTAs of the pair
+                            tma_load_2d_mc(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES + crank * (C::B_BYTES / 2), kit * kBlockK,
+                                           n_blk * BN + crank * (BN / 2), (uint16_t)3);
+                        else
+                            tma_load_2d(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES, kit * kBlockK, n_blk * BN);
                     }
                     if (++stage == C::kStages) {
                         stage = 0;
@@ -241,7 +257,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = t_first; tile < t_total; tile += t_step) {
                 if constexpr (!kSplit) {
                     mbar_wait(&bar_tempty[as], aphase ^ 1);
                     tc_fence_after();
@@ -267,16 +283,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         } else {
                             const uint64_t a1 = umma_desc_sw128(s0 + PL), b1 = umma_desc_sw128(s0 + PL + C::A_BYTES);
                             const uint64_t a2 = umma_desc_sw128(s0 + 2 * PL), b2 = umma_desc_sw128(s0 + 2 * PL + C::A_BYTES);
-                            // smallest products first so they are summed before the large term enters
-                            umma_bf16(tmem_d, a0 + 2 * k, b2 + 2 * k, idesc, k != 0 ? 1u : 0u);
-                            umma_bf16(tmem_d, a1 + 2 * k, b1 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, a2 + 2 * k, b0 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, 1u);
+                            const uint32_t tmem_s = tmem_d + 2 * BN;   // second accumulator: the small cross terms
+                            umma_bf16(tmem_s, a0 + 2 * k, b2 + 2 * k, idesc, k != 0 ? 1u : 0u);
+                            umma_bf16(tmem_s, a1 + 2 * k, b1 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_s, a2 + 2 * k, b0 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_s, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_s, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
+                            umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, k != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit(&bar_empty[stage]);  // frees the smem slot when these MMAs retire
+                    // frees the smem slot when these MMAs retire (in pair mode: tells BOTH producers, whose multicasts fill it)
+                    if (p.clu == 2) umma_commit_mc(&bar_empty[stage], (uint16_t)3);
+                    else umma_commit(&bar_empty[stage]);
                     if (++stage == C::kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -311,8 +329,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         int buf = 0;
         constexpr int n_chunks = BN / CH;
 
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+        for (int tile = t_first; tile < t_total; tile += t_step) {
+            const int m_blk = (tile / p.num_n_tiles) * p.clu + crank, n_blk = tile % p.num_n_tiles;
             const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
             const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
             const int i0 = r % p.E0, i1 = (r / p.E0) % p.E1, i2 = r / (p.E0 * p.E1);
@@ -534,10 +552,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         if constexpr (BN == 64) if (wg == 0) {
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
+                                float t2[32];
                                 tmem_ld_32x32(taddr + h * 32, reinterpret_cast<uint32_t*>(t));
+                                tmem_ld_32x32(taddr + 2 * BN + h * 32, reinterpret_cast<uint32_t*>(t2));
                                 tmem_ld_wait();
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) acc[h * 32 + j] += t[j];
+                                for (int j = 0; j < 32; ++j) acc[h * 32 + j] += t[j] + t2[j];
                             }
                         }
                     } else {
@@ -547,10 +567,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                             if (c < n_chunks) {
 #pragma unroll
                                 for (int j0 = 0; j0 < CH; j0 += 32) {
+                                    float t2[32];
                                     tmem_ld_32x32(taddr + c * CH + j0, reinterpret_cast<uint32_t*>(t));
+                                    tmem_ld_32x32(taddr + 2 * BN + c * CH + j0, reinterpret_cast<uint32_t*>(t2));
                                     tmem_ld_wait();
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) acc[i * CH + j0 + j] += t[j];
+                                    for (int j = 0; j < 32; ++j) acc[i * CH + j0 + j] += t[j] + t2[j];
                                 }
                             }
                         }
@@ -579,6 +601,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
 
     tc_fence_before();
     __syncthreads();
+    if (p.clu == 2) {
+        __syncwarp();
+        cluster_sync_all();   // the peer may still be arriving on this CTA's barriers
+    }
     if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
@@ -599,7 +625,23 @@ static int launch_inst(const GemmOp& g, cudaStream_t s) {
         WD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, kSplit>::SMEM_BYTES));
         attr_set = true;
     }
-    kern<<<g.grid, kNumThreads, Cfg<BN, kSplit>::SMEM_BYTES, s>>>(g.prm);
+    if (g.prm.clu == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(g.grid);
+        cfg.blockDim = dim3(kNumThreads);
+        cfg.dynamicSmemBytes = Cfg<BN, kSplit>::SMEM_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        WD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g.prm));
+    } else {
+        kern<<<g.grid, kNumThreads, Cfg<BN, kSplit>::SMEM_BYTES, s>>>(g.prm);
+    }
     WD_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -685,6 +727,10 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     P.num_n_tiles = ceil_div(P.N, g->block_n);
     P.num_tiles = P.num_m_tiles * P.num_n_tiles;
     P.rows_a = P.E0 * P.E1 * P.E2;
+    // pair mode: 256-wide tiles of the fast path; halves the B bytes each SM pulls through L2 (the L2->SM fabric, not
+    // HBM or the tensor pipe, is what bounds 128x256 tiles).  I[36] = 1 disables it (A/B measurements).
+    P.clu = (g->block_n == 256 && !g->split && P.epi_mode == 0 && P.num_m_tiles >= 2 && I[36] == 0) ? 2 : 1;
+    P.num_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
 
     // --- A: rank-4 (k, d0, d1, d2), bf16, box (64, E0, E1, E2), 128B swizzle
     {
@@ -700,7 +746,7 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         WD_REQUIRE(bk_valid <= (long long)Kc * P.ntaps && bk_valid % 8 == 0, "gemm: bad B K extent");
         uint64_t dims[2] = {(uint64_t)bk_valid, (uint64_t)P.N};
         uint64_t str[1] = {(uint64_t)ldb * 2};
-        uint32_t box[2] = {kBlockK, (uint32_t)g->block_n};
+        uint32_t box[2] = {kBlockK, (uint32_t)(P.clu == 2 ? g->block_n / 2 : g->block_n)};
         for (int pl = 0; pl < (g->split ? 3 : 1); ++pl)
             if (encode_tmap(&P.tmB[pl], (const __nv_bfloat16*)op.p[1] + pl * b_ps, 2, 2, dims, str, box, true)) return -1;
     }
@@ -725,6 +771,10 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     const int sms = device_sm_count();
     if (sms <= 0) return -2;
     g->grid = P.num_tiles < sms ? P.num_tiles : sms;
+    if (P.clu == 2) {
+        const int want = 2 * P.num_pair_tiles;
+        g->grid = want < (sms & ~1) ? want : (sms & ~1);
+    }
     out = std::move(g);
     return 0;
 }
