@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     }
                     // ---- stage into swizzled smem, then TMA store (precise bf16 output: one pass per plane) ----
                     uint8_t* sbuf = wg_bufs + buf * C::EPI_BUF_BYTES;
-                    uint8_t* srow = sbuf + r * 128;
+                    const uint32_t srow_s = smem_u32(sbuf) + r * 128;   // explicit shared-space stores (STS), not generic ST
                     const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
                     constexpr int kOutPlanes = (kSplit && kOutBf16) ? 3 : 1;
 #pragma unroll
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                                 w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
                                 w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
                                 w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                                *reinterpret_cast<uint4*>(srow + ((q ^ (r & 7)) << 4)) = w;
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + ((q ^ (r & 7)) << 4)), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
                                 if constexpr (kSplit) {  // keep the remainder for the next plane
                                     v[q * 8 + 0] -= bf16_lo(w.x); v[q * 8 + 1] -= bf16_hi(w.x);
                                     v[q * 8 + 2] -= bf16_lo(w.y); v[q * 8 + 3] -= bf16_hi(w.y);
@@ -457,8 +457,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         } else {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                const float4 w = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                                *reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4)) = w;
+                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + ((q ^ (r & 7)) << 4)), "f"(v[q * 4 + 0]), "f"(v[q * 4 + 1]), "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3]) : "memory");
                             }
                         }
                         fence_proxy_async_smem();

@@ -154,31 +154,51 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long
     }
 }
 
+// exclusive scan of the (digit-major) tile histograms: one block, 8 entries per thread per sweep, shuffle-based
 __global__ void __launch_bounds__(1024) rs_scan_kernel(const unsigned int* __restrict__ n_ptr, unsigned int* __restrict__ hist) {
-    __shared__ unsigned int part[1024];
+    __shared__ unsigned int wsum[32];
+    __shared__ unsigned int carry_s;
     const unsigned int n = *n_ptr;
     const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
     const unsigned long long len = 256ull * num_tiles;
-    const unsigned long long per = (len + 1023) / 1024;
-    const unsigned long long lo = per * threadIdx.x, hi = (lo + per < len) ? lo + per : len;
-    unsigned int s = 0;
-    for (unsigned long long i = lo; i < hi; ++i) s += hist[i];
-    part[threadIdx.x] = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int run = 0;
-        for (int i = 0; i < 1024; ++i) {
-            const unsigned int t = part[i];
-            part[i] = run;
-            run += t;
+    for (unsigned long long base = 0; base < len; base += 8192) {
+        const unsigned long long i0 = base + (unsigned long long)threadIdx.x * 8;
+        unsigned int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (i0 + j < len) ? hist[i0 + j] : 0u;
+        unsigned int tsum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tsum += v[j];
+        unsigned int incl = tsum;   // inclusive warp scan of the thread sums
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-    }
-    __syncthreads();
-    unsigned int run = part[threadIdx.x];
-    for (unsigned long long i = lo; i < hi; ++i) {
-        const unsigned int t = hist[i];
-        hist[i] = run;
-        run += t;
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int w = wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wsum[lane] = wi - w;   // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        unsigned int run = carry_s + wsum[warp] + (incl - tsum);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (i0 + j < len) hist[i0 + j] = run;
+            run += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = run;   // total so far (last thread's running value after its 8 entries)
+        __syncthreads();
     }
 }
 
