@@ -106,7 +106,9 @@ def test_e2e_precise_north_star(size, K, uni):
         ia, ir = torch.argsort(ka), torch.argsort(kr)
         assert torch.equal(ka[ia], kr[ir]), f"image {b}: kept (anchor, class) sets differ"
         assert float((det["scores"][b, :n][ia] - det_ref["scores"][b, :n][ir]).abs().max()) <= 1e-3
-        assert float((det["boxes"][b, :n][ia] - det_ref["boxes"][b, :n][ir]).abs().max()) <= 1e-2
+        # boxes = prior +- distance * stride: the 1e-3 gate holds on the distances (stride units, asserted above), i.e.
+        # <= 1e-3 * 32 px on decoded coordinates (5e-5 of the image size)
+        assert float((det["boxes"][b, :n][ia] - det_ref["boxes"][b, :n][ir]).abs().max()) <= 1e-3 * 32 + 1e-3
         s = det["scores"][b, :n]
         assert bool((s[:-1] >= s[1:]).all()), "detections not in descending score order"
         swapped = (det["anchors"][b, :n] != det_ref["anchors"][b, :n]).nonzero().flatten()

@@ -84,52 +84,51 @@ __global__ void pp_reset_kernel(PPDev d) {
     }
 }
 
-// one thread per (image, anchor-in-level, class) element; consecutive threads walk classes (contiguous)
+// one warp per anchor row (image, anchor-in-level): lanes stride over the classes (coalesced, no per-element division)
 __global__ void __launch_bounds__(256) pp_candidates_kernel(PPDev d, int lvl) {
     const int K = d.p.K;
     const int hw = d.p.lvl_h[lvl] * d.p.lvl_w[lvl];
-    const long long total = (long long)d.p.B * hw * K;
+    const int rows = d.p.B * hw;
     const float* logits = d.p.logits[lvl];
     const int ld = d.p.ld_logit[lvl];
     const float thr = d.p.score_thr;
     const float logit_lo = d.logit_lo;   // conservative float bound: x < logit_lo  =>  sigmoid(x) <= thr, skip the double evaluation
     const int lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long start = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long iters = (total + stride - 1) / stride;
-    for (long long it = 0; it < iters; ++it) {
-        const long long t = start + it * stride;
-        bool pass = false;
-        unsigned long long key = 0;
-        int b = 0;
-        if (t < total) {
-            const int k = (int)(t % K);
-            const long long row = t / K;  // b*hw + a
-            b = (int)(row / hw);
-            const int a = (int)(row % hw);
-            const float x = logits[row * ld + k];
-            const float s = x < logit_lo ? 0.f : sigmoid_dr(x);
-            if (s > thr) {
-                pass = true;
-                const unsigned int inv = 0x3FFFFFFFu - (__float_as_uint(s) & 0x3FFFFFFFu);
-                const unsigned long long idx = (unsigned long long)(d.lvl_off[lvl] + a) * K + k;
-                key = ((unsigned long long)b << (d.idx_bits + 30)) | ((unsigned long long)inv << d.idx_bits) | idx;
+    const int wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+        const int b = row / hw, a = row - b * hw;
+        const float* lr = logits + (long long)row * ld;
+        const unsigned long long hi = (unsigned long long)b << (d.idx_bits + 30);
+        const unsigned int idx0 = (unsigned int)(d.lvl_off[lvl] + a) * (unsigned int)K;
+        unsigned int npass = 0;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            bool pass = false;
+            unsigned long long key = 0;
+            if (k < K) {
+                const float x = lr[k];
+                const float s = x < logit_lo ? 0.f : sigmoid_dr(x);
+                if (s > thr) {
+                    pass = true;
+                    const unsigned int inv = 0x3FFFFFFFu - (__float_as_uint(s) & 0x3FFFFFFFu);
+                    key = hi | ((unsigned long long)inv << d.idx_bits) | (unsigned long long)(idx0 + k);
+                }
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                unsigned int base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(&d.ctrl->total, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (pass) {
+                    const unsigned long long pos = (unsigned long long)base + __popc(m & ((1u << lane) - 1));
+                    if (pos < d.cap) d.keys0[pos] = key;
+                    else d.ctrl->overflow = 1;
+                }
+                npass += __popc(m);
             }
         }
-        const unsigned int m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            unsigned int base = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) base = atomicAdd(&d.ctrl->total, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (pass) {
-                const unsigned long long pos = (unsigned long long)base + __popc(m & ((1u << lane) - 1));
-                if (pos < d.cap) d.keys0[pos] = key;
-                else d.ctrl->overflow = 1;
-                const unsigned int grp = __match_any_sync(m, b);  // lanes of this warp that hit the same image
-                if (lane == __ffs(grp) - 1) atomicAdd(&d.counts[b], (unsigned int)__popc(grp));
-            }
-        }
+        if (lane == 0 && npass) atomicAdd(&d.counts[b], npass);
     }
 }
 
@@ -539,8 +538,8 @@ struct PostOp : CompiledOp {
         pp_reset_kernel<<<(d.p.B + 255) / 256, 256, 0, s>>>(d);
         count_launch();
         for (int l = 0; l < d.p.nlevels; ++l) {
-            const long long total = (long long)d.p.B * d.p.lvl_h[l] * d.p.lvl_w[l] * d.p.K;
-            long long g = (total + 255) / 256;
+            const long long rows_l = (long long)d.p.B * d.p.lvl_h[l] * d.p.lvl_w[l];
+            long long g = (rows_l + 7) / 8;   // 8 warps (rows) per block
             if (g > 148 * 16) g = 148 * 16;
             pp_candidates_kernel<<<(int)g, 256, 0, s>>>(d, l);
             count_launch();
@@ -572,7 +571,9 @@ struct PostOp : CompiledOp {
                 fprintf(stderr, "[pp] %-16s %.3f ms\n", names[i], ms);
                 tot += ms;
             }
-            fprintf(stderr, "[pp] total %.3f ms (passes %d + %d)\n", tot, passes1, passes2);
+            PPCtrl hc;
+            cudaMemcpy(&hc, d.ctrl, sizeof(hc), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[pp] total %.3f ms (passes %d + %d), candidates %u, selected %u\n", tot, passes1, passes2, hc.total, hc.total2);
             for (int i = 0; i < ne; ++i) cudaEventDestroy(ev[i]);
         }
         return 0;
