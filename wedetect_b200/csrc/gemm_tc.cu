@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_epi = smem + C::kStages * C::STAGE_BYTES;
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
-    uint64_t* bar_empty = bar_full + C::kStages;
-    uint64_t* bar_tfull = bar_empty + C::kStages;
+    uint64_t* bar_empty = bar_full + 8;    // up to 8 stages (pair mode uses 6 half-width stages)
+    uint64_t* bar_tfull = bar_empty + 8;
     uint64_t* bar_tempty = bar_tfull + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
 
@@ -187,19 +187,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         tma_prefetch_desc(&p.tmC[0]);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < C::kStages; ++s) {
+        for (int s = 0; s < 8; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], (uint32_t)p.clu);   // one tcgen05.commit arrival per CTA that reads this stage
+            mbar_init(&bar_empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tfull[a], 1);
-            mbar_init(&bar_tempty[a], 4 * kNumEpiWG);
+            mbar_init(&bar_tempty[a], 4 * kNumEpiWG * p.clu);   // pair mode: the leader waits for both CTAs' epilogues
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-        tmem_relinquish();
+        if (p.clu == 2) {
+            tmem_alloc_2sm(tmem_ptr_smem, C::TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -216,6 +221,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     const int t_first = p.clu == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
     const int t_step = p.clu == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int t_total = p.clu == 2 ? p.num_pair_tiles : p.num_tiles;
+    // pair mode (cta_group::2): each CTA stages its own 128 A rows and HALF of the B tile; one UMMA of M = 256 issued by
+    // the leader reads both halves, so every SM moves 32 KB per k-step through its shared memory instead of 48 KB
+    const int stage_bytes = p.clu == 2 ? (C::A_BYTES + C::B_BYTES / 2) : C::STAGE_BYTES;
+    const int nstages = p.clu == 2 ? (C::kStages * C::STAGE_BYTES) / (C::A_BYTES + C::B_BYTES / 2) : C::kStages;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -231,18 +240,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     const int tap = kit / p.kc_iters, kc = kit - tap * p.kc_iters;
                     const int dx = tap % p.tap_w - p.pad, dy = tap / p.tap_w - p.pad;
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
+                    if (p.clu == 2) {
+                        uint8_t* sA = smem + stage * stage_bytes;
+                        const uint32_t lead_full = mapa_u32(smem_u32(&bar_full[stage]), 0);
+                        if (crank == 0) mbar_arrive_expect_tx(&bar_full[stage], 2u * (uint32_t)(p.rows_a * 128 + C::B_BYTES / 2));
+                        tma_load_4d_2sm(&p.tmA[0], lead_full, sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
+                        tma_load_2d_2sm(&p.tmB[0], lead_full, sA + C::A_BYTES, kit * kBlockK, n_blk * BN + crank * (BN / 2));
+                    } else {
+                        mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
 #pragma unroll
-                    for (int pl = 0; pl < (kSplit ? 3 : 1); ++pl) {
-                        uint8_t* sA = smem + stage * C::STAGE_BYTES + pl * (C::A_BYTES + C::B_BYTES);
-                        tma_load_4d(&p.tmA[pl], &bar_full[stage], sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
-                        if (p.clu == 2)   // this CTA fetches its half of B for both CTAs of the pair
-                            tma_load_2d_mc(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES + crank * (C::B_BYTES / 2), kit * kBlockK,
-                                           n_blk * BN + crank * (BN / 2), (uint16_t)3);
-                        else
+                        for (int pl = 0; pl < (kSplit ? 3 : 1); ++pl) {
+                            uint8_t* sA = smem + stage * C::STAGE_BYTES + pl * (C::A_BYTES + C::B_BYTES);
+                            tma_load_4d(&p.tmA[pl], &bar_full[stage], sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
                             tma_load_2d(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES, kit * kBlockK, n_blk * BN);
+                        }
                     }
-                    if (++stage == C::kStages) {
+                    if (++stage == nstages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -251,8 +264,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && crank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+            constexpr uint32_t idesc2 = umma_idesc_bf16(2 * kTileM, BN);   // M = 256 across the CTA pair
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -272,14 +286,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
                     mbar_wait(&bar_full[stage], phase);
                     tc_fence_after();
-                    const uint32_t s0 = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t s0 = smem_u32(smem + stage * stage_bytes);
                     constexpr uint32_t PL = C::A_BYTES + C::B_BYTES;
                     const uint64_t a0 = umma_desc_sw128(s0), b0 = umma_desc_sw128(s0 + C::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
                         if constexpr (!kSplit) {
-                            umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
+                            if (p.clu == 2) umma_bf16_2sm(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc2, (kit | k) != 0 ? 1u : 0u);
+                            else umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
                         } else {
                             const uint64_t a1 = umma_desc_sw128(s0 + PL), b1 = umma_desc_sw128(s0 + PL + C::A_BYTES);
                             const uint64_t a2 = umma_desc_sw128(s0 + 2 * PL), b2 = umma_desc_sw128(s0 + 2 * PL + C::A_BYTES);
@@ -293,9 +308,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         }
                     }
                     // frees the smem slot when these MMAs retire (in pair mode: tells BOTH producers, whose multicasts fill it)
-                    if (p.clu == 2) umma_commit_mc(&bar_empty[stage], (uint16_t)3);
+                    if (p.clu == 2) umma_commit_2sm_mc(&bar_empty[stage], (uint16_t)3);
                     else umma_commit(&bar_empty[stage]);
-                    if (++stage == C::kStages) {
+                    if (++stage == nstages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -308,7 +323,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     }
                 }
                 if constexpr (!kSplit) {
-                    umma_commit(&bar_tfull[as]);  // accumulator complete -> epilogue
+                    // accumulator complete -> epilogue (of both CTAs in pair mode)
+                    if (p.clu == 2) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
+                    else umma_commit(&bar_tfull[as]);
                     if (++as == 2) {
                         as = 0;
                         aphase ^= 1;
@@ -328,6 +345,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         uint32_t aphase = 0;
         int buf = 0;
         constexpr int n_chunks = BN / CH;
+        // hand an accumulator buffer back to the MMA issuer (the pair leader's barrier in pair mode)
+        auto release_acc = [&](int a) {
+            if (p.clu == 2 && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[a]), 0));
+            else mbar_arrive(&bar_tempty[a]);
+        };
 
         for (int tile = t_first; tile < t_total; tile += t_step) {
             const int m_blk = (tile / p.num_n_tiles) * p.clu + crank, n_blk = tile % p.num_n_tiles;
@@ -508,13 +530,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_tempty[as]);
+                    if (lane == 0) release_acc(as);
                 } else {
                     if (wg >= n_chunks) {
                         // this warpgroup owns no column chunk of the tile (BN == CH): still hand the accumulator back
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_tempty[as]);
+                        if (lane == 0) release_acc(as);
                     }
                     for (int c = wg; c < n_chunks; c += kNumEpiWG) {
                         float v[CH];
@@ -525,7 +547,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                             // last TMEM read of this warp for this tile: hand the accumulator back
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&bar_tempty[as]);
+                            if (lane == 0) release_acc(as);
                         }
                         finish_chunk(v, c);
                     }
@@ -578,7 +600,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_tempty[as]);
+                    if (lane == 0) release_acc(as);
                     if (++as == 2) {
                         as = 0;
                         aphase ^= 1;
@@ -604,7 +626,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         __syncwarp();
         cluster_sync_all();   // the peer may still be arriving on this CTA's barriers
     }
-    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (warp == 2) {
+        if (p.clu == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+        else tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
