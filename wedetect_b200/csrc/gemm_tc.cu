@@ -163,8 +163,12 @@ __device__ __forceinline__ void epi_bias_act(float* v, const float* bias, const 
     }
 }
 
-template <int BN, typename OutT, bool kSplit>
+template <int BN, typename OutT, bool kSplit, bool kPair = false>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+    // kPair: the kernel is launched in clusters of two CTAs and every tcgen05 instruction is the cta_group::2 form (a kernel
+    // may not mix the two forms: ptxas tags it TCGEN05_2CTA_USED and the driver then refuses a launch without clusters)
+    static_assert(!kPair || !kSplit, "pair mode is bf16 single-plane only");
+    constexpr int kClu = kPair ? 2 : 1;
     using C = Cfg<BN, kSplit>;
     constexpr int CH = 128 / (int)sizeof(OutT);  // columns per epilogue chunk (one 128 B swizzle row)
     constexpr bool kOutBf16 = sizeof(OutT) == 2;
@@ -193,12 +197,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tfull[a], 1);
-            mbar_init(&bar_tempty[a], 4 * kNumEpiWG * p.clu);   // pair mode: the leader waits for both CTAs' epilogues
+            mbar_init(&bar_tempty[a], 4 * kNumEpiWG * kClu);   // pair mode: the leader waits for both CTAs' epilogues
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        if (p.clu == 2) {
+        if constexpr (kPair) {
             tmem_alloc_2sm(tmem_ptr_smem, C::TMEM_COLS);
             tmem_relinquish_2sm();
         } else {
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if (p.clu == 2) {
+    if (kPair) {
         __syncwarp();
         cluster_sync_all();   // peer barriers initialised before any multicast can signal them
     }
@@ -217,14 +221,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
 
     const int k_iters = p.kc_iters * p.ntaps;
     // work distribution: plain persistent CTAs, or CTA pairs walking (m-pair, n) tiles in lock step
-    const int crank = p.clu == 2 ? (int)cluster_ctarank() : 0;
-    const int t_first = p.clu == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
-    const int t_step = p.clu == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int t_total = p.clu == 2 ? p.num_pair_tiles : p.num_tiles;
+    const int crank = kPair ? (int)cluster_ctarank() : 0;
+    const int t_first = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int t_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int t_total = kPair ? p.num_pair_tiles : p.num_tiles;
     // pair mode (cta_group::2): each CTA stages its own 128 A rows and HALF of the B tile; one UMMA of M = 256 issued by
     // the leader reads both halves, so every SM moves 32 KB per k-step through its shared memory instead of 48 KB
-    const int stage_bytes = p.clu == 2 ? (C::A_BYTES + C::B_BYTES / 2) : C::STAGE_BYTES;
-    const int nstages = p.clu == 2 ? (C::kStages * C::STAGE_BYTES) / (C::A_BYTES + C::B_BYTES / 2) : C::kStages;
+    const int stage_bytes = kPair ? (C::A_BYTES + C::B_BYTES / 2) : C::STAGE_BYTES;
+    const int nstages = kPair ? (C::kStages * C::STAGE_BYTES) / (C::A_BYTES + C::B_BYTES / 2) : C::kStages;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -233,14 +237,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             uint32_t phase = 0;
             const uint32_t tx_bytes = (kSplit ? 3u : 1u) * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
             for (int tile = t_first; tile < t_total; tile += t_step) {
-                const int m_blk = (tile / p.num_n_tiles) * p.clu + crank, n_blk = tile % p.num_n_tiles;
+                const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
                 const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
                 const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;   // beyond the tensor for the odd pair's ghost tile
                 for (int kit = 0; kit < k_iters; ++kit) {
                     const int tap = kit / p.kc_iters, kc = kit - tap * p.kc_iters;
                     const int dx = tap % p.tap_w - p.pad, dy = tap / p.tap_w - p.pad;
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    if (p.clu == 2) {
+                    if constexpr (kPair) {
                         uint8_t* sA = smem + stage * stage_bytes;
                         const uint32_t lead_full = mapa_u32(smem_u32(&bar_full[stage]), 0);
                         if (crank == 0) mbar_arrive_expect_tx(&bar_full[stage], 2u * (uint32_t)(p.rows_a * 128 + C::B_BYTES / 2));
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
                         if constexpr (!kSplit) {
-                            if (p.clu == 2) umma_bf16_2sm(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc2, (kit | k) != 0 ? 1u : 0u);
+                            if constexpr (kPair) umma_bf16_2sm(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc2, (kit | k) != 0 ? 1u : 0u);
                             else umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
                         } else {
                             const uint64_t a1 = umma_desc_sw128(s0 + PL), b1 = umma_desc_sw128(s0 + PL + C::A_BYTES);
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         }
                     }
                     // frees the smem slot when these MMAs retire (in pair mode: tells BOTH producers, whose multicasts fill it)
-                    if (p.clu == 2) umma_commit_2sm_mc(&bar_empty[stage], (uint16_t)3);
+                    if constexpr (kPair) umma_commit_2sm_mc(&bar_empty[stage], (uint16_t)3);
                     else umma_commit(&bar_empty[stage]);
                     if (++stage == nstages) {
                         stage = 0;
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 }
                 if constexpr (!kSplit) {
                     // accumulator complete -> epilogue (of both CTAs in pair mode)
-                    if (p.clu == 2) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
+                    if constexpr (kPair) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
                     else umma_commit(&bar_tfull[as]);
                     if (++as == 2) {
                         as = 0;
@@ -347,12 +351,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         constexpr int n_chunks = BN / CH;
         // hand an accumulator buffer back to the MMA issuer (the pair leader's barrier in pair mode)
         auto release_acc = [&](int a) {
-            if (p.clu == 2 && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[a]), 0));
+            if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[a]), 0));
             else mbar_arrive(&bar_tempty[a]);
         };
 
         for (int tile = t_first; tile < t_total; tile += t_step) {
-            const int m_blk = (tile / p.num_n_tiles) * p.clu + crank, n_blk = tile % p.num_n_tiles;
+            const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
             const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
             const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
             const int i0 = r % p.E0, i1 = (r / p.E0) % p.E1, i2 = r / (p.E0 * p.E1);
@@ -622,12 +626,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
 
     tc_fence_before();
     __syncthreads();
-    if (p.clu == 2) {
+    if (kPair) {
         __syncwarp();
         cluster_sync_all();   // the peer may still be arriving on this CTA's barriers
     }
     if (warp == 2) {
-        if (p.clu == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+        if constexpr (kPair) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
         else tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
@@ -641,15 +645,15 @@ struct GemmOp : CompiledOp {
     int launch(cudaStream_t s) override;
 };
 
-template <int BN, typename OutT, bool kSplit>
+template <int BN, typename OutT, bool kSplit, bool kPair = false>
 static int launch_inst(const GemmOp& g, cudaStream_t s) {
-    auto kern = gemm_tc_kernel<BN, OutT, kSplit>;
+    auto kern = gemm_tc_kernel<BN, OutT, kSplit, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
         WD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, kSplit>::SMEM_BYTES));
         attr_set = true;
     }
-    if (g.prm.clu == 2) {
+    if constexpr (kPair) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(g.grid);
         cfg.blockDim = dim3(kNumThreads);
@@ -679,6 +683,8 @@ int GemmOp::launch(cudaStream_t s) {
     }
     WD_DISPATCH(64)
     WD_DISPATCH(128)
+    if (block_n == 256 && !split && prm.clu == 2)
+        return out_f32 ? launch_inst<256, float, false, true>(*this, s) : launch_inst<256, __nv_bfloat16, false, true>(*this, s);
     WD_DISPATCH(256)
 #undef WD_DISPATCH
     if (split && block_n == 64) return out_f32 ? launch_inst<64, float, true>(*this, s) : launch_inst<64, __nv_bfloat16, true>(*this, s);
