@@ -6,6 +6,7 @@
 // coalesced along channels.  `*_lo` outputs are the low bf16 plane of the bf16x3 precise mode.
 #include "internal.h"
 #include <functional>
+#include <algorithm>
 #include <math.h>
 
 namespace wd {
@@ -303,394 +304,144 @@ __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// depthwise 7x7 (pad 3) + bias, shared-memory tiled (the production path; LayerNorm follows as ln_rows on the
-// L2-resident fp32 result).
-//   block  = (8*tx) x (4*ty) output pixels x 32 channels of one image  (grid.z = image x channel chunk)
-//   thread = 2 channels x (8 wide x 4 tall) outputs: 64 fp32 accumulators + a sliding window of 4 weight rows;
-//            every halo value is read from smem once per thread and feeds up to 28 FMAs (FMA-pipe bound)
-// L2->SM traffic is (1 + 6/(8tx))(1 + 6/(4ty)) x the input instead of 7x for the register-only kernel above.
-// ------------------------------------------------------------------------------------------------
 constexpr int kDw2CK = 32;
 
-__global__ void __launch_bounds__(192, 2) dwconv7_tiled_kernel(const float* __restrict__ in, int H, int W, int C, int nchunks,
-                                                               const float* __restrict__ wt, const float* __restrict__ bias,
-                                                               float* __restrict__ yscr, int tx, int ty) {
-    extern __shared__ float dsm[];
-    const int HW_ = 8 * tx + 6, HH_ = 4 * ty + 6;
-    float* halo = dsm;                                // [HH_][HW_][32]
-    float* wsm = dsm + HH_ * HW_ * kDw2CK;            // [49][32]
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int pair = tid & 15, tile = tid >> 4;
-    const bool active = tile < tx * ty;
-    const int tix = tile % tx, tiy = tile / tx;
-    const int x0 = blockIdx.x * 8 * tx, y0 = blockIdx.y * 4 * ty;
-    const int bi = blockIdx.z / nchunks, c0 = (blockIdx.z % nchunks) * kDw2CK;
-    const float* inb = in + (long long)bi * H * W * C;
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float unpack_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float unpack_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
-    // ---- cooperative async loads (cp.async 16 B, zero-fill = the conv's zero padding): all requests of a thread
-    //      are in flight together, one memory latency per block instead of one per loop iteration ----
-    {
-        const int npix = HH_ * HW_, pstep = nthr >> 3;   // nthr is a multiple of 32: 8 threads (one 128-byte row) per pixel
-        const int c4 = tid & 7;
-        const bool cok = c0 + c4 * 4 < C;
-        int pix = tid >> 3;
-        int py = pix / HW_, px = pix - py * HW_;           // one division per thread, then incremental stepping
-        const uint32_t sbase = smem_u32(halo + c4 * 4);
-        const float* gbase = inb + c0 + c4 * 4;
-        for (; pix < npix; pix += pstep) {
-            const int gy = y0 - 3 + py, gx = x0 - 3 + px;
-            const bool ok = cok && gy >= 0 && gy < H && gx >= 0 && gx < W;
-            const float* src = ok ? gbase + ((long long)gy * W + gx) * C : inb;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + pix * (kDw2CK * 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
-            px += pstep;
-            while (px >= HW_) {
-                px -= HW_;
-                ++py;
+// ------------------------------------------------------------------------------------------------
+// Depthwise 7x7, persistent + TMA-pipelined (the production path).  One CTA per SM walks a list of work items
+// (image, 8tx x 4ty output tile, 32-channel chunk).  A producer warp streams each item's halo (a rank-4 TMA box whose
+// out-of-bounds part is zero-filled = the conv's zero padding) and its 49x32 weights into a two-slot shared-memory ring;
+// eight consumer warps (two per scheduler) run the FFMA2 loop on one slot while the other slot is in flight, so the SM
+// never stops issuing FMAs to wait for memory and no instruction is spent on addressing the halo.
+//   thread = 2 channels x (8 wide x 4 tall) outputs: 32 packed fp32x2 accumulators + a sliding window of 4 weight rows;
+//            every halo value is read from shared memory once per thread and feeds up to 28 packed FMAs.
+// Measured (B200, stage 2 of WeDetect-Base, bs 32): 87 us per layer = the 3-register-operand FMA issue rate (one FFMA2
+// per 4 cycles per scheduler, i.e. 64 FMA/clk/SM) x the 78 % tile efficiency of a 40x40 map; LayerNorm follows as ln_rows
+// on the L2-resident fp32 result.
+// ------------------------------------------------------------------------------------------------
+struct DwTmaParams {
+    CUtensorMap tm_in;   // fp32 [B][H][W][C], box (32, 8tx+6, 4ty+6, 1)
+    CUtensorMap tm_w;    // fp32 [49][C],      box (32, 49)
+    const float* bias;
+    float* yscr;
+    int H, W, C, nchunks, tx, ty, ntx, nty, num_items;
+};
+constexpr int kDwConsumerWarps = 8;
+
+__global__ void __launch_bounds__((kDwConsumerWarps + 1) * 32, 1) dwconv7_tma_kernel(const __grid_constant__ DwTmaParams p) {
+    extern __shared__ __align__(128) uint8_t dsm_raw[];
+    uint8_t* dsm8 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsm_raw) + 127) & ~uintptr_t(127));
+    const int HW_ = 8 * p.tx + 6, HH_ = 4 * p.ty + 6;
+    const int halo_bytes = HH_ * HW_ * kDw2CK * 4, slot_bytes = halo_bytes + 49 * kDw2CK * 4 + 128 - (49 * kDw2CK * 4) % 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm8 + 2 * slot_bytes);   // full[2], empty[2]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[i], 1);
+            mbar_init(&bars[2 + i], kDwConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int per_img = p.nty * p.ntx * p.nchunks;
+    if (warp == kDwConsumerWarps) {
+        if (lane == 0) {
+            int slot = 0, phase = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                const int bi = item / per_img, r0 = item - bi * per_img;
+                const int ck = r0 % p.nchunks, r1 = r0 / p.nchunks;
+                const int xt = r1 % p.ntx, yt = r1 / p.ntx;
+                mbar_wait(&bars[2 + slot], phase ^ 1);
+                mbar_arrive_expect_tx(&bars[slot], (uint32_t)(halo_bytes + 49 * kDw2CK * 4));
+                uint8_t* dst = dsm8 + slot * slot_bytes;
+                tma_load_4d(&p.tm_in, &bars[slot], dst, ck * kDw2CK, xt * 8 * p.tx - 3, yt * 4 * p.ty - 3, bi);
+                tma_load_2d(&p.tm_w, &bars[slot], dst + halo_bytes, ck * kDw2CK, 0);
+                if (++slot == 2) {
+                    slot = 0;
+                    phase ^= 1;
+                }
             }
         }
+        return;
     }
-    for (int i = tid; i < 49 * 8; i += nthr) {
-        const int c4 = i & 7, tap = i >> 3;
-        const bool ok = c0 + c4 * 4 < C;
-        const float* src = ok ? wt + (long long)tap * C + c0 + c4 * 4 : wt;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(wsm + tap * kDw2CK + c4 * 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
-    }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    if (!active || c0 + pair * 2 >= C) return;
-    float2 acc[4][8];
+    const int pair = tid & 15, tile = tid >> 4;
+    const bool active = tile < p.tx * p.ty;
+    const int tix = tile % p.tx, tiy = tile / p.tx;
+    int slot = 0, phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int bi = item / per_img, r0 = item - bi * per_img;
+        const int ck = r0 % p.nchunks, r1 = r0 / p.nchunks;
+        const int xt = r1 % p.ntx, yt = r1 / p.ntx;
+        const int c0 = ck * kDw2CK, x0 = xt * 8 * p.tx, y0 = yt * 4 * p.ty;
+        mbar_wait(&bars[slot], phase);
+        if (active && c0 + pair * 2 < p.C && y0 + tiy * 4 < p.H && x0 + tix * 8 < p.W) {
+            const float* halo = reinterpret_cast<const float*>(dsm8 + slot * slot_bytes);
+            const float* wsm = reinterpret_cast<const float*>(dsm8 + slot * slot_bytes + halo_bytes);
+            uint64_t acc[4][8];
 #pragma unroll
-    for (int oy = 0; oy < 4; ++oy)
+            for (int oy = 0; oy < 4; ++oy)
 #pragma unroll
-        for (int ox = 0; ox < 8; ++ox) acc[oy][ox] = make_float2(0.f, 0.f);
-    float2 wrow[4][7];
+                for (int ox = 0; ox < 8; ++ox) acc[oy][ox] = 0ull;
+            uint64_t wrow[4][7];
 #pragma unroll
-    for (int oy = 0; oy < 4; ++oy)
+            for (int oy = 0; oy < 4; ++oy)
 #pragma unroll
-        for (int dx = 0; dx < 7; ++dx) wrow[oy][dx] = make_float2(0.f, 0.f);
-    const float* hbase = halo + ((tiy * 4) * HW_ + tix * 8) * kDw2CK + pair * 2;
+                for (int dx = 0; dx < 7; ++dx) wrow[oy][dx] = 0ull;
+            const float* hbase = halo + ((tiy * 4) * HW_ + tix * 8) * kDw2CK + pair * 2;
 #pragma unroll
-    for (int iy = 0; iy < 10; ++iy) {
-        // wrow[oy] holds the weight row dy = iy - oy
+            for (int iy = 0; iy < 10; ++iy) {
+                // wrow[oy] holds the weight row dy = iy - oy
 #pragma unroll
-        for (int oy = 3; oy > 0; --oy)
+                for (int oy = 3; oy > 0; --oy)
 #pragma unroll
-            for (int dx = 0; dx < 7; ++dx) wrow[oy][dx] = wrow[oy - 1][dx];
-        if (iy < 7) {
+                    for (int dx = 0; dx < 7; ++dx) wrow[oy][dx] = wrow[oy - 1][dx];
+                if (iy < 7) {
 #pragma unroll
-            for (int dx = 0; dx < 7; ++dx) wrow[0][dx] = *reinterpret_cast<const float2*>(wsm + (iy * 7 + dx) * kDw2CK + pair * 2);
-        }
-        const float* hrow = hbase + iy * HW_ * kDw2CK;
+                    for (int dx = 0; dx < 7; ++dx) wrow[0][dx] = *reinterpret_cast<const uint64_t*>(wsm + (iy * 7 + dx) * kDw2CK + pair * 2);
+                }
+                const float* hrow = hbase + iy * HW_ * kDw2CK;
 #pragma unroll
-        for (int ix = 0; ix < 14; ++ix) {
-            const float2 v = *reinterpret_cast<const float2*>(hrow + ix * kDw2CK);
+                for (int ix = 0; ix < 14; ++ix) {
+                    const uint64_t v = *reinterpret_cast<const uint64_t*>(hrow + ix * kDw2CK);
 #pragma unroll
-            for (int oy = 0; oy < 4; ++oy) {
-                if (iy - oy >= 0 && iy - oy < 7) {
+                    for (int oy = 0; oy < 4; ++oy) {
+                        if (iy - oy >= 0 && iy - oy < 7) {
 #pragma unroll
-                    for (int ox = 0; ox < 8; ++ox) {
-                        if (ix - ox >= 0 && ix - ox < 7) {
-                            acc[oy][ox].x = fmaf(v.x, wrow[oy][ix - ox].x, acc[oy][ox].x);
-                            acc[oy][ox].y = fmaf(v.y, wrow[oy][ix - ox].y, acc[oy][ox].y);
+                            for (int ox = 0; ox < 8; ++ox) {
+                                if (ix - ox >= 0 && ix - ox < 7) acc[oy][ox] = ffma2(v, wrow[oy][ix - ox], acc[oy][ox]);
+                            }
                         }
                     }
                 }
             }
-        }
-    }
-    const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c0 + pair * 2));
+            const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + c0 + pair * 2));
+            float* obase = p.yscr + (((long long)bi * p.H + y0 + tiy * 4) * p.W + x0 + tix * 8) * p.C + c0 + pair * 2;
 #pragma unroll
-    for (int oy = 0; oy < 4; ++oy) {
-        const int y = y0 + tiy * 4 + oy;
+            for (int oy = 0; oy < 4; ++oy) {
+                if (y0 + tiy * 4 + oy < p.H) {
 #pragma unroll
-        for (int ox = 0; ox < 8; ++ox) {
-            const int x = x0 + tix * 8 + ox;
-            if (y < H && x < W)
-                *reinterpret_cast<float2*>(yscr + (((long long)bi * H + y) * W + x) * C + c0 + pair * 2) =
-                    make_float2(acc[oy][ox].x + b2.x, acc[oy][ox].y + b2.y);
+                    for (int ox = 0; ox < 8; ++ox) {
+                        if (x0 + tix * 8 + ox < p.W)
+                            *reinterpret_cast<float2*>(obase + ((long long)oy * p.W + ox) * p.C) =
+                                make_float2(unpack_lo(acc[oy][ox]) + b2.x, unpack_hi(acc[oy][ox]) + b2.y);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2 + slot]);   // this warp is done reading the slot
+        if (++slot == 2) {
+            slot = 0;
+            phase ^= 1;
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// stem patch gather: NCHW image -> rows [B*(H/4)*(W/4), 64], k = c*16 + dy*4 + dx (48 valid, 16 zero)
-// ------------------------------------------------------------------------------------------------
-template <typename InT>
-__global__ void stem_patch_kernel(const InT* __restrict__ in, int B, int H, int W, float scale, __nv_bfloat16* out_hi, long long out_ps) {
-    const int Wo = W / 4, Ho = H / 4;
-    const long long total = (long long)B * Ho * Wo * 16;  // 16 groups of 4 k-values per row
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int grp = (int)(t & 15);
-        const long long m = t >> 4;
-        const int px = (int)(m % Wo), py = (int)((m / Wo) % Ho), bi = (int)(m / ((long long)Wo * Ho));
-        float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
-        if (grp < 12) {
-            const int ch = grp >> 2, dy = grp & 3;
-            const InT* src = in + (((long long)bi * 3 + ch) * H + (py * 4 + dy)) * W + px * 4;
-            a = (float)src[0] * scale; b = (float)src[1] * scale; c = (float)src[2] * scale; d = (float)src[3] * scale;
-        }
-        store_bf16x4(out_hi, out_ps, m * 64 + grp * 4, a, b, c, d);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// im2col for 3x3 stride-2 pad-1 conv, bf16 NHWC -> rows [B*Ho*Wo, 9*C], k = (ky*3+kx)*C + c
-// ------------------------------------------------------------------------------------------------
-__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, long long in_ps, int B, int H, int W, int C, int ld_in,
-                                 __nv_bfloat16* out, long long out_ps) {
-    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    const int vec = C / 8;
-    const long long total = (long long)B * Ho * Wo * 9 * vec;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(t % vec);
-        long long r = t / vec;
-        const int tap = (int)(r % 9);
-        r /= 9;
-        const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho), bi = (int)(r / ((long long)Wo * Ho));
-        const int iy = oy * 2 + tap / 3 - 1, ix = ox * 2 + tap % 3 - 1;
-        const bool inb = iy >= 0 && iy < H && ix >= 0 && ix < W;
-        const long long src = (((long long)bi * H + iy) * W + ix) * ld_in + cv * 8;
-        const long long dst = r * (9LL * C) + (long long)tap * C + cv * 8;
-        for (int pl = 0; pl < (out_ps ? 3 : 1); ++pl) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (inb) v = *reinterpret_cast<const uint4*>(in + pl * in_ps + src);
-            *reinterpret_cast<uint4*>(out + pl * out_ps + dst) = v;
-        }
-    }
-}
-
-__global__ void cast_bf16_kernel(const float* __restrict__ in, long long rows, int C, int ld_in, int ld_out, __nv_bfloat16* out, long long out_ps) {
-    const int vec = C / 4;
-    const long long total = rows * vec;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long r = t / vec;
-        const int c = (int)(t % vec) * 4;
-        const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
-        store_bf16x4(out, out_ps, r * ld_out + c, v.x, v.y, v.z, v.w);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// XLM-R embeddings + LayerNorm (one warp per token)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) text_embed_kernel(const int* __restrict__ ids, int S, int L, int Hd, int pad_idx, const float* __restrict__ word,
-                                                         const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ lnw,
-                                                         const float* __restrict__ lnb, float eps, float* out_f32, __nv_bfloat16* out_hi,
-                                                         long long out_ps) {
-    const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tok >= S * L) return;
-    const int lane = threadIdx.x & 31;
-    const int s = tok / L, l = tok % L;
-    const int id = ids[tok];
-    int pos_id = pad_idx;
-    if (id != pad_idx) {
-        int cnt = 0;
-        for (int j = 0; j <= l; ++j) cnt += (ids[s * L + j] != pad_idx) ? 1 : 0;
-        pos_id = cnt + pad_idx;
-    }
-    const float* wr = word + (long long)id * Hd;
-    const float* pr = pos + (long long)pos_id * Hd;
-    float4 v[8];  // Hd <= 1024
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < Hd) {
-            const float4 a = *reinterpret_cast<const float4*>(wr + c);
-            const float4 t = *reinterpret_cast<const float4*>(type + c);
-            const float4 p4 = *reinterpret_cast<const float4*>(pr + c);
-            // HF order: inputs_embeds + token_type_embeddings, then + position_embeddings
-            v[i] = make_float4((a.x + t.x) + p4.x, (a.y + t.y) + p4.y, (a.z + t.z) + p4.z, (a.w + t.w) + p4.w);
-            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        }
-    }
-    const float mean = warp_sum(sum) / (float)Hd;
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < Hd) {
-            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-            sq += (a * a + b * b) + (cc * cc + d * d);
-        }
-    }
-    const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)Hd + eps);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < Hd) {
-            const float4 ww = *reinterpret_cast<const float4*>(lnw + c);
-            const float4 bb = *reinterpret_cast<const float4*>(lnb + c);
-            const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x, y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
-            const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z, y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
-            const long long idx = (long long)tok * Hd + c;
-            *reinterpret_cast<float4*>(out_f32 + idx) = make_float4(y0, y1, y2, y3);
-            store_bf16x4(out_hi, out_ps, idx, y0, y1, y2, y3);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// short-sequence attention: one warp per (sequence, head); L <= 32, head_dim == 64.
-// softmax(q k^T * scale + mask) v, masked keys get -inf (== HF additive float-min mask after softmax)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) attn_small_kernel(const float* __restrict__ qkv, const int* __restrict__ mask, int S, int L, int heads, int ld,
-                                                         float scale, __nv_bfloat16* out_hi, long long out_ps) {
-    extern __shared__ float sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = blockIdx.x * 4 + warp;
-    if (pair >= S * heads) return;
-    const int s = pair / heads, h = pair % heads;
-    const int Hd = heads * 64;
-    float* Q = sm + warp * (3 * L * 65);
-    float* K = Q + L * 65;
-    float* V = K + L * 65;
-    for (int t = lane; t < L * 64; t += 32) {
-        const int j = t >> 6, d = t & 63;
-        const float* row = qkv + (long long)(s * L + j) * ld + h * 64 + d;
-        Q[j * 65 + d] = row[0];
-        K[j * 65 + d] = row[Hd];
-        V[j * 65 + d] = row[2 * Hd];
-    }
-    __syncwarp();
-    const bool key_ok = lane < L && mask[s * L + (lane < L ? lane : 0)] != 0;
-    for (int i = 0; i < L; ++i) {
-        float sc = -INFINITY;
-        if (lane < L) {
-            float a = 0.f;
-#pragma unroll 16
-            for (int d = 0; d < 64; ++d) a = fmaf(Q[i * 65 + d], K[lane * 65 + d], a);
-            sc = key_ok ? a * scale : -INFINITY;
-        }
-        const float mx = warp_max(sc);
-        const float e = (lane < L && key_ok) ? expf(sc - mx) : 0.f;
-        const float den = warp_sum(e);
-        const float pj = e / den;
-        float o0 = 0.f, o1 = 0.f;
-        for (int j = 0; j < L; ++j) {
-            const float pp = __shfl_sync(0xffffffffu, pj, j);
-            o0 = fmaf(pp, V[j * 65 + lane], o0);
-            o1 = fmaf(pp, V[j * 65 + lane + 32], o1);
-        }
-        const long long idx = (long long)(s * L + i) * Hd + h * 64;
-        store_bf16x1(out_hi, out_ps, idx + lane, o0);
-        store_bf16x1(out_hi, out_ps, idx + lane + 32, o1);
-    }
-}
-
-__global__ void l2norm_rows_kernel(const float* __restrict__ in, int S, int C, int ld_in, float* out) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= S) return;
-    const int lane = threadIdx.x & 31;
-    float sq = 0.f;
-    for (int c = lane; c < C; c += 32) {
-        const float v = in[(long long)row * ld_in + c];
-        sq += v * v;
-    }
-    const float nrm = fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
-    for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = in[(long long)row * ld_in + c] / nrm;
-}
-
-__global__ void gather_rows_kernel(const float* __restrict__ in, int S, int C, int row_stride, int ld_in, __nv_bfloat16* out, long long out_ps) {
-    const int vec = C / 4;
-    const long long total = (long long)S * vec;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long r = t / vec;
-        const int c = (int)(t % vec) * 4;
-        const float4 v = *reinterpret_cast<const float4*>(in + r * row_stride * ld_in + c);
-        store_bf16x4(out, out_ps, r * C + c, v.x, v.y, v.z, v.w);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// fold BNContrastiveHead (+ optional L2-normalised text) into GEMM weights; one block per class k
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fold_text_kernel(const float* __restrict__ text, int K, int C, int normalize, const float* __restrict__ g,
-                                                        const float* __restrict__ hh, const float* __restrict__ logit_scale, const float* __restrict__ bias,
-                                                        __nv_bfloat16* W, long long W_ps, float* bprime) {
-    __shared__ float red[8];
-    __shared__ float bc;
-    const int k = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (k >= K) {  // zero padding rows
-        for (int c = threadIdx.x; c < C; c += blockDim.x) store_bf16x1(W, W_ps, (long long)k * C + c, 0.f);
-        if (threadIdx.x == 0) bprime[k] = 0.f;
-        return;
-    }
-    const float* t = text + (long long)k * C;
-    float inv = 1.f;
-    if (normalize) {
-        float sq = 0.f;
-        for (int c = threadIdx.x; c < C; c += blockDim.x) sq += t[c] * t[c];
-        sq = warp_sum(sq);
-        if (lane == 0) red[warp] = sq;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float tot = 0.f;
-            for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
-            bc = 1.f / fmaxf(sqrtf(tot), 1e-12f);
-        }
-        __syncthreads();
-        inv = bc;
-        __syncthreads();
-    }
-    const float es = expf(logit_scale[0]);
-    float dot = 0.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float tn = t[c] * inv;
-        const float wv = tn * g[c] * es;
-        store_bf16x1(W, W_ps, (long long)k * C + c, wv);
-        dot += hh[c] * tn;
-    }
-    dot = warp_sum(dot);
-    if (lane == 0) red[warp] = dot;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float tot = 0.f;
-        for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
-        bprime[k] = es * tot + bias[0];
-    }
-}
-
-// kept proposals -> BN'd embedding rows (generate_proposal.py:1129, 1209-1212)
-struct GatherEmbedArgs {
-    const __nv_bfloat16* emb[3];
-    long long emb_ps[3];
-    int lvl_size[3];
-    int nlevels, B, C, max_keep;
-};
-__global__ void gather_embed_kernel(GatherEmbedArgs a, const int* __restrict__ keep_anchor, const int* __restrict__ counts, const float* __restrict__ g,
-                                    const float* __restrict__ hh, float* out) {
-    const int j = blockIdx.x, b = blockIdx.y;
-    float* o = out + ((long long)b * a.max_keep + j) * a.C;
-    if (j >= counts[b]) {
-        for (int c = threadIdx.x; c < a.C; c += blockDim.x) o[c] = 0.f;
-        return;
-    }
-    int anchor = keep_anchor[b * a.max_keep + j];
-    int lvl = 0;
-    while (lvl + 1 < a.nlevels && anchor >= a.lvl_size[lvl]) {
-        anchor -= a.lvl_size[lvl];
-        ++lvl;
-    }
-    const long long row = (long long)b * a.lvl_size[lvl] + anchor;
-    const __nv_bfloat16* e = a.emb[lvl] + row * a.C;
-    const long long eps_ = a.emb_ps[lvl];
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-        float v = __bfloat162float(e[c]);
-        if (eps_) v += __bfloat162float(e[eps_ + c]) + __bfloat162float(e[2 * eps_ + c]);
-        o[c] = v * g[lvl * a.C + c] + hh[lvl * a.C + c];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// host: compile
-// ------------------------------------------------------------------------------------------------
-static int grid_for(long long total, int block) {
-    long long g = (total + block - 1) / block;
-    const long long cap = 148LL * 32;
-    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
 int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
@@ -733,33 +484,57 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const int ld_out = I[4] > 0 ? I[4] : C;
             WD_REQUIRE(ld_out >= C && ld_out % 4 == 0, "dwconv_ln: bad ld_out");
             float* yscr = (float*)P[7];
-            if (yscr) {  // shared-memory tiled conv -> fp32 scratch (L2 resident), then LayerNorm rows -> bf16
+            if (yscr) {  // persistent TMA-pipelined conv -> fp32 scratch (L2 resident), then LayerNorm rows -> bf16
                 const int tx = I[5], ty = I[6];
-                WD_REQUIRE(tx >= 1 && ty >= 1 && tx * ty <= 12 && C % 4 == 0 && C <= kLnMaxVec * 128, "dwconv_ln: bad tile %d x %d", tx, ty);
-                const int thr = ((16 * tx * ty + 31) / 32) * 32;
-                const int smem = ((8 * tx + 6) * (4 * ty + 6) + 49) * kDw2CK * (int)sizeof(float);
-                const int nchunks = (C + kDw2CK - 1) / kDw2CK;
-                WD_REQUIRE(thr <= 192 && smem <= 220 * 1024 && (long long)B * nchunks <= 65535, "dwconv_ln: tile / grid too large");
-                const int rows = B * H * W;
+                WD_REQUIRE(tx >= 1 && ty >= 1 && tx * ty <= 2 * kDwConsumerWarps && C % 4 == 0 && C <= kLnMaxVec * 128, "dwconv_ln: bad tile %d x %d", tx, ty);
+                const int HW_ = 8 * tx + 6, HH_ = 4 * ty + 6;
+                const int halo_bytes = HH_ * HW_ * kDw2CK * 4, slot_bytes = halo_bytes + 49 * kDw2CK * 4 + 128 - (49 * kDw2CK * 4) % 128;
+                const int smem = 2 * slot_bytes + 64 + 128;
+                WD_REQUIRE(HW_ <= 256 && HH_ <= 256 && smem <= 227 * 1024, "dwconv_ln: tile %d x %d needs %d bytes of shared memory", tx, ty, smem);
                 struct DwOp : CompiledOp {
-                    std::function<int(cudaStream_t)> fn;
-                    int launch(cudaStream_t s) override { return fn(s); }
+                    DwTmaParams prm;
+                    int grid, smem, rows, ld_out;
+                    const float *lw, *lb;
+                    float eps;
+                    __nv_bfloat16* oh;
+                    long long ol;
+                    int launch(cudaStream_t s) override {
+                        static bool attr = false;
+                        if (!attr) {
+                            WD_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                            attr = true;
+                        }
+                        dwconv7_tma_kernel<<<grid, (kDwConsumerWarps + 1) * 32, smem, s>>>(prm);
+                        launch_ln_rows(s, prm.yscr, rows, prm.C, prm.C, lw, lb, eps, oh, ol, nullptr, ld_out, 0, 0, 0);
+                        WD_CHECK_CUDA(cudaGetLastError());
+                        count_launch(2);
+                        return 0;
+                    }
                     int num_kernels() const override { return 2; }
                 };
                 auto d = std::make_unique<DwOp>();
-                d->fn = [=](cudaStream_t s) {
-                    static bool attr = false;
-                    if (!attr) {
-                        WD_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                        attr = true;
-                    }
-                    dim3 grid((W + 8 * tx - 1) / (8 * tx), (H + 4 * ty - 1) / (4 * ty), B * nchunks);
-                    dwconv7_tiled_kernel<<<grid, thr, smem, s>>>(in, H, W, C, nchunks, wt, bs, yscr, tx, ty);
-                    launch_ln_rows(s, yscr, rows, C, C, lw, lb, eps, oh, ol, nullptr, ld_out, 0, 0, 0);
-                    WD_CHECK_CUDA(cudaGetLastError());
-                    count_launch(2);
-                    return 0;
-                };
+                DwTmaParams& q = d->prm;
+                q.bias = bs; q.yscr = yscr; q.H = H; q.W = W; q.C = C;
+                q.nchunks = (C + kDw2CK - 1) / kDw2CK;
+                q.tx = tx; q.ty = ty;
+                q.ntx = (W + 8 * tx - 1) / (8 * tx);
+                q.nty = (H + 4 * ty - 1) / (4 * ty);
+                const long long items = (long long)B * q.nty * q.ntx * q.nchunks;
+                WD_REQUIRE(items < (1ll << 31), "dwconv_ln: too many work items");
+                q.num_items = (int)items;
+                {
+                    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+                    const uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+                    const uint32_t box[4] = {(uint32_t)kDw2CK, (uint32_t)HW_, (uint32_t)HH_, 1u};
+                    if (encode_tmap(&q.tm_in, in, 4, 4, dims, str, box, false)) return -1;
+                    const uint64_t wd[2] = {(uint64_t)C, 49};
+                    const uint64_t ws[1] = {(uint64_t)C * 4};
+                    const uint32_t wb[2] = {(uint32_t)kDw2CK, 49u};
+                    if (encode_tmap(&q.tm_w, wt, 4, 2, wd, ws, wb, false)) return -1;
+                }
+                d->grid = (int)std::min<long long>(items, device_sm_count());
+                d->smem = smem; d->rows = B * H * W; d->ld_out = ld_out;
+                d->lw = lw; d->lb = lb; d->eps = eps; d->oh = oh; d->ol = ol;
                 out = std::move(d);
                 return 0;
             }

@@ -229,18 +229,19 @@ def ln_rows(x, w, b, eps, *, out_bf16=None, out_f32=None, s2d_hw=None):
 
 @functools.lru_cache(maxsize=None)
 def pick_dw_tile(W, H):
-    """(tx, ty): block tile = 8tx x 4ty output pixels for the tiled depthwise kernel (<= 16 thread tiles, <= 100 KB smem)."""
+    """(tx, ty): one work item of the persistent depthwise kernel = 8tx x 4ty output pixels x 32 channels, computed by
+    tx*ty <= 16 thread tiles (8 consumer warps); two halo slots of (8tx+6)(4ty+6) x 128 B + weights must fit in shared memory.
+    Every item costs the same time, so the pick maximises useful outputs per item (then prefers the smaller halo)."""
     best = None
-    for tx in range(1, 7):
-        for ty in range(1, 9):
-            if tx * ty > 12 or ((8 * tx + 6) * (4 * ty + 6) + 49) * 128 > 100 * 1024:
+    for tx in range(1, 17):
+        for ty in range(1, 17):
+            slot = (8 * tx + 6) * (4 * ty + 6) * 128 + 6400
+            if tx * ty > 16 or 2 * slot + 192 > 227 * 1024:
                 continue
-            bx, by = -(-W // (8 * tx)), -(-H // (4 * ty))
-            compute = bx * by * 32 * tx * ty
-            halo = bx * by * (8 * tx + 6) * (4 * ty + 6)
-            cost = compute + 0.4 * halo + (0.05 * compute if (tx * ty) % 2 else 0)
-            if best is None or cost < best[0]:
-                best = (cost, (tx, ty))
+            items = -(-W // (8 * tx)) * -(-H // (4 * ty))
+            key = (items, (8 * tx + 6) * (4 * ty + 6))
+            if best is None or key < best[0]:
+                best = (key, (tx, ty))
     return best[1]
 
 
