@@ -315,6 +315,286 @@ __device__ __forceinline__ float unpack_lo(uint64_t v) { return __uint_as_float(
 __device__ __forceinline__ float unpack_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
 // ------------------------------------------------------------------------------------------------
+// stem patch gather: NCHW image -> rows [B*(H/4)*(W/4), 64], k = c*16 + dy*4 + dx (48 valid, 16 zero)
+// ------------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void stem_patch_kernel(const InT* __restrict__ in, int B, int H, int W, float scale, __nv_bfloat16* out_hi, long long out_ps) {
+    const int Wo = W / 4, Ho = H / 4;
+    const long long total = (long long)B * Ho * Wo * 16;  // 16 groups of 4 k-values per row
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int grp = (int)(t & 15);
+        const long long m = t >> 4;
+        const int px = (int)(m % Wo), py = (int)((m / Wo) % Ho), bi = (int)(m / ((long long)Wo * Ho));
+        float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+        if (grp < 12) {
+            const int ch = grp >> 2, dy = grp & 3;
+            const InT* src = in + (((long long)bi * 3 + ch) * H + (py * 4 + dy)) * W + px * 4;
+            a = (float)src[0] * scale; b = (float)src[1] * scale; c = (float)src[2] * scale; d = (float)src[3] * scale;
+        }
+        store_bf16x4(out_hi, out_ps, m * 64 + grp * 4, a, b, c, d);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col for 3x3 stride-2 pad-1 conv, bf16 NHWC -> rows [B*Ho*Wo, 9*C], k = (ky*3+kx)*C + c
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, long long in_ps, int B, int H, int W, int C, int ld_in,
+                                 __nv_bfloat16* out, long long out_ps) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const int vec = C / 8;
+    const long long total = (long long)B * Ho * Wo * 9 * vec;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(t % vec);
+        long long r = t / vec;
+        const int tap = (int)(r % 9);
+        r /= 9;
+        const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho), bi = (int)(r / ((long long)Wo * Ho));
+        const int iy = oy * 2 + tap / 3 - 1, ix = ox * 2 + tap % 3 - 1;
+        const bool inb = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const long long src = (((long long)bi * H + iy) * W + ix) * ld_in + cv * 8;
+        const long long dst = r * (9LL * C) + (long long)tap * C + cv * 8;
+        for (int pl = 0; pl < (out_ps ? 3 : 1); ++pl) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (inb) v = *reinterpret_cast<const uint4*>(in + pl * in_ps + src);
+            *reinterpret_cast<uint4*>(out + pl * out_ps + dst) = v;
+        }
+    }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, long long rows, int C, int ld_in, int ld_out, __nv_bfloat16* out, long long out_ps) {
+    const int vec = C / 4;
+    const long long total = rows * vec;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / vec;
+        const int c = (int)(t % vec) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+        store_bf16x4(out, out_ps, r * ld_out + c, v.x, v.y, v.z, v.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// XLM-R embeddings + LayerNorm (one warp per token)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) text_embed_kernel(const int* __restrict__ ids, int S, int L, int Hd, int pad_idx, const float* __restrict__ word,
+                                                         const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ lnw,
+                                                         const float* __restrict__ lnb, float eps, float* out_f32, __nv_bfloat16* out_hi,
+                                                         long long out_ps) {
+    const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tok >= S * L) return;
+    const int lane = threadIdx.x & 31;
+    const int s = tok / L, l = tok % L;
+    const int id = ids[tok];
+    int pos_id = pad_idx;
+    if (id != pad_idx) {
+        int cnt = 0;
+        for (int j = 0; j <= l; ++j) cnt += (ids[s * L + j] != pad_idx) ? 1 : 0;
+        pos_id = cnt + pad_idx;
+    }
+    const float* wr = word + (long long)id * Hd;
+    const float* pr = pos + (long long)pos_id * Hd;
+    float4 v[8];  // Hd <= 1024
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < Hd) {
+            const float4 a = *reinterpret_cast<const float4*>(wr + c);
+            const float4 t = *reinterpret_cast<const float4*>(type + c);
+            const float4 p4 = *reinterpret_cast<const float4*>(pr + c);
+            // HF order: inputs_embeds + token_type_embeddings, then + position_embeddings
+            v[i] = make_float4((a.x + t.x) + p4.x, (a.y + t.y) + p4.y, (a.z + t.z) + p4.z, (a.w + t.w) + p4.w);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(sum) / (float)Hd;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < Hd) {
+            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + b * b) + (cc * cc + d * d);
+        }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)Hd + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < Hd) {
+            const float4 ww = *reinterpret_cast<const float4*>(lnw + c);
+            const float4 bb = *reinterpret_cast<const float4*>(lnb + c);
+            const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x, y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+            const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z, y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+            const long long idx = (long long)tok * Hd + c;
+            *reinterpret_cast<float4*>(out_f32 + idx) = make_float4(y0, y1, y2, y3);
+            store_bf16x4(out_hi, out_ps, idx, y0, y1, y2, y3);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// short-sequence attention: one warp per (sequence, head); L <= 32, head_dim == 64.
+// softmax(q k^T * scale + mask) v, masked keys get -inf (== HF additive float-min mask after softmax)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_small_kernel(const float* __restrict__ qkv, const int* __restrict__ mask, int S, int L, int heads, int ld,
+                                                         float scale, __nv_bfloat16* out_hi, long long out_ps) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * 4 + warp;
+    if (pair >= S * heads) return;
+    const int s = pair / heads, h = pair % heads;
+    const int Hd = heads * 64;
+    float* Q = sm + warp * (3 * L * 65);
+    float* K = Q + L * 65;
+    float* V = K + L * 65;
+    for (int t = lane; t < L * 64; t += 32) {
+        const int j = t >> 6, d = t & 63;
+        const float* row = qkv + (long long)(s * L + j) * ld + h * 64 + d;
+        Q[j * 65 + d] = row[0];
+        K[j * 65 + d] = row[Hd];
+        V[j * 65 + d] = row[2 * Hd];
+    }
+    __syncwarp();
+    const bool key_ok = lane < L && mask[s * L + (lane < L ? lane : 0)] != 0;
+    for (int i = 0; i < L; ++i) {
+        float sc = -INFINITY;
+        if (lane < L) {
+            float a = 0.f;
+#pragma unroll 16
+            for (int d = 0; d < 64; ++d) a = fmaf(Q[i * 65 + d], K[lane * 65 + d], a);
+            sc = key_ok ? a * scale : -INFINITY;
+        }
+        const float mx = warp_max(sc);
+        const float e = (lane < L && key_ok) ? expf(sc - mx) : 0.f;
+        const float den = warp_sum(e);
+        const float pj = e / den;
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float pp = __shfl_sync(0xffffffffu, pj, j);
+            o0 = fmaf(pp, V[j * 65 + lane], o0);
+            o1 = fmaf(pp, V[j * 65 + lane + 32], o1);
+        }
+        const long long idx = (long long)(s * L + i) * Hd + h * 64;
+        store_bf16x1(out_hi, out_ps, idx + lane, o0);
+        store_bf16x1(out_hi, out_ps, idx + lane + 32, o1);
+    }
+}
+
+__global__ void l2norm_rows_kernel(const float* __restrict__ in, int S, int C, int ld_in, float* out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= S) return;
+    const int lane = threadIdx.x & 31;
+    float sq = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float v = in[(long long)row * ld_in + c];
+        sq += v * v;
+    }
+    const float nrm = fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
+    for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = in[(long long)row * ld_in + c] / nrm;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ in, int S, int C, int row_stride, int ld_in, __nv_bfloat16* out, long long out_ps) {
+    const int vec = C / 4;
+    const long long total = (long long)S * vec;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / vec;
+        const int c = (int)(t % vec) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(in + r * row_stride * ld_in + c);
+        store_bf16x4(out, out_ps, r * C + c, v.x, v.y, v.z, v.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fold BNContrastiveHead (+ optional L2-normalised text) into GEMM weights; one block per class k
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fold_text_kernel(const float* __restrict__ text, int K, int C, int normalize, const float* __restrict__ g,
+                                                        const float* __restrict__ hh, const float* __restrict__ logit_scale, const float* __restrict__ bias,
+                                                        __nv_bfloat16* W, long long W_ps, float* bprime) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int k = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k >= K) {  // zero padding rows
+        for (int c = threadIdx.x; c < C; c += blockDim.x) store_bf16x1(W, W_ps, (long long)k * C + c, 0.f);
+        if (threadIdx.x == 0) bprime[k] = 0.f;
+        return;
+    }
+    const float* t = text + (long long)k * C;
+    float inv = 1.f;
+    if (normalize) {
+        float sq = 0.f;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) sq += t[c] * t[c];
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+            for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+            bc = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+        }
+        __syncthreads();
+        inv = bc;
+        __syncthreads();
+    }
+    const float es = expf(logit_scale[0]);
+    float dot = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float tn = t[c] * inv;
+        const float wv = tn * g[c] * es;
+        store_bf16x1(W, W_ps, (long long)k * C + c, wv);
+        dot += hh[c] * tn;
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+        bprime[k] = es * tot + bias[0];
+    }
+}
+
+// kept proposals -> BN'd embedding rows (generate_proposal.py:1129, 1209-1212)
+struct GatherEmbedArgs {
+    const __nv_bfloat16* emb[3];
+    long long emb_ps[3];
+    int lvl_size[3];
+    int nlevels, B, C, max_keep;
+};
+__global__ void gather_embed_kernel(GatherEmbedArgs a, const int* __restrict__ keep_anchor, const int* __restrict__ counts, const float* __restrict__ g,
+                                    const float* __restrict__ hh, float* out) {
+    const int j = blockIdx.x, b = blockIdx.y;
+    float* o = out + ((long long)b * a.max_keep + j) * a.C;
+    if (j >= counts[b]) {
+        for (int c = threadIdx.x; c < a.C; c += blockDim.x) o[c] = 0.f;
+        return;
+    }
+    int anchor = keep_anchor[b * a.max_keep + j];
+    int lvl = 0;
+    while (lvl + 1 < a.nlevels && anchor >= a.lvl_size[lvl]) {
+        anchor -= a.lvl_size[lvl];
+        ++lvl;
+    }
+    const long long row = (long long)b * a.lvl_size[lvl] + anchor;
+    const __nv_bfloat16* e = a.emb[lvl] + row * a.C;
+    const long long eps_ = a.emb_ps[lvl];
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        float v = __bfloat162float(e[c]);
+        if (eps_) v += __bfloat162float(e[eps_ + c]) + __bfloat162float(e[2 * eps_ + c]);
+        o[c] = v * g[lvl * a.C + c] + hh[lvl * a.C + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: compile
+// ------------------------------------------------------------------------------------------------
+static int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 32;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ------------------------------------------------------------------------------------------------
 // Depthwise 7x7, persistent + TMA-pipelined (the production path).  One CTA per SM walks a list of work items
 // (image, 8tx x 4ty output tile, 32-channel chunk).  A producer warp streams each item's halo (a rank-4 TMA box whose
 // out-of-bounds part is zero-filled = the conv's zero padding) and its 49x32 weights into a two-slot shared-memory ring;
