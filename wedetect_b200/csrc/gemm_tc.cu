@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
 
     const int k_iters = p.kc_iters * p.ntaps;
     // work distribution: plain persistent CTAs, or CTA pairs walking (m-pair, n) tiles in lock step
-    const int crank = kPair ? (int)cluster_ctarank() : 0;
-    const int t_first = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
+    // (cluster dims are (2,1,1): rank and cluster id follow from blockIdx, which the compiler knows to be warp-uniform)
+    const int crank = kPair ? (int)(blockIdx.x & 1) : 0;
+    const int t_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int t_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int t_total = kPair ? p.num_pair_tiles : p.num_tiles;
     // pair mode (cta_group::2): each CTA stages its own 128 A rows and HALF of the B tile; one UMMA of M = 256 issued by
@@ -232,18 +233,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t tx_bytes = (kSplit ? 3u : 1u) * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
-            for (int tile = t_first; tile < t_total; tile += t_step) {
-                const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
-                const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
-                const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;   // beyond the tensor for the odd pair's ghost tile
-                for (int kit = 0; kit < k_iters; ++kit) {
-                    const int tap = kit / p.kc_iters, kc = kit - tap * p.kc_iters;
-                    const int dx = tap % p.tap_w - p.pad, dy = tap / p.tap_w - p.pad;
-                    mbar_wait(&bar_empty[stage], phase ^ 1);
+        // The whole warp walks the loops (warp-uniform values live in uniform registers and feed UTMALDG directly); one
+        // elected lane arms the barrier and issues.  Taps and k-chunks advance by counters: no division per k-step.
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx_bytes = (kSplit ? 3u : 1u) * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
+        for (int tile = t_first; tile < t_total; tile += t_step) {
+            const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
+            const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
+            const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;   // beyond the tensor for the odd pair's ghost tile
+            int kc = 0, tx_ = 0, dy = -p.pad;
+            for (int kit = 0; kit < k_iters; ++kit) {
+                const int dx = tx_ - p.pad;
+                mbar_wait(&bar_empty[stage], phase ^ 1);
+                __syncwarp();
+                if (elect_one()) {
                     if constexpr (kPair) {
                         uint8_t* sA = smem + stage * stage_bytes;
                         const uint32_t lead_full = mapa_u32(smem_u32(&bar_full[stage]), 0);
@@ -259,18 +263,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                             tma_load_2d(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES, kit * kBlockK, n_blk * BN);
                         }
                     }
-                    if (++stage == nstages) {
-                        stage = 0;
-                        phase ^= 1;
+                }
+                __syncwarp();
+                if (++kc == p.kc_iters) {
+                    kc = 0;
+                    if (++tx_ == p.tap_w) {
+                        tx_ = 0;
+                        ++dy;
                     }
+                }
+                if (++stage == nstages) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && crank == 0) {
+        // Same scheme: warp-uniform loops, one elected lane issues the UMMAs and their commits.  The issue loop has to stay
+        // well under 128 cycles per UMMA (the tensor pipe's time for a 128x256x16 step), or the pipe idles between them.
+        if (crank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
             constexpr uint32_t idesc2 = umma_idesc_bf16(2 * kTileM, BN);   // M = 256 across the CTA pair
+            const uint32_t smem0 = smem_u32(smem);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -290,36 +305,47 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
                     mbar_wait(&bar_full[stage], phase);
                     tc_fence_after();
-                    const uint32_t s0 = smem_u32(smem + stage * stage_bytes);
-                    constexpr uint32_t PL = C::A_BYTES + C::B_BYTES;
-                    const uint64_t a0 = umma_desc_sw128(s0), b0 = umma_desc_sw128(s0 + C::A_BYTES);
+                    __syncwarp();
+                    if (elect_one()) {
+                        // descriptor low words: (address >> 4) in 14 bits; +32 bytes along K inside the swizzle atom = +2
+                        const uint32_t a_lo = ((smem0 + (uint32_t)(stage * stage_bytes)) >> 4) & 0x3FFFu;
+                        const uint32_t b_lo = ((smem0 + (uint32_t)(stage * stage_bytes) + C::A_BYTES) >> 4) & 0x3FFFu;
+                        constexpr uint32_t PL = (C::A_BYTES + C::B_BYTES) >> 4;
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-                        if constexpr (!kSplit) {
-                            if constexpr (kPair) umma_bf16_2sm(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc2, (kit | k) != 0 ? 1u : 0u);
-                            else umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
-                        } else {
-                            const uint64_t a1 = umma_desc_sw128(s0 + PL), b1 = umma_desc_sw128(s0 + PL + C::A_BYTES);
-                            const uint64_t a2 = umma_desc_sw128(s0 + 2 * PL), b2 = umma_desc_sw128(s0 + 2 * PL + C::A_BYTES);
-                            const uint32_t tmem_s = tmem_d + 2 * BN;   // second accumulator: the small cross terms
-                            umma_bf16(tmem_s, a0 + 2 * k, b2 + 2 * k, idesc, k != 0 ? 1u : 0u);
-                            umma_bf16(tmem_s, a1 + 2 * k, b1 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_s, a2 + 2 * k, b0 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_s, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_s, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
-                            umma_bf16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, k != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            if constexpr (!kSplit) {
+                                const uint64_t ad = umma_desc_from_lo(a_lo + 2 * k), bd = umma_desc_from_lo(b_lo + 2 * k);
+                                if constexpr (kPair) umma_bf16_2sm(tmem_d, ad, bd, idesc2, (kit | k) != 0 ? 1u : 0u);
+                                else umma_bf16(tmem_d, ad, bd, idesc, (kit | k) != 0 ? 1u : 0u);
+                            } else {
+                                const uint64_t a0 = umma_desc_from_lo(a_lo + 2 * k), b0 = umma_desc_from_lo(b_lo + 2 * k);
+                                const uint64_t a1 = umma_desc_from_lo(a_lo + PL + 2 * k), b1 = umma_desc_from_lo(b_lo + PL + 2 * k);
+                                const uint64_t a2 = umma_desc_from_lo(a_lo + 2 * PL + 2 * k), b2 = umma_desc_from_lo(b_lo + 2 * PL + 2 * k);
+                                const uint32_t tmem_s = tmem_d + 2 * BN;   // second accumulator: the small cross terms
+                                umma_bf16(tmem_s, a0, b2, idesc, k != 0 ? 1u : 0u);
+                                umma_bf16(tmem_s, a1, b1, idesc, 1u);
+                                umma_bf16(tmem_s, a2, b0, idesc, 1u);
+                                umma_bf16(tmem_s, a0, b1, idesc, 1u);
+                                umma_bf16(tmem_s, a1, b0, idesc, 1u);
+                                umma_bf16(tmem_d, a0, b0, idesc, k != 0 ? 1u : 0u);
+                            }
+                        }
+                        // frees the smem slot when these MMAs retire (in pair mode: tells BOTH CTAs' producers)
+                        if constexpr (kPair) umma_commit_2sm_mc(&bar_empty[stage], (uint16_t)3);
+                        else umma_commit(&bar_empty[stage]);
+                        if constexpr (kSplit) umma_commit(&bar_tfull[as]);
+                        else if (kit == k_iters - 1) {
+                            // accumulator complete -> epilogue (of both CTAs in pair mode)
+                            if constexpr (kPair) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
+                            else umma_commit(&bar_tfull[as]);
                         }
                     }
-                    // frees the smem slot when these MMAs retire (in pair mode: tells BOTH producers, whose multicasts fill it)
-                    if constexpr (kPair) umma_commit_2sm_mc(&bar_empty[stage], (uint16_t)3);
-                    else umma_commit(&bar_empty[stage]);
+                    __syncwarp();
                     if (++stage == nstages) {
                         stage = 0;
                         phase ^= 1;
                     }
                     if constexpr (kSplit) {
-                        umma_commit(&bar_tfull[as]);
                         if (++as == 2) {
                             as = 0;
                             aphase ^= 1;
@@ -327,9 +353,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     }
                 }
                 if constexpr (!kSplit) {
-                    // accumulator complete -> epilogue (of both CTAs in pair mode)
-                    if constexpr (kPair) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
-                    else umma_commit(&bar_tfull[as]);
                     if (++as == 2) {
                         as = 0;
                         aphase ^= 1;
