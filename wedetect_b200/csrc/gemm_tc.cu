@@ -139,14 +139,18 @@ __device__ __forceinline__ uint64_t act2_fast(uint64_t x) {
     }
 }
 
-// v[j] = gamma[n] * act(v[j] + bias[n]) over one column chunk
-template <int CH, int ACT, bool kFast>
-__device__ __forceinline__ void epi_bias_act(float* v, const float* bias, const float* gamma, int n_base, int N) {
+// v[j] = gamma[n] * act(v[j] + bias[n]) over one column chunk.
+// kMode 0: generic (null / ragged checks per vector); 1: whole chunk inside N, bias, no gamma; 2: whole chunk, bias and gamma.
+// The checked form costs ~2x the instructions of the math itself, and the epilogue of a short-K GEMM is what bounds its tile
+// time, so the common shapes get the unchecked forms.
+template <int CH, int ACT, bool kFast, int kMode>
+__device__ __forceinline__ void epi_bias_act(float* v, const float* __restrict__ bias, const float* __restrict__ gamma, int n_base, int N) {
 #pragma unroll
     for (int j = 0; j < CH; j += 4) {
         const int n = n_base + j;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        if constexpr (kMode != 0) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        else if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
         if constexpr (kFast && (ACT == WD_ACT_GELU || ACT == WD_ACT_SILU)) {
             upk2(act2_fast<ACT>(add2(pk2(v[j + 0], v[j + 1]), pk2(b4.x, b4.y))), v[j + 0], v[j + 1]);
             upk2(act2_fast<ACT>(add2(pk2(v[j + 2], v[j + 3]), pk2(b4.z, b4.w))), v[j + 2], v[j + 3]);
@@ -156,9 +160,14 @@ __device__ __forceinline__ void epi_bias_act(float* v, const float* bias, const 
             v[j + 2] = act_fn<ACT, kFast>(v[j + 2] + b4.z);
             v[j + 3] = act_fn<ACT, kFast>(v[j + 3] + b4.w);
         }
-        if (gamma && n < N) {
+        if constexpr (kMode == 2) {
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n));
             v[j + 0] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
+        } else if constexpr (kMode == 0) {
+            if (gamma && n < N) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n));
+                v[j + 0] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
+            }
         }
     }
 }
@@ -231,6 +240,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     const int stage_bytes = kPair ? (C::A_BYTES + C::B_BYTES / 2) : C::STAGE_BYTES;
     const int nstages = kPair ? (C::kStages * C::STAGE_BYTES) / (C::A_BYTES + C::B_BYTES / 2) : C::kStages;
 
+    // Register re-balancing between the warpgroups (inside the role branches, so the allocator sees which code runs under
+    // which budget): the producer / MMA / allocator warps need few registers; the epilogue warps hold a 64-column accumulator
+    // slice, a prefetched residual slice and staging addresses each.  128 x 80 + 256 x 208 <= 384 x 168 (the launch allocation).
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (warp == 0) {
         // ================= TMA producer =================
         // The whole warp walks the loops (warp-uniform values live in uniform registers and feed UTMALDG directly); one
@@ -360,7 +374,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         // ================= epilogue warpgroups =================
         const int wg = (warp - 4) >> 2;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
@@ -411,21 +427,30 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 if (n_base < p.N) {  // warp-uniform: whole chunk beyond N is skipped (nothing to store)
                     // ---- math: v = resid*alpha + gamma * act(acc + bias); the activation is uniform per launch ----
                     constexpr bool kFast = kOutBf16 && !kSplit;
+                    // warp-uniform: 1 / 2 = whole chunk inside N with bias (and gamma) -> unchecked forms
+                    const int mode = (p.bias != nullptr && n_base + CH <= p.N) ? (p.gamma ? 2 : 1) : 0;
+#define WD_EPI(ACT, FAST)                                                                        \
+    do {                                                                                         \
+        if (mode == 1) epi_bias_act<CH, ACT, FAST, 1>(v, p.bias, p.gamma, n_base, p.N);          \
+        else if (mode == 2) epi_bias_act<CH, ACT, FAST, 2>(v, p.bias, p.gamma, n_base, p.N);     \
+        else epi_bias_act<CH, ACT, FAST, 0>(v, p.bias, p.gamma, n_base, p.N);                    \
+    } while (0)
                     if (kFast && !p.exact_act) {
                         switch (p.act) {
-                            case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                            case WD_ACT_SILU: epi_bias_act<CH, WD_ACT_SILU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                            case WD_ACT_GELU: epi_bias_act<CH, WD_ACT_GELU, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
-                            default: epi_bias_act<CH, WD_ACT_NONE, kFast>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, kFast, 0>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_SILU: WD_EPI(WD_ACT_SILU, kFast); break;
+                            case WD_ACT_GELU: WD_EPI(WD_ACT_GELU, kFast); break;
+                            default: WD_EPI(WD_ACT_NONE, kFast); break;
                         }
                     } else {
                         switch (p.act) {
-                            case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, false>(v, p.bias, p.gamma, n_base, p.N); break;
-                            case WD_ACT_SILU: epi_bias_act<CH, WD_ACT_SILU, false>(v, p.bias, p.gamma, n_base, p.N); break;
-                            case WD_ACT_GELU: epi_bias_act<CH, WD_ACT_GELU, false>(v, p.bias, p.gamma, n_base, p.N); break;
-                            default: epi_bias_act<CH, WD_ACT_NONE, false>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_RELU: epi_bias_act<CH, WD_ACT_RELU, false, 0>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_SILU: epi_bias_act<CH, WD_ACT_SILU, false, 0>(v, p.bias, p.gamma, n_base, p.N); break;
+                            case WD_ACT_GELU: epi_bias_act<CH, WD_ACT_GELU, false, 0>(v, p.bias, p.gamma, n_base, p.N); break;
+                            default: WD_EPI(WD_ACT_NONE, false); break;
                         }
                     }
+#undef WD_EPI
                     if (rq_valid) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
