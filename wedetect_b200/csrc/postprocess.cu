@@ -50,6 +50,7 @@ struct PPDev {
     // workspace pointers
     unsigned long long *keys0, *keys1, *keys2a, *keys2b;
     unsigned int* hist;
+    unsigned int* totals;   // [32][256] per-pass digit totals (zeroed by pp_reset)
     PPCtrl* ctrl;
     unsigned int *counts, *seg, *nsel, *seg2;
     unsigned int* maxc;     // per image max coordinate (order-preserving uint encoding of float)
@@ -82,10 +83,16 @@ __global__ void pp_reset_kernel(PPDev d) {
         d.counts[t] = 0;
         d.maxc[t] = 0;  // smaller than the encoding of any float
     }
+    if (t < 32 * 256) d.totals[t] = 0;
 }
 
-// one warp per anchor row (image, anchor-in-level): lanes stride over the classes (coalesced, no per-element division)
+// One warp per contiguous range of anchor rows (image, anchor-in-level): lanes stride over the classes (coalesced, no
+// per-element division).  Passing keys are compacted into a per-warp shared-memory buffer and flushed with ONE atomic per
+// ~160 keys (the global append counter is a single address: an atomic per row serialised the whole kernel); the per-image
+// counts are accumulated in a register and flushed when the image changes.
+constexpr int PP_WBUF = 192;
 __global__ void __launch_bounds__(256) pp_candidates_kernel(PPDev d, int lvl) {
+    __shared__ unsigned long long wbuf[8][PP_WBUF];
     const int K = d.p.K;
     const int hw = d.p.lvl_h[lvl] * d.p.lvl_w[lvl];
     const int rows = d.p.B * hw;
@@ -93,48 +100,67 @@ __global__ void __launch_bounds__(256) pp_candidates_kernel(PPDev d, int lvl) {
     const int ld = d.p.ld_logit[lvl];
     const float thr = d.p.score_thr;
     const float logit_lo = d.logit_lo;   // conservative float bound: x < logit_lo  =>  sigmoid(x) <= thr, skip the double evaluation
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int rpw = (rows + nwarps - 1) / nwarps;
+    const int r0 = (blockIdx.x * (blockDim.x >> 5) + w) * rpw;
+    const int r1 = r0 + rpw < rows ? r0 + rpw : rows;
+    unsigned int cnt = 0, img_cnt = 0;   // warp-uniform
+    int cur_b = -1;
+    auto flush = [&]() {
+        if (cnt) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&d.ctrl->total, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (unsigned int i = lane; i < cnt; i += 32) {
+                const unsigned long long pos = (unsigned long long)base + i;
+                if (pos < d.cap) d.keys0[pos] = wbuf[w][i];
+                else d.ctrl->overflow = 1;
+            }
+            cnt = 0;
+            __syncwarp();
+        }
+    };
+    for (int row = r0; row < r1; ++row) {
         const int b = row / hw, a = row - b * hw;
+        if (b != cur_b) {
+            if (lane == 0 && img_cnt) atomicAdd(&d.counts[cur_b], img_cnt);
+            img_cnt = 0;
+            cur_b = b;
+        }
         const float* lr = logits + (long long)row * ld;
         const unsigned long long hi = (unsigned long long)b << (d.idx_bits + 30);
         const unsigned int idx0 = (unsigned int)(d.lvl_off[lvl] + a) * (unsigned int)K;
-        unsigned int npass = 0;
         for (int k0 = 0; k0 < K; k0 += 32) {
             const int k = k0 + lane;
             bool pass = false;
             unsigned long long key = 0;
             if (k < K) {
                 const float x = lr[k];
-                const float s = x < logit_lo ? 0.f : sigmoid_dr(x);
-                if (s > thr) {
+                const float sc = x < logit_lo ? 0.f : sigmoid_dr(x);
+                if (sc > thr) {
                     pass = true;
-                    const unsigned int inv = 0x3FFFFFFFu - (__float_as_uint(s) & 0x3FFFFFFFu);
+                    const unsigned int inv = 0x3FFFFFFFu - (__float_as_uint(sc) & 0x3FFFFFFFu);
                     key = hi | ((unsigned long long)inv << d.idx_bits) | (unsigned long long)(idx0 + k);
                 }
             }
             const unsigned int m = __ballot_sync(0xffffffffu, pass);
             if (m) {
-                unsigned int base = 0;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) base = atomicAdd(&d.ctrl->total, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (pass) {
-                    const unsigned long long pos = (unsigned long long)base + __popc(m & ((1u << lane) - 1));
-                    if (pos < d.cap) d.keys0[pos] = key;
-                    else d.ctrl->overflow = 1;
-                }
-                npass += __popc(m);
+                if (pass) wbuf[w][cnt + __popc(m & ((1u << lane) - 1))] = key;
+                cnt += __popc(m);
+                img_cnt += __popc(m);
+                __syncwarp();
+                if (cnt > PP_WBUF - 32) flush();
             }
         }
-        if (lane == 0 && npass) atomicAdd(&d.counts[b], npass);
     }
+    flush();
+    if (lane == 0 && img_cnt) atomicAdd(&d.counts[cur_b], img_cnt);
 }
 
 // ---------------- stable LSD radix sort (keys only, 8-bit digit) ----------------
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ n_ptr, int shift,
-                                                             unsigned int* __restrict__ hist) {
+                                                             unsigned int* __restrict__ hist, unsigned int* __restrict__ totals) {
     __shared__ unsigned int h[256];
     const unsigned int n = *n_ptr;
     const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
@@ -149,55 +175,41 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long
         }
         __syncthreads();
         hist[(unsigned long long)threadIdx.x * num_tiles + tile] = h[threadIdx.x];
+        if (h[threadIdx.x]) atomicAdd(&totals[threadIdx.x], h[threadIdx.x]);   // 256 addresses: the digit totals of this pass
         __syncthreads();
     }
 }
 
-// exclusive scan of the (digit-major) tile histograms: one block, 8 entries per thread per sweep, shuffle-based
-__global__ void __launch_bounds__(1024) rs_scan_kernel(const unsigned int* __restrict__ n_ptr, unsigned int* __restrict__ hist) {
-    __shared__ unsigned int wsum[32];
-    __shared__ unsigned int carry_s;
+// Exclusive scan of the (digit-major) tile histograms, one warp per digit: the digit's base is the sum of the totals of all
+// smaller digits (accumulated by the histogram kernel), then a coalesced shuffle scan along the digit's row of tiles.
+// 256 independent warps instead of one block sweeping the whole table.
+__global__ void __launch_bounds__(256) rs_scan_kernel(const unsigned int* __restrict__ n_ptr, unsigned int* __restrict__ hist,
+                                                      const unsigned int* __restrict__ totals) {
     const unsigned int n = *n_ptr;
     const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
-    const unsigned long long len = 256ull * num_tiles;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (unsigned long long base = 0; base < len; base += 8192) {
-        const unsigned long long i0 = base + (unsigned long long)threadIdx.x * 8;
-        unsigned int v[8];
+    const int lane = threadIdx.x & 31;
+    const unsigned int digit = blockIdx.x * 8 + (threadIdx.x >> 5);
+    unsigned int part = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (i0 + j < len) ? hist[i0 + j] : 0u;
-        unsigned int tsum = 0;
+    for (int j = 0; j < 8; ++j) {
+        const unsigned int i = lane * 8 + j;
+        if (i < digit) part += totals[i];
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tsum += v[j];
-        unsigned int incl = tsum;   // inclusive warp scan of the thread sums
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    unsigned int run = part;
+    unsigned int* row = hist + (unsigned long long)digit * num_tiles;
+    for (unsigned int t0 = 0; t0 < num_tiles; t0 += 32) {
+        const unsigned int t = t0 + lane;
+        const unsigned int v = t < num_tiles ? row[t] : 0u;
+        unsigned int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
         }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned int w = wsum[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            wsum[lane] = wi - w;   // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        unsigned int run = carry_s + wsum[warp] + (incl - tsum);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (i0 + j < len) hist[i0 + j] = run;
-            run += v[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = run;   // total so far (last thread's running value after its 8 entries)
-        __syncthreads();
+        if (t < num_tiles) row[t] = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -317,11 +329,20 @@ __global__ void __launch_bounds__(256) pp_decode_kernel(PPDev d, const unsigned 
 }
 
 // ---------------- class-aware greedy NMS: one block per (class, image) ----------------
+// IoU > thr with the reference's arithmetic (inter / union in fp32, round-to-nearest, strict compare).  The division is
+// only evaluated when the outcome is not already decided: no overlap -> the quotient is 0 (or NaN): false; otherwise
+// inter vs thr * union with a 1e-6 relative margin (>> the 2^-24 rounding of either side) decides all but razor-edge pairs.
 __device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float area_b, float thr) {
     const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
     const float inter = __fmul_rn(w, h);
+    if (thr > 0.f && !(inter > 0.f)) return false;
     const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    const float q = __fmul_rn(thr, uni);
+    if (q > 1e-30f && q < 1e30f) {
+        if (inter > __fmul_rn(q, 1.000001f)) return true;
+        if (inter < __fmul_rn(q, 0.999999f)) return false;
+    }
     return __fdiv_rn(inter, uni) > thr;
 }
 
@@ -488,7 +509,7 @@ static PPLayout pp_layout(int B, int A, int K, int nms_pre) {
     unsigned long long o = 0;
     L.off_keys0 = o; o = align256(o + cap * 8);
     L.off_keys1 = o; o = align256(o + cap * 8);
-    L.off_hist = o; o = align256(o + tiles * 256 * 4);
+    L.off_hist = o; o = align256(o + (tiles + 32) * 256 * 4);   // tile histograms + 32 passes of digit totals
     L.off_ctrl = o; o = align256(o + sizeof(PPCtrl));
     L.off_counts = o; o = align256(o + (B + 1) * 4ull);
     L.off_seg = o; o = align256(o + (B + 1) * 4ull);
@@ -511,12 +532,13 @@ struct PostOp : CompiledOp {
     PPDev d;
     int passes1, passes2, kernels;
     int num_kernels() const override { return kernels; }
-    int sort(unsigned long long* a, unsigned long long* b, const unsigned int* n_ptr, int passes, cudaStream_t s) {
+    int sort(unsigned long long* a, unsigned long long* b, const unsigned int* n_ptr, int passes, int slot0, cudaStream_t s) {
         for (int p = 0; p < passes; ++p) {
             const unsigned long long* src = (p & 1) ? b : a;
             unsigned long long* dst = (p & 1) ? a : b;
-            rs_hist_kernel<<<RS_GRID, RS_THREADS, 0, s>>>(src, n_ptr, p * 8, d.hist);
-            rs_scan_kernel<<<1, 1024, 0, s>>>(n_ptr, d.hist);
+            unsigned int* tot = d.totals + (size_t)(slot0 + p) * 256;
+            rs_hist_kernel<<<RS_GRID, RS_THREADS, 0, s>>>(src, n_ptr, p * 8, d.hist, tot);
+            rs_scan_kernel<<<32, 256, 0, s>>>(n_ptr, d.hist, tot);
             rs_scatter_kernel<<<RS_GRID, RS_THREADS, 0, s>>>(src, dst, n_ptr, p * 8, d.hist);
             count_launch(3);
         }
@@ -535,24 +557,25 @@ struct PostOp : CompiledOp {
             }
         };
         mark();
-        pp_reset_kernel<<<(d.p.B + 255) / 256, 256, 0, s>>>(d);
+        pp_reset_kernel<<<(d.p.B + 255) / 256 > 32 ? (d.p.B + 255) / 256 : 32, 256, 0, s>>>(d);
         count_launch();
         for (int l = 0; l < d.p.nlevels; ++l) {
             const long long rows_l = (long long)d.p.B * d.p.lvl_h[l] * d.p.lvl_w[l];
-            long long g = (rows_l + 7) / 8;   // 8 warps (rows) per block
-            if (g > 148 * 16) g = 148 * 16;
+            long long g = (rows_l + 63) / 64;   // >= 8 rows per warp, 8 warps per block
+            if (g > 148 * 8) g = 148 * 8;
+            if (g < 1) g = 1;
             pp_candidates_kernel<<<(int)g, 256, 0, s>>>(d, l);
             count_launch();
         }
         mark();
-        if (sort(d.keys0, d.keys1, &d.ctrl->total, passes1, s)) return -2;
+        if (sort(d.keys0, d.keys1, &d.ctrl->total, passes1, 0, s)) return -2;
         mark();
         const unsigned long long* sorted1 = (passes1 & 1) ? d.keys1 : d.keys0;
         pp_segments_kernel<<<1, 32, 0, s>>>(d);
         pp_decode_kernel<<<dim3(32, d.p.B), 256, 0, s>>>(d, sorted1);
         count_launch(2);
         mark();
-        if (sort(d.keys2a, d.keys2b, &d.ctrl->total2, passes2, s)) return -2;
+        if (sort(d.keys2a, d.keys2b, &d.ctrl->total2, passes2, 16, s)) return -2;
         mark();
         const unsigned long long* sorted2 = (passes2 & 1) ? d.keys2b : d.keys2a;
         pp_nms_kernel<<<dim3(d.p.K, d.p.B), 128, 0, s>>>(d, sorted2, kept);
@@ -624,6 +647,7 @@ int compile_postprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     o->d.keys0 = (unsigned long long*)(w + L.off_keys0);
     o->d.keys1 = (unsigned long long*)(w + L.off_keys1);
     o->d.hist = (unsigned int*)(w + L.off_hist);
+    o->d.totals = o->d.hist + (((unsigned long long)p.B * A * p.K + RS_TILE - 1) / RS_TILE + 1) * 256;
     o->d.ctrl = (PPCtrl*)(w + L.off_ctrl);
     o->d.counts = (unsigned int*)(w + L.off_counts);
     o->d.seg = (unsigned int*)(w + L.off_seg);

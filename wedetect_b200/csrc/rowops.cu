@@ -617,7 +617,8 @@ constexpr int kDwConsumerWarps = 8;
 
 __global__ void __launch_bounds__((kDwConsumerWarps + 1) * 32, 1) dwconv7_tma_kernel(const __grid_constant__ DwTmaParams p) {
     extern __shared__ __align__(128) uint8_t dsm_raw[];
-    uint8_t* dsm8 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsm_raw) + 127) & ~uintptr_t(127));
+    // align by offsetting the __shared__ array itself: the pointer keeps its address space, so the loads below are LDS
+    uint8_t* dsm8 = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
     const int HW_ = 8 * p.tx + 6, HH_ = 4 * p.ty + 6;
     const int halo_bytes = HH_ * HW_ * kDw2CK * 4, slot_bytes = halo_bytes + 49 * kDw2CK * 4 + 128 - (49 * kDw2CK * 4) % 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(dsm8 + 2 * slot_bytes);   // full[2], empty[2]
