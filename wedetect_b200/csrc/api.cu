@@ -1,5 +1,6 @@
 // api.cu — C ABI: error plumbing, TMA descriptor encoding, program (op list) executor, CUDA graphs.
 #include "internal.h"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -54,6 +55,11 @@ static EncodeTiledFn get_encode_fn() {
             fn = reinterpret_cast<EncodeTiledFn>(p);
     });
     return fn;
+}
+
+bool pdl_enabled() {
+    static const bool on = getenv("WD_NO_PDL") == nullptr;
+    return on;
 }
 
 int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,

@@ -51,6 +51,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// Every kernel of the op list is launched with programmatic stream serialization: it may become resident (and run its
+// prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous kernel drains, and calls pdl_wait()
+// before it touches global memory.  pdl_launch_dependents() at the top lets the NEXT kernel do the same with this one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     // may not mix the two forms: ptxas tags it TCGEN05_2CTA_USED and the driver then refuses a launch without clusters)
     static_assert(!kPair || !kSplit, "pair mode is bf16 single-plane only");
     constexpr int kClu = kPair ? 2 : 1;
+    pdl_launch_dependents();
     using C = Cfg<BN, kSplit>;
     constexpr int CH = 128 / (int)sizeof(OutT);  // columns per epilogue chunk (one 128 B swizzle row)
     constexpr bool kOutBf16 = sizeof(OutT) == 2;
@@ -239,6 +240,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     // the leader reads both halves, so every SM moves 32 KB per k-step through its shared memory instead of 48 KB
     const int stage_bytes = kPair ? (C::A_BYTES + C::B_BYTES / 2) : C::STAGE_BYTES;
     const int nstages = kPair ? (C::kStages * C::STAGE_BYTES) / (C::A_BYTES + C::B_BYTES / 2) : C::kStages;
+
+    pdl_wait();   // everything above overlapped the previous kernel's tail; from here on global memory is read / written
 
     // Register re-balancing between the warpgroups (inside the role branches, so the allocator sees which code runs under
     // which budget): the producer / MMA / allocator warps need few registers; the epilogue warps hold a 64-column accumulator
@@ -701,23 +704,7 @@ static int launch_inst(const GemmOp& g, cudaStream_t s) {
         WD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, kSplit>::SMEM_BYTES));
         attr_set = true;
     }
-    if constexpr (kPair) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(g.grid);
-        cfg.blockDim = dim3(kNumThreads);
-        cfg.dynamicSmemBytes = Cfg<BN, kSplit>::SMEM_BYTES;
-        cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        WD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g.prm));
-    } else {
-        kern<<<g.grid, kNumThreads, Cfg<BN, kSplit>::SMEM_BYTES, s>>>(g.prm);
-    }
+    WD_CHECK_CUDA(launch_pdl(kern, dim3(g.grid), dim3(kNumThreads), (size_t)Cfg<BN, kSplit>::SMEM_BYTES, s, kPair ? 2 : 1, g.prm));
     WD_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;

@@ -6,6 +6,7 @@
 #include <vector>
 #include <memory>
 #include <atomic>
+#include <utility>
 #include "../../include/wedetect_b200.h"
 #include "common.cuh"
 
@@ -15,6 +16,36 @@ extern std::atomic<uint64_t> g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 
 int device_sm_count();
+
+bool pdl_enabled();   // WD_NO_PDL=1 turns programmatic dependent launch off (A/B measurements)
+
+// Launch with the programmatic-stream-serialization attribute (kernels launched this way call pdl_wait() before touching
+// global memory), optionally as clusters of `cluster_x` CTAs.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster_x;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // A compiled op: validated parameters + prebuilt TMA descriptors; `launch` enqueues its kernel(s).
 struct CompiledOp {

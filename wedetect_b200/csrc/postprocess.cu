@@ -73,6 +73,8 @@ __device__ __forceinline__ float ord_float(unsigned int o) {
 }
 
 __global__ void pp_reset_kernel(PPDev d) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) {
         d.ctrl->total = 0;
@@ -92,6 +94,8 @@ __global__ void pp_reset_kernel(PPDev d) {
 // counts are accumulated in a register and flushed when the image changes.
 constexpr int PP_WBUF = 192;
 __global__ void __launch_bounds__(256) pp_candidates_kernel(PPDev d, int lvl) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ unsigned long long wbuf[8][PP_WBUF];
     const int K = d.p.K;
     const int hw = d.p.lvl_h[lvl] * d.p.lvl_w[lvl];
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(256) pp_candidates_kernel(PPDev d, int lvl) {
 // ---------------- stable LSD radix sort (keys only, 8-bit digit) ----------------
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ n_ptr, int shift,
                                                              unsigned int* __restrict__ hist, unsigned int* __restrict__ totals) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ unsigned int h[256];
     const unsigned int n = *n_ptr;
     const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
@@ -185,6 +191,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long
 // 256 independent warps instead of one block sweeping the whole table.
 __global__ void __launch_bounds__(256) rs_scan_kernel(const unsigned int* __restrict__ n_ptr, unsigned int* __restrict__ hist,
                                                       const unsigned int* __restrict__ totals) {
+    pdl_launch_dependents();
+    pdl_wait();
     const unsigned int n = *n_ptr;
     const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
     const int lane = threadIdx.x & 31;
@@ -215,6 +223,8 @@ __global__ void __launch_bounds__(256) rs_scan_kernel(const unsigned int* __rest
 
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long* __restrict__ out,
                                                                 const unsigned int* __restrict__ n_ptr, int shift, const unsigned int* __restrict__ hist) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ unsigned int wh[RS_THREADS / 32][256];
     const unsigned int n = *n_ptr;
     const unsigned int num_tiles = (n + RS_TILE - 1) / RS_TILE;
@@ -266,6 +276,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 
 // ---------------- segments, decode ----------------
 __global__ void pp_segments_kernel(PPDev d) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned int run = 0, run2 = 0;
         for (int b = 0; b < d.p.B; ++b) {
@@ -284,6 +296,8 @@ __global__ void pp_segments_kernel(PPDev d) {
 }
 
 __global__ void __launch_bounds__(256) pp_decode_kernel(PPDev d, const unsigned long long* __restrict__ sorted) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     const unsigned int ns = d.nsel[b];
     const int K = d.p.K;
@@ -347,6 +361,8 @@ __device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float
 }
 
 __global__ void __launch_bounds__(128) pp_nms_kernel(PPDev d, const unsigned long long* __restrict__ sorted2, float4* __restrict__ kept_scratch) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float4 cbox[128];
     __shared__ float carea[128];
     __shared__ unsigned int cmask[128][4];
@@ -436,6 +452,8 @@ __global__ void __launch_bounds__(128) pp_nms_kernel(PPDev d, const unsigned lon
 }
 
 __global__ void __launch_bounds__(256) pp_finalize_kernel(PPDev d) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int s_warp[8];
     __shared__ int s_base;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -537,9 +555,9 @@ struct PostOp : CompiledOp {
             const unsigned long long* src = (p & 1) ? b : a;
             unsigned long long* dst = (p & 1) ? a : b;
             unsigned int* tot = d.totals + (size_t)(slot0 + p) * 256;
-            rs_hist_kernel<<<RS_GRID, RS_THREADS, 0, s>>>(src, n_ptr, p * 8, d.hist, tot);
-            rs_scan_kernel<<<32, 256, 0, s>>>(n_ptr, d.hist, tot);
-            rs_scatter_kernel<<<RS_GRID, RS_THREADS, 0, s>>>(src, dst, n_ptr, p * 8, d.hist);
+            launch_pdl(rs_hist_kernel, dim3(RS_GRID), dim3(RS_THREADS), (size_t)0, s, 1, src, n_ptr, p * 8, d.hist, tot);
+            launch_pdl(rs_scan_kernel, dim3(32), dim3(256), (size_t)0, s, 1, n_ptr, d.hist, tot);
+            launch_pdl(rs_scatter_kernel, dim3(RS_GRID), dim3(RS_THREADS), (size_t)0, s, 1, src, dst, n_ptr, p * 8, d.hist);
             count_launch(3);
         }
         WD_CHECK_CUDA(cudaGetLastError());
@@ -557,30 +575,30 @@ struct PostOp : CompiledOp {
             }
         };
         mark();
-        pp_reset_kernel<<<(d.p.B + 255) / 256 > 32 ? (d.p.B + 255) / 256 : 32, 256, 0, s>>>(d);
+        launch_pdl(pp_reset_kernel, dim3((d.p.B + 255) / 256 > 32 ? (d.p.B + 255) / 256 : 32), dim3(256), (size_t)0, s, 1, d);
         count_launch();
         for (int l = 0; l < d.p.nlevels; ++l) {
             const long long rows_l = (long long)d.p.B * d.p.lvl_h[l] * d.p.lvl_w[l];
             long long g = (rows_l + 63) / 64;   // >= 8 rows per warp, 8 warps per block
             if (g > 148 * 8) g = 148 * 8;
             if (g < 1) g = 1;
-            pp_candidates_kernel<<<(int)g, 256, 0, s>>>(d, l);
+            launch_pdl(pp_candidates_kernel, dim3((int)g), dim3(256), (size_t)0, s, 1, d, l);
             count_launch();
         }
         mark();
         if (sort(d.keys0, d.keys1, &d.ctrl->total, passes1, 0, s)) return -2;
         mark();
         const unsigned long long* sorted1 = (passes1 & 1) ? d.keys1 : d.keys0;
-        pp_segments_kernel<<<1, 32, 0, s>>>(d);
-        pp_decode_kernel<<<dim3(32, d.p.B), 256, 0, s>>>(d, sorted1);
+        launch_pdl(pp_segments_kernel, dim3(1), dim3(32), (size_t)0, s, 1, d);
+        launch_pdl(pp_decode_kernel, dim3(dim3(32, d.p.B)), dim3(256), (size_t)0, s, 1, d, sorted1);
         count_launch(2);
         mark();
         if (sort(d.keys2a, d.keys2b, &d.ctrl->total2, passes2, 16, s)) return -2;
         mark();
         const unsigned long long* sorted2 = (passes2 & 1) ? d.keys2b : d.keys2a;
-        pp_nms_kernel<<<dim3(d.p.K, d.p.B), 128, 0, s>>>(d, sorted2, kept);
+        launch_pdl(pp_nms_kernel, dim3(dim3(d.p.K, d.p.B)), dim3(128), (size_t)0, s, 1, d, sorted2, kept);
         mark();
-        pp_finalize_kernel<<<d.p.B, 256, 0, s>>>(d);
+        launch_pdl(pp_finalize_kernel, dim3(d.p.B), dim3(256), (size_t)0, s, 1, d);
         count_launch(2);
         mark();
         WD_CHECK_CUDA(cudaGetLastError());

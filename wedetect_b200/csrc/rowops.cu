@@ -54,6 +54,8 @@ constexpr int kLnMaxVec = 12;  // C <= 1536
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, int rows, int C, int ld_in, const float* __restrict__ w,
                                                       const float* __restrict__ b, float eps, __nv_bfloat16* out_hi, long long out_ps,
                                                       float* out_f32, int ld_out, int s2d, int W, int H) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -108,6 +110,8 @@ template <int NV, int R>
 __global__ void __launch_bounds__(256) ln_rows_multi_kernel(const float* __restrict__ in, int rows, int C, int ld_in, const float* __restrict__ w,
                                                             const float* __restrict__ b, float eps, __nv_bfloat16* out_hi, long long out_ps,
                                                             float* out_f32, int ld_out, int s2d, int W, int H) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int wrp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const long long row0 = (long long)wrp * R;
@@ -173,15 +177,15 @@ static void launch_ln_rows(cudaStream_t s, const float* in, int rows, int C, int
                            long long ol, float* of, int ld_out, int s2d, int W, int H) {
     if (C <= 128) {
         const int warps = (rows + 3) / 4;
-        ln_rows_multi_kernel<1, 4><<<(warps + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+        launch_pdl(ln_rows_multi_kernel<1, 4>, dim3((warps + 7) / 8), dim3(256), (size_t)(0), s, 1, in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
     } else if (C <= 256) {
         const int warps = (rows + 3) / 4;
-        ln_rows_multi_kernel<2, 4><<<(warps + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+        launch_pdl(ln_rows_multi_kernel<2, 4>, dim3((warps + 7) / 8), dim3(256), (size_t)(0), s, 1, in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
     } else if (C <= 512) {
         const int warps = (rows + 1) / 2;
-        ln_rows_multi_kernel<4, 2><<<(warps + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+        launch_pdl(ln_rows_multi_kernel<4, 2>, dim3((warps + 7) / 8), dim3(256), (size_t)(0), s, 1, in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
     } else {
-        ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+        launch_pdl(ln_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)(0), s, 1, in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
     }
 }
 
@@ -195,6 +199,8 @@ constexpr int kDwTX = 8, kDwTY = 2;
 __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict__ in, int B, int H, int W, int C, const float* __restrict__ wt,
                                                          const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                          float eps, __nv_bfloat16* out_hi, long long out_ps, int ld_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[kDwTY * kDwTX][12];
     const int cg = threadIdx.x;
     const int c = cg * 4;
@@ -319,6 +325,8 @@ __device__ __forceinline__ float unpack_hi(uint64_t v) { return __uint_as_float(
 // ------------------------------------------------------------------------------------------------
 template <typename InT>
 __global__ void stem_patch_kernel(const InT* __restrict__ in, int B, int H, int W, float scale, __nv_bfloat16* out_hi, long long out_ps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int Wo = W / 4, Ho = H / 4;
     const long long total = (long long)B * Ho * Wo * 16;  // 16 groups of 4 k-values per row
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -340,6 +348,8 @@ __global__ void stem_patch_kernel(const InT* __restrict__ in, int B, int H, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, long long in_ps, int B, int H, int W, int C, int ld_in,
                                  __nv_bfloat16* out, long long out_ps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const int vec = C / 8;
     const long long total = (long long)B * Ho * Wo * 9 * vec;
@@ -362,6 +372,8 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, long long
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, long long rows, int C, int ld_in, int ld_out, __nv_bfloat16* out, long long out_ps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int vec = C / 4;
     const long long total = rows * vec;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -616,6 +628,8 @@ struct DwTmaParams {
 constexpr int kDwConsumerWarps = 8;
 
 __global__ void __launch_bounds__((kDwConsumerWarps + 1) * 32, 1) dwconv7_tma_kernel(const __grid_constant__ DwTmaParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t dsm_raw[];
     // align by offsetting the __shared__ array itself: the pointer keeps its address space, so the loads below are LDS
     uint8_t* dsm8 = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
@@ -785,7 +799,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
                             WD_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                             attr = true;
                         }
-                        dwconv7_tma_kernel<<<grid, (kDwConsumerWarps + 1) * 32, smem, s>>>(prm);
+                        launch_pdl(dwconv7_tma_kernel, dim3(grid), dim3((kDwConsumerWarps + 1) * 32), (size_t)(smem), s, 1, prm);
                         launch_ln_rows(s, prm.yscr, rows, prm.C, prm.C, lw, lb, eps, oh, ol, nullptr, ld_out, 0, 0, 0);
                         WD_CHECK_CUDA(cudaGetLastError());
                         count_launch(2);
@@ -821,7 +835,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             }
             f->fn = [=](cudaStream_t s) {
                 dim3 grid((W + kDwTX - 1) / kDwTX, (H + kDwTY - 1) / kDwTY, B);
-                dwconv7_ln_kernel<<<grid, threads, 0, s>>>(in, B, H, W, C, wt, bs, lw, lb, eps, oh, ol, ld_out);
+                launch_pdl(dwconv7_ln_kernel, dim3(grid), dim3(threads), (size_t)(0), s, 1, in, B, H, W, C, wt, bs, lw, lb, eps, oh, ol, ld_out);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
                 return 0;
@@ -838,8 +852,8 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const long long ol = I[30];
             const long long total = (long long)B * (H / 4) * (W / 4) * 16;
             f->fn = [=](cudaStream_t s) {
-                if (dt == 0) stem_patch_kernel<uint8_t><<<grid_for(total, 256), 256, 0, s>>>((const uint8_t*)in, B, H, W, scale, oh, ol);
-                else stem_patch_kernel<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)in, B, H, W, scale, oh, ol);
+                if (dt == 0) launch_pdl(stem_patch_kernel<uint8_t>, dim3(grid_for(total, 256)), dim3(256), (size_t)0, s, 1, (const uint8_t*)in, B, H, W, scale, oh, ol);
+                else launch_pdl(stem_patch_kernel<float>, dim3(grid_for(total, 256)), dim3(256), (size_t)0, s, 1, (const float*)in, B, H, W, scale, oh, ol);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
                 return 0;
@@ -855,7 +869,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             WD_REQUIRE((inl == 0) == (ol == 0), "im2col_s2: both or neither plane stride");
             const long long total = (long long)B * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * 9 * (C / 8);
             f->fn = [=](cudaStream_t s) {
-                im2col_s2_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, inl, B, H, W, C, ld_in, o, ol);
+                launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, s, 1, in, inl, B, H, W, C, ld_in, o, ol);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
                 return 0;
@@ -869,7 +883,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             __nv_bfloat16* o = (__nv_bfloat16*)P[1];
             const long long ol = I[30];
             f->fn = [=](cudaStream_t s) {
-                cast_bf16_kernel<<<grid_for((long long)rows * (C / 4), 256), 256, 0, s>>>(in, rows, C, ld_in, ld_out, o, ol);
+                launch_pdl(cast_bf16_kernel, dim3(grid_for((long long)rows * (C / 4), 256)), dim3(256), (size_t)0, s, 1, in, rows, C, ld_in, ld_out, o, ol);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
                 return 0;
