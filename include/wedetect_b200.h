@@ -54,7 +54,8 @@ enum wd_op_kind {
      *    25 tap_w (3 for 3x3)  26 pad (1 for 3x3)  27 group_valid (columns of a group present in memory, 0 = group_cols)
      *    28 K_valid (channels of A present in memory, 0 = Kc; TMA zero-fills up to Kc)
      *    29 BK_valid (columns of B present in memory, 0 = ntaps*Kc)
-     *    36 no_pair (1: do not use 2-CTA clusters with TMA multicast for 256-wide tiles)
+     *    36 no_pair (1: do not use 2-CTA clusters (cta_group::2 UMMA) for 256-wide tiles)
+     *    37 no_warp_store (1: one 128-row TMA store per epilogue warpgroup instead of one 32-row store per warp; A/B switch)
      *    35 exact_act (1: erf-GELU / exp-SiLU instead of the MUFU.TANH forms used for bf16 outputs of the fast path)
      *    30 planes (0|1 fast, 3 precise)  31 A plane stride  32 B plane stride  33 C plane stride  34 resid plane stride
      * f: 0 resid_alpha

@@ -32,6 +32,8 @@ constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle atom
 
 struct GemmParams {
     CUtensorMap tmA[3], tmB[3], tmC[3];   // plane 0 (+ planes 1, 2 in the bf16x3 "precise" mode)
+    CUtensorMap tmCw[3];                  // C with a 32-row box: the quarter of the tile one epilogue warp owns (warp_store)
+    int warp_store, w0, w1, w2;           // warp_store: per-warp stores enabled; (w0, w1, w2) = the 32-row sub-brick
     int D0, D1, D2, E0, E1, E2, nt0, nt1, nt2;
     int kc_iters, ntaps, tap_w, pad;
     int N, num_m_tiles, num_n_tiles, num_tiles;
@@ -403,6 +405,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
             const int i0 = r % p.E0, i1 = (r / p.E0) % p.E1, i2 = r / (p.E0 * p.E1);
             const int d0 = o0 + i0, d1 = o1 + i1, d2 = o2 + i2;
+            // first row of this warp's quarter inside the tile brick (per-warp TMA stores)
+            const int qr = quarter * 32;
+            const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
             const bool row_ok = (i2 < p.E2) && d0 < p.D0 && d1 < p.D1 && d2 < p.D2;
             const long long pix = ((long long)d2 * p.D1 + d1) * p.D0 + d0;
 
@@ -513,8 +518,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     constexpr int kOutPlanes = (kSplit && kOutBf16) ? 3 : 1;
 #pragma unroll
                     for (int pl = 0; pl < kOutPlanes; ++pl) {
-                        if (issuer) tma_store_wait_read<C::EPI_BUFS - 1>();  // buffer `buf` no longer being read
-                        named_bar_sync(1 + wg, 128);
+                        // buffer `buf` no longer being read by an earlier store.  warp_store: every warp stages and stores its
+                        // own 32 rows (4 KB of the buffer) with its own bulk groups, so the four warps never wait for each other
+                        if (p.warp_store) {
+                            if (lane == 0) tma_store_wait_read<C::EPI_BUFS - 1>();
+                            __syncwarp();
+                        } else {
+                            if (issuer) tma_store_wait_read<C::EPI_BUFS - 1>();
+                            named_bar_sync(1 + wg, 128);
+                        }
                         if constexpr (kOutBf16) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
@@ -538,10 +550,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                             }
                         }
                         fence_proxy_async_smem();
-                        named_bar_sync(1 + wg, 128);
-                        if (issuer) {
-                            tma_store_5d(&p.tmC[pl], sbuf, c0, o0, o1, o2, g);
-                            tma_store_commit();
+                        if (p.warp_store) {
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_5d(&p.tmCw[pl], sbuf + quarter * 4096, c0, o0 + q0, o1 + q1, o2 + q2, g);
+                                tma_store_commit();
+                            }
+                        } else {
+                            named_bar_sync(1 + wg, 128);
+                            if (issuer) {
+                                tma_store_5d(&p.tmC[pl], sbuf, c0, o0, o1, o2, g);
+                                tma_store_commit();
+                            }
                         }
                     }
                     buf = (buf + 1) % C::EPI_BUFS;
@@ -672,7 +692,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 }
             }
         }
-        if (issuer) tma_store_wait_all<0>();
+        if (p.warp_store ? (lane == 0) : issuer) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -823,6 +843,25 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         uint64_t str[4] = {(uint64_t)sc0 * eb, (uint64_t)sc1 * eb, (uint64_t)sc2 * eb, (uint64_t)(n_groups == 1 ? sc2 * P.D2 : scg) * eb};
         uint32_t box[5] = {(uint32_t)CH, (uint32_t)P.E0, (uint32_t)P.E1, (uint32_t)P.E2, 1};
         if (encode_tmap(&P.tmC[0], op.p[2], eb, 5, dims, str, box, true)) return -1;
+        // per-warp stores (I[37] = 1 turns them off): the 32 rows of one TMEM lane quarter must form a sub-brick (w0, w1, w2).
+        // In-run A/B on B200: -3.8 % on the GELU and residual epilogues of the ConvNeXt stage-2 GEMMs (no warpgroup barriers).
+        P.warp_store = 0;
+        P.w0 = P.w1 = P.w2 = 1;
+        if (I[37] == 0) {
+            if (P.E0 % 32 == 0) { P.w0 = 32; P.warp_store = 1; }
+            else if (32 % P.E0 == 0) {
+                const int r1 = 32 / P.E0;
+                if (P.E1 % r1 == 0) { P.w0 = P.E0; P.w1 = r1; P.warp_store = 1; }
+                else if (r1 % P.E1 == 0 && P.E2 % (r1 / P.E1) == 0) { P.w0 = P.E0; P.w1 = P.E1; P.w2 = r1 / P.E1; P.warp_store = 1; }
+            }
+        }
+        if (P.warp_store) {
+            uint32_t wbox[5] = {(uint32_t)CH, (uint32_t)P.w0, (uint32_t)P.w1, (uint32_t)P.w2, 1};
+            if (encode_tmap(&P.tmCw[0], op.p[2], eb, 5, dims, str, wbox, true)) return -1;
+            if (g->split && !g->out_f32)
+                for (int pl = 1; pl < 3; ++pl)
+                    if (encode_tmap(&P.tmCw[pl], (__nv_bfloat16*)op.p[2] + pl * c_ps, eb, 5, dims, str, wbox, true)) return -1;
+        }
         if (g->split && !g->out_f32) {
             WD_REQUIRE(c_ps > 0, "gemm: precise mode with bf16 output needs a C plane stride");
             for (int pl = 1; pl < 3; ++pl)

@@ -94,6 +94,7 @@ def pick_block_n(N, out_f32=False, split=False):
 
 # activations for which the fast path must use the exact formula (debug / accuracy studies): subset of {ACT_SILU, ACT_GELU}
 import os as _os
+NO_WARP_STORE = 1 if _os.environ.get("WD_NO_WARP_STORE") == "1" else 0   # A/B switch: warpgroup-wide epilogue stores
 EXACT_ACT = {dict(silu=L.ACT_SILU, gelu=L.ACT_GELU)[a] for a in _os.environ.get("WD_EXACT_ACT", "").split(",") if a in ("silu", "gelu")}
 
 
@@ -123,6 +124,7 @@ def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, 
     I[25], I[26] = (3, 1) if ntaps == 9 else (1, 0)
     I[27], I[28], I[29] = group_valid, k_valid, bk_valid
     I[35] = 1 if act in EXACT_ACT else 0
+    I[37] = NO_WARP_STORE
     I[30] = 3 if split else 1
     I[31], I[32], I[33], I[34] = a_ps, w_ps, c_ps, r_ps
     op.f[0] = alpha
