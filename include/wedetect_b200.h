@@ -55,6 +55,8 @@ enum wd_op_kind {
      *    28 K_valid (channels of A present in memory, 0 = Kc; TMA zero-fills up to Kc)
      *    29 BK_valid (columns of B present in memory, 0 = ntaps*Kc)
      *    36 no_pair (1: do not use 2-CTA clusters (cta_group::2 UMMA) for 256-wide tiles)
+     *    38, 39 input width / height of a stride-2 3x3 convolution (both > 0: A is walked with TMA element strides 2, the
+     *           tile / D extents then describe the OUTPUT map); 0 = stride 1
      *    37 no_warp_store (1: one 128-row TMA store per epilogue warpgroup instead of one 32-row store per warp; A/B switch)
      *    35 exact_act (1: erf-GELU / exp-SiLU instead of the MUFU.TANH forms used for bf16 outputs of the fast path)
      *    30 planes (0|1 fast, 3 precise)  31 A plane stride  32 B plane stride  33 C plane stride  34 resid plane stride

@@ -128,6 +128,24 @@ def test_conv3x3(B, H, W, Cin, N):
     report_close(f"conv3x3 {B}x{H}x{W}x{Cin}->{N}", C.reshape(-1, N), ref.reshape(-1, N), rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 40, 40, 128, 128), (1, 37, 29, 96, 64), (3, 80, 80, 256, 256), (2, 20, 20, 64, 192)])
+def test_conv3x3_stride2_into_slice(B, H, W, Cin, N):
+    """3x3 / stride 2 / pad 1 as an implicit GEMM over a TMA map with element strides 2 (no im2col); odd sizes exercise the
+    zero-filled right / bottom halo, the output is a channel slice of a wider buffer (the neck's concat fusion)."""
+    from wedetect_b200 import ops
+    A, Wt = _rand_bf16(B, H, W, Cin, seed=33), _rand_bf16(N, 9 * Cin, seed=34, scale=0.04)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(35))
+    d = _dev()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    buf = torch.full((B, Ho, Wo, N + 64), 3.0, dtype=torch.bfloat16, device=d)
+    C = buf[..., 64:]
+    _run(ops.conv3x3(A.to(d), _pad_taps(Wt, Cin).to(d), C, bias=bias.to(d), act=1, stride=2))
+    w = Wt.float().view(N, 3, 3, Cin).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(A.float().permute(0, 3, 1, 2), w, bias=bias, stride=2, padding=1).relu().permute(0, 2, 3, 1)
+    report_close(f"conv3x3/s2 {B}x{H}x{W}x{Cin}->{N}", C.reshape(-1, N), ref.reshape(-1, N), rtol=1e-2, atol=1e-2)
+    assert float((buf[..., :64].float() - 3).abs().max()) == 0
+
+
 @pytest.mark.parametrize("Cin,Co", [(128, 128), (96, 96), (192, 192)])
 def test_deconv2x2_into_slice(Cin, Co):
     from wedetect_b200 import ops

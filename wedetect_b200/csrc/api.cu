@@ -63,7 +63,7 @@ bool pdl_enabled() {
 }
 
 int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, const uint32_t* elem_strides) {
     EncodeTiledFn fn = get_encode_fn();
     WD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     WD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base %p not 16-byte aligned", base);
@@ -72,7 +72,7 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i];
         bx[i] = box[i];
-        estr[i] = 1;
+        estr[i] = elem_strides ? elem_strides[i] : 1;
         WD_REQUIRE(box[i] >= 1 && box[i] <= 256, "tensor map box[%d]=%u out of range", i, box[i]);
     }
     for (int i = 0; i + 1 < rank; ++i) {

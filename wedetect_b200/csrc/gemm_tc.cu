@@ -38,6 +38,7 @@ struct GemmParams {
     int kc_iters, ntaps, tap_w, pad;
     int N, num_m_tiles, num_n_tiles, num_tiles;
     int act, resid_dtype, ld_res, group_cols, epi_mode, rows_a, exact_act;
+    int a_step;          // 1, or 2 for a stride-2 tap walk (input pixel = 2 * output pixel + tap offset)
     int clu, num_pair_tiles;   // clu == 2: clusters of two CTAs (same n-block, adjacent m-blocks) share B through TMA multicast
     float alpha;
     const float* bias;
@@ -271,14 +272,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         uint8_t* sA = smem + stage * stage_bytes;
                         const uint32_t lead_full = mapa_u32(smem_u32(&bar_full[stage]), 0);
                         if (crank == 0) mbar_arrive_expect_tx(&bar_full[stage], 2u * (uint32_t)(p.rows_a * 128 + C::B_BYTES / 2));
-                        tma_load_4d_2sm(&p.tmA[0], lead_full, sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
+                        tma_load_4d_2sm(&p.tmA[0], lead_full, sA, kc * kBlockK, o0 * p.a_step + dx, o1 * p.a_step + dy, o2);
                         tma_load_2d_2sm(&p.tmB[0], lead_full, sA + C::A_BYTES, kit * kBlockK, n_blk * BN + crank * (BN / 2));
                     } else {
                         mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
 #pragma unroll
                         for (int pl = 0; pl < (kSplit ? 3 : 1); ++pl) {
                             uint8_t* sA = smem + stage * C::STAGE_BYTES + pl * (C::A_BYTES + C::B_BYTES);
-                            tma_load_4d(&p.tmA[pl], &bar_full[stage], sA, kc * kBlockK, o0 + dx, o1 + dy, o2);
+                            tma_load_4d(&p.tmA[pl], &bar_full[stage], sA, kc * kBlockK, o0 * p.a_step + dx, o1 * p.a_step + dy, o2);
                             tma_load_2d(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES, kit * kBlockK, n_blk * BN);
                         }
                     }
@@ -820,11 +821,17 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     // --- A: rank-4 (k, d0, d1, d2), bf16, box (64, E0, E1, E2), 128B swizzle
     {
         WD_REQUIRE(k_valid <= Kc && k_valid % 8 == 0, "gemm: K_valid=%d must be <= Kc and a multiple of 8", k_valid);
-        uint64_t dims[4] = {(uint64_t)k_valid, (uint64_t)P.D0, (uint64_t)P.D1, (uint64_t)P.D2};
+        // stride-2 convolution (I[38], I[39] = input width / height): the tensor map walks the input with element strides
+        // (1, 2, 2, 1), so a box of (2 E0) x (2 E1) source pixels delivers the E0 x E1 pixels one tap needs: no im2col
+        const int in_w = I[38], in_h = I[39];
+        P.a_step = (in_w > 0 && in_h > 0) ? 2 : 1;
+        WD_REQUIRE(P.a_step == 1 || (P.ntaps == 9 && 2 * P.E0 <= 256 && 2 * P.E1 <= 256), "gemm: stride-2 walk needs a 3x3 tap set and E0, E1 <= 128");
+        uint64_t dims[4] = {(uint64_t)k_valid, (uint64_t)(P.a_step == 2 ? in_w : P.D0), (uint64_t)(P.a_step == 2 ? in_h : P.D1), (uint64_t)P.D2};
         uint64_t str[3] = {(uint64_t)sa0 * 2, (uint64_t)sa1 * 2, (uint64_t)sa2 * 2};
-        uint32_t box[4] = {kBlockK, (uint32_t)P.E0, (uint32_t)P.E1, (uint32_t)P.E2};
+        uint32_t box[4] = {kBlockK, (uint32_t)(P.E0 * P.a_step), (uint32_t)(P.E1 * P.a_step), (uint32_t)P.E2};
+        uint32_t est[4] = {1u, (uint32_t)P.a_step, (uint32_t)P.a_step, 1u};
         for (int pl = 0; pl < (g->split ? 3 : 1); ++pl)
-            if (encode_tmap(&P.tmA[pl], (const __nv_bfloat16*)op.p[0] + pl * a_ps, 2, 4, dims, str, box, true)) return -1;
+            if (encode_tmap(&P.tmA[pl], (const __nv_bfloat16*)op.p[0] + pl * a_ps, 2, 4, dims, str, box, true, est)) return -1;
     }
     // --- B: rank-2 (k_total, n)
     {

@@ -56,8 +56,10 @@ struct CompiledOp {
 
 // Encode a tiled bf16/f32 tensor map (rank <= 5).  dims/box are innermost-first; strides are in BYTES
 // for dims 1..rank-1.  swizzle128: inner box must span exactly 128 bytes.
+// elem_strides (optional, innermost-first): traversal stride per dim; box[i] then spans box[i] source elements and
+// delivers ceil(box[i] / elem_strides[i]) of them.
 int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, const uint32_t* elem_strides = nullptr);
 
 int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out);
 int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out);  // LN / dwconv / stem / im2col / cast / text

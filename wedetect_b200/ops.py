@@ -100,7 +100,7 @@ EXACT_ACT = {dict(silu=L.ACT_SILU, gelu=L.ACT_GELU)[a] for a in _os.environ.get(
 
 def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, block_n=None, out_f32=False,
              act=L.ACT_NONE, bias=None, gamma=None, resid=None, ld_res=0, alpha=1.0, group_cols=None, n_groups=1,
-             c_gstride=0, dfl=False, a_ps=0, w_ps=0, c_ps=0, r_ps=0, group_valid=0, k_valid=0, bk_valid=0):
+             c_gstride=0, dfl=False, a_ps=0, w_ps=0, c_ps=0, r_ps=0, group_valid=0, k_valid=0, bk_valid=0, in_wh=None):
     op = WdOp()
     op.kind = L.OP_GEMM
     split = bool(a_ps) and bool(w_ps)
@@ -125,6 +125,8 @@ def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, 
     I[27], I[28], I[29] = group_valid, k_valid, bk_valid
     I[35] = 1 if act in EXACT_ACT else 0
     I[37] = NO_WARP_STORE
+    if in_wh is not None:
+        I[38], I[39] = in_wh
     I[30] = 3 if split else 1
     I[31], I[32], I[33], I[34] = a_ps, w_ps, c_ps, r_ps
     op.f[0] = alpha
@@ -164,24 +166,28 @@ def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_N
                     k_valid=K, bk_valid=K)
 
 
-def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None):
-    """3x3 stride-1 pad-1 convolution as 9 shifted TMA brick loads.  A [B,H,W,Cin], W [N, 9*pad64(Cin)] (tap-major)."""
+def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, stride=1):
+    """3x3 pad-1 convolution (stride 1 or 2) as 9 shifted TMA brick loads.  A [B,H,W,Cin], W [N, 9*pad64(Cin)] (tap-major).
+    stride 2: the A tensor map walks the input with element strides 2 (no im2col); C is [B, ceil(H/2), ceil(W/2), N]."""
     (A, a_ps), (W, w_ps), (C, c_ps), (resid, r_ps) = _tp(A), _tp(W), _tp(C), _tp(resid)
     _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
     B, H, Wd, Cin = A.shape
     N = W.shape[0]
     Kc = (Cin + 63) // 64 * 64
+    assert stride in (1, 2)
+    Ho, Wo = (H - 1) // stride + 1, (Wd - 1) // stride + 1
     assert W.shape[1] == 9 * Kc and Cin % 8 == 0, "W must be [N, 9*pad64(Cin)] (zero padded per tap)"
-    assert C.shape == (B, H, Wd, N) and C.stride(3) == 1
+    assert C.shape == (B, Ho, Wo, N) and C.stride(3) == 1
     ld_res = 0
     if resid is not None:
-        assert resid.shape == (B, H, Wd, N) and resid.stride(3) == 1
+        assert resid.shape == (B, Ho, Wo, N) and resid.stride(3) == 1
         ld_res = resid.stride(2)
-        assert resid.stride(1) == Wd * ld_res and resid.stride(0) == H * Wd * ld_res
-    return gemm_raw(A=A, W=W, C=C, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Kc, k_valid=Cin, ntaps=9, N=N,
+        assert resid.stride(1) == Wo * ld_res and resid.stride(0) == Ho * Wo * ld_res
+    return gemm_raw(A=A, W=W, C=C, dims=(Wo, Ho, B), tile=pick_tile(Wo, Ho, B), Kc=Kc, k_valid=Cin, ntaps=9, N=N,
                     a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
                     c_strides=(C.stride(2), C.stride(1), C.stride(0)), block_n=block_n, out_f32=C.dtype == torch.float32,
-                    act=act, bias=bias, resid=resid, ld_res=ld_res, alpha=alpha, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps, r_ps=r_ps)
+                    act=act, bias=bias, resid=resid, ld_res=ld_res, alpha=alpha, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps, r_ps=r_ps,
+                    in_wh=(Wd, H) if stride == 2 else None)
 
 
 def deconv2x2(A, W, C, bias2):

@@ -106,11 +106,11 @@ class VisionPlan:
                                     resid=None if resid is None else resid.p3_4d, alpha=alpha))
 
     def _conv3x3_s2(self, a, wname, out, *, bias, act):
-        """3x3 stride-2: im2col gather then a plain GEMM (4 small sites in the neck)."""
+        """3x3 stride-2 (4 sites in the neck): implicit GEMM, the A tensor map walks the input with element strides 2."""
         Ho, Wo = (a.H - 1) // 2 + 1, (a.W - 1) // 2 + 1
-        col = self._act(f"im2col.{wname}", a.B, Ho, Wo, 9 * a.C)
-        self.ops.append(ops.im2col_s2(a.p3_4d, col.p3))
-        self._linear(col, wname, out, bias=bias, act=act)
+        o4 = out.p3_4d
+        assert tuple(o4.t.shape[:3]) == (a.B, Ho, Wo), (tuple(o4.t.shape), a.B, Ho, Wo)
+        self.ops.append(ops.conv3x3(a.p3_4d, self._mat(wname), o4, bias=bias, act=act, stride=2))
 
     def _cba1x1(self, a, name, out, act):
         self._linear(a, f"neck.{name}.w", out, bias=self.Wt[f"neck.{name}.b"], act=act)

@@ -119,8 +119,6 @@ def prepare_vision(sd, size, device, *, input_format="f32_rgb", precise=False):
             w, b = _fold_bn(sd, nm + ".block.conv.weight", nm + ".block.bn", schema.BN_EPS_NECK)
             if m["k"] == 1:
                 W.put_mat(nm + ".w", w.reshape(w.shape[0], w.shape[1]))
-            elif m["stride"] == 2:
-                W.put_mat(nm + ".w", _taps_flat(w))
             else:
                 W.put_mat(nm + ".w", _taps(w))
             W.put_f32(nm + ".b", b)
