@@ -212,7 +212,7 @@ def run_ours(args):
     # a fresh process starts with idle clocks / cold TLBs: keep replaying (untimed) until the device has been busy for ~1.5 s,
     # otherwise a 10-step (0.2 s) timed region measures the clock ramp instead of the steady state
     t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 1.5:
+    while time.perf_counter() - t_w < 1.5 and not os.environ.get("WD_BENCH_NO_RAMP"):   # (off under ncu)
         for _ in range(5):
             plan.run()
         torch.cuda.synchronize()
@@ -289,7 +289,16 @@ def run_ours(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     ach = fam[dom]["flops"] / (fam[dom]["ms"] / 1000.0) / 1e12
-    roofline = dict(bound="tensor", kernel=dom, achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=None, peak_source=peak_src,
+    traffic, traffic_note = None, None
+    try:   # DRAM bytes of one representative launch of the dominant kernel, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic_r01.json")))
+        ent = tj["kernels"].get(dom)
+        if ent and (args.size, H, K, B) == ("base", 640, 80, 32):
+            traffic = ent["dram_bytes_per_launch"]
+            traffic_note = f"{ent['launch']}; {tj['source']}"
+    except Exception:
+        pass
+    roofline = dict(bound="tensor", kernel=dom, achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=traffic, traffic_note=traffic_note, peak_source=peak_src,
                     launches_per_step=fam[dom]["launches"], avg_launch_ms=fam[dom]["ms"] / fam[dom]["launches"],
                     share_of_step=fam[dom]["ms"] / total_ms,
                     all_gemm=dict(tflops=gemm_fl / (gemm_ms / 1000) / 1e12, frac=gemm_fl / (gemm_ms / 1000) / 1e12 / peak_tf, share_of_step=gemm_ms / total_ms),
