@@ -124,8 +124,21 @@ enum wd_op_kind {
      * generate_proposal.py:1129,1209-1212.  i: 0 B 1 A 2 C 3 max_keep  4 nlevels 5..7 level sizes
      *    30..32 embed plane strides
      * p: 0..2 embed bf16 per level [B*HW_l, C]  3 keep_anchor i32[B,max]  4 counts i32[B]
-     *    5 bn_g f32[3*C] 6 bn_h f32[3*C] 7 out f32 [B,max,C] */
+     *    5 bn_g f32[3*C] 6 bn_h f32[3*C] 7 out f32 [B,max,C]
+     *    optional (all four or none; eval_retrieval/extract_embedding.py:1181-1190,1238-1260 `scales` / `bias`):
+     *    8 logit_scale per level f32[nlevels]  9 bias per level f32[nlevels]  10 out scales f32[B,max]  11 out bias f32[B,max] */
     WD_OP_GATHER_EMBED = 13,
+    /* Row-scaled cast: out[r,:] = bf16(in[r,:] * exp(scale[r])) for rows r = b*P + j with j < counts[b], else 0.
+     * First stage of retrieval scoring (eval_retrieval/retrieval_metric.py:365-372): the per-proposal exp(scale) is
+     * applied to the embedding row so that the class logits are one GEMM against the text matrix.
+     * i: 0 B 1 P (rows per image) 2 C 30 out plane stride
+     * p: 0 in f32 [B*P, C]  1 scale f32 [B*P] (nullable: 1)  2 counts i32 [B] (nullable: all rows)  3 out bf16 [B*P, C] */
+    WD_OP_SCALE_ROWS = 14,
+    /* Retrieval score reduce: out[b,k] = max_{j < counts[b]} sigmoid(z[b*P+j, k] + bias[b*P+j]); 0 when counts[b] == 0.
+     * eval_retrieval/retrieval_metric.py:372-373 (sigmoid, max over proposals).
+     * i: 0 B 1 P 2 K 3 ldz
+     * p: 0 z f32 [B*P, ldz]  1 bias f32 [B*P] (nullable: 0)  2 counts i32 [B] (nullable: P)  3 out f32 [B, K] */
+    WD_OP_RETR_REDUCE = 15,
 };
 
 enum wd_act { WD_ACT_NONE = 0, WD_ACT_RELU = 1, WD_ACT_SILU = 2, WD_ACT_GELU = 3 };

@@ -58,3 +58,45 @@ def test_all_gather_detections_world2():
         p.join(timeout=60)
     assert [r[1] for r in res] == [[0, 1, 2, 3], [4, 5, 6, 7]]
     assert all(r[2] for r in res)
+
+
+def _gather_rows_worker(rank, world, port, total, q):
+    import torch
+    import torch.distributed as dist
+    from wedetect_b200 import dist as wdist
+    from wedetect_b200.retrieval import gather_rows
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    mine = wdist.shard_indices(total, world, rank)
+    local = torch.stack([torch.full((3,), float(i)) for i in mine]) if len(mine) else torch.zeros(0, 3)
+    full = gather_rows(local, total)
+    q.put((rank, full[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_retrieval_gather_rows_unequal_shards_gloo():
+    """C5's exchange step: ONE fixed-shape all-gather of per-image rows from contiguous, possibly unequal shards."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    total, world, port = 5, 2, 29653
+    ps = [ctx.Process(target=_gather_rows_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+    for r in range(world):
+        assert got[r] == [0.0, 1.0, 2.0, 3.0, 4.0]
+
+
+def test_retrieval_metric_restatement():
+    """evaluate_retrieval_per_class / predictions_from_scores follow retrieval_metric.py:14-47,374-377."""
+    import torch
+    from wedetect_b200.retrieval import evaluate_retrieval_per_class, predictions_from_scores
+    scores = torch.tensor([[0.9, 0.1, 0.31], [0.2, 0.8, 0.3], [0.5, 0.5, 0.0]])
+    pred = predictions_from_scores(scores, [7, 8, 9], ["a", "b", "c"], thre=0.3)
+    assert pred == {"a": [7, 9], "b": [8, 9], "c": [7]}          # strict >, ids in image order
+    res = evaluate_retrieval_per_class(pred, {"a": {7}, "b": {8, 9, 10}, "c": set(), "d": {1}})
+    assert res["a"] == dict(precision=0.5, recall=1.0, f1=0.6667, support=1, n_pred=2)
+    assert res["b"] == dict(precision=1.0, recall=0.6667, f1=0.8, support=3, n_pred=2)
+    assert "c" not in res and res["d"]["recall"] == 0.0

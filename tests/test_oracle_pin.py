@@ -125,3 +125,36 @@ def test_c_postprocess_matches_torch_reference_ops(offsets_always):
     assert n == len(ts)
     assert torch.equal(det["anchors"][0, :n].long(), ta) and torch.equal(det["labels"][0, :n].long(), tl)
     assert torch.equal(det["scores"][0, :n], ts) and torch.equal(det["boxes"][0, :n], tb.clamp(min=0))
+
+
+def test_retrieval_oracle_matches_reference_goldens():
+    """oracle/retrieval.py against the outputs of the reference's own extract_embedding.head_predict and the
+    reference's own retrieval_metric.py scoring lines (tests/golden/make_golden_retrieval.py)."""
+    from oracle import retrieval as R, synth
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "reference_retrieval.pt"))
+    sd = synth.synth_state_dict("base", seed=0, uni=True, regime="sparse")
+    x = synth.synth_images(2, 320, 320, seed=2)
+    with torch.no_grad():
+        res = R.extract_ref(sd, "base", x)
+    text = torch.nn.functional.normalize(torch.randn(80, 768, generator=torch.Generator().manual_seed(gold["text_seed"])), dim=-1)
+    pred = {"image_embedding": [], "text_embedding": text}
+    for i, (r, g) in enumerate(zip(res, gold["proposals"])):
+        n = len(g["scores"])
+        assert len(r["scores"]) == n
+        torch.testing.assert_close(r["scores"], g["scores"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(r["bboxes"], g["bboxes"].clamp(min=0), rtol=1e-4, atol=1e-3)
+        assert torch.equal(r["labels"], g["labels"])
+        assert torch.equal(r["scales"], g["scales"]) and torch.equal(r["bias"], g["bias"])
+        _digest_close(r["embeddings"], g["embeddings"])
+        pred["image_embedding"].append(dict(image_id=100 + i, embedding=r["embeddings"], scale=r["scales"], bias=r["bias"]))
+        s = R.image_scores_ref(r["embeddings"], text, r["scales"], r["bias"])
+        torch.testing.assert_close(s, gold["scores"][i], rtol=1e-4, atol=1e-5)
+    classnames = [f"class_{k}" for k in range(80)]
+    for thre in (0.3, 0.01):
+        got, want = R.predictions_ref(pred, classnames, thre), gold[f"predictions_{thre}"]
+        # identical up to scores within 1e-5 of the threshold (the oracle's embeddings differ from the reference's in the last bits)
+        near = {(classnames[k], 100 + i) for i in range(2) for k in range(80) if abs(float(gold["scores"][i, k]) - thre) < 1e-5}
+        for c in classnames:
+            assert {(c, i) for i in got[c]} ^ {(c, i) for i in want[c]} <= near
+    got = R.predictions_ref(pred, classnames, 0.55, model="hqclip")
+    assert sum(len(v) for v in got.values()) == sum(len(v) for v in gold["predictions_hqclip_0.55"].values())

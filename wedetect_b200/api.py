@@ -3,12 +3,16 @@
     infer_wedetect.py:      from mmdet.apis import init_detector        ->  from wedetect_b200.api import init_detector
                             from mmengine.config import Config          ->  from wedetect_b200.api import Config
     generate_proposal.py:   SimpleYOLOWorldDetector(...)                ->  from wedetect_b200.api import SimpleYOLOWorldDetector
+    eval_retrieval/extract_embedding.py:  SimpleYOLOWorldDetector(...)  ->  SimpleYOLOWorldDetector(..., extract=True) + extract_corpus
+    eval_retrieval/retrieval_metric.py:   the per-image scoring loop    ->  score_saved / predictions_from_scores / evaluate_retrieval_per_class
 See INTEGRATION.md for the exact diffs.
 """
 import torch
 
 from .config import Config, parse_cfg_options  # noqa: F401
 from .detector import SimpleYOLOWorldDetector, YOLOWorldDetector  # noqa: F401
+from .retrieval import (RetrievalScorer, evaluate_retrieval_per_class, extract_corpus, predictions_from_scores,  # noqa: F401
+                        save_corpus, score_saved)
 from .structures import DetDataSample, InstanceData  # noqa: F401
 
 

@@ -108,7 +108,9 @@ static int compile_op(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         case WD_OP_L2NORM_ROWS:
         case WD_OP_GATHER_ROWS:
         case WD_OP_FOLD_TEXT:
-        case WD_OP_GATHER_EMBED: return compile_rowops(op, out);
+        case WD_OP_GATHER_EMBED:
+        case WD_OP_SCALE_ROWS:
+        case WD_OP_RETR_REDUCE: return compile_rowops(op, out);
         default: set_last_error("unknown op kind %d", op.kind); return -1;
     }
 }

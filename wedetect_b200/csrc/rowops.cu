@@ -573,12 +573,18 @@ struct GatherEmbedArgs {
     int lvl_size[3];
     int nlevels, B, C, max_keep;
 };
+// optional (extract_embedding.py:1181-1190,1253-1260): per kept proposal the logit_scale / bias of its pyramid level
 __global__ void gather_embed_kernel(GatherEmbedArgs a, const int* __restrict__ keep_anchor, const int* __restrict__ counts, const float* __restrict__ g,
-                                    const float* __restrict__ hh, float* out) {
+                                    const float* __restrict__ hh, float* out, const float* __restrict__ lvl_scale, const float* __restrict__ lvl_bias,
+                                    float* out_scale, float* out_bias) {
     const int j = blockIdx.x, b = blockIdx.y;
     float* o = out + ((long long)b * a.max_keep + j) * a.C;
     if (j >= counts[b]) {
         for (int c = threadIdx.x; c < a.C; c += blockDim.x) o[c] = 0.f;
+        if (threadIdx.x == 0 && out_scale) {
+            out_scale[b * a.max_keep + j] = 0.f;
+            out_bias[b * a.max_keep + j] = 0.f;
+        }
         return;
     }
     int anchor = keep_anchor[b * a.max_keep + j];
@@ -587,6 +593,10 @@ __global__ void gather_embed_kernel(GatherEmbedArgs a, const int* __restrict__ k
         anchor -= a.lvl_size[lvl];
         ++lvl;
     }
+    if (threadIdx.x == 0 && out_scale) {
+        out_scale[b * a.max_keep + j] = lvl_scale[lvl];
+        out_bias[b * a.max_keep + j] = lvl_bias[lvl];
+    }
     const long long row = (long long)b * a.lvl_size[lvl] + anchor;
     const __nv_bfloat16* e = a.emb[lvl] + row * a.C;
     const long long eps_ = a.emb_ps[lvl];
@@ -594,6 +604,56 @@ __global__ void gather_embed_kernel(GatherEmbedArgs a, const int* __restrict__ k
         float v = __bfloat162float(e[c]);
         if (eps_) v += __bfloat162float(e[eps_ + c]) + __bfloat162float(e[2 * eps_ + c]);
         o[c] = v * g[lvl * a.C + c] + hh[lvl * a.C + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Retrieval scoring (eval_retrieval/retrieval_metric.py:362-374): per image
+//     max_j sigmoid( (emb[j] . text[k]) * exp(scale[j]) + bias[j] )
+// = scale_rows (emb * exp(scale) -> bf16 GEMM operand) -> tensor-core GEMM against the text matrix -> retr_reduce.
+// ------------------------------------------------------------------------------------------------
+__global__ void scale_rows_kernel(const float* __restrict__ in, const float* __restrict__ scale, const int* __restrict__ counts, long long rows, int P,
+                                  int C, __nv_bfloat16* out, long long out_ps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int vec = C / 4;
+    const long long total = rows * vec;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / vec;
+        const int c = (int)(t % vec) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool valid = counts == nullptr || (int)(r % P) < counts[r / P];
+        if (valid) {
+            v = *reinterpret_cast<const float4*>(in + r * C + c);
+            const float es = scale ? expf(scale[r]) : 1.f;
+            v.x *= es; v.y *= es; v.z *= es; v.w *= es;
+        }
+        store_bf16x4(out, out_ps, r * C + c, v.x, v.y, v.z, v.w);
+    }
+}
+
+constexpr int kRetrJ = 4;   // proposal lanes per block (blockDim.y)
+__global__ void __launch_bounds__(128 * kRetrJ) retr_reduce_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ bias,
+                                                                   const int* __restrict__ counts, int P, int K, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float red[kRetrJ][128];
+    const int k = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+    const int n = counts ? min(counts[b], P) : P;
+    float m = 0.f;   // sigmoid > 0: an image without proposals scores 0 everywhere
+    if (k < K) {
+        const float* zb = z + (long long)b * P * ldz + k;
+        for (int j = threadIdx.y; j < n; j += kRetrJ) {
+            const float v = zb[(long long)j * ldz] + (bias ? bias[b * P + j] : 0.f);
+            m = fmaxf(m, 1.f / (1.f + expf(-v)));
+        }
+    }
+    red[threadIdx.y][threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.y == 0 && k < K) {
+#pragma unroll
+        for (int y = 1; y < kRetrJ; ++y) m = fmaxf(m, red[y][threadIdx.x]);
+        out[(long long)b * K + k] = m;
     }
 }
 
@@ -987,8 +1047,41 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const int* cnt = (const int*)P[4];
             const float *g = (const float*)P[5], *hh = (const float*)P[6];
             float* o = (float*)P[7];
+            const float *ls = (const float*)P[8], *lb = (const float*)P[9];
+            float *os = (float*)P[10], *ob = (float*)P[11];
+            WD_REQUIRE((os == nullptr) == (ob == nullptr) && (os == nullptr || (ls && lb)), "gather_embed: scale / bias outputs need both outputs and both level tables");
             f->fn = [=](cudaStream_t s) {
-                gather_embed_kernel<<<dim3(a.max_keep, a.B), 128, 0, s>>>(a, ka, cnt, g, hh, o);
+                gather_embed_kernel<<<dim3(a.max_keep, a.B), 128, 0, s>>>(a, ka, cnt, g, hh, o, ls, lb, os, ob);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_SCALE_ROWS: {
+            const int B = I[0], Pn = I[1], C = I[2];
+            WD_REQUIRE(B > 0 && Pn > 0 && C > 0 && C % 4 == 0 && P[0] && P[3], "scale_rows: bad arguments");
+            const float *in = (const float*)P[0], *sc = (const float*)P[1];
+            const int* cnt = (const int*)P[2];
+            __nv_bfloat16* o = (__nv_bfloat16*)P[3];
+            const long long ol = I[30];
+            const long long rows = (long long)B * Pn;
+            f->fn = [=](cudaStream_t s) {
+                launch_pdl(scale_rows_kernel, dim3(grid_for(rows * (C / 4), 256)), dim3(256), (size_t)0, s, 1, in, sc, cnt, rows, Pn, C, o, ol);
+                WD_CHECK_CUDA(cudaGetLastError());
+                count_launch();
+                return 0;
+            };
+            break;
+        }
+        case WD_OP_RETR_REDUCE: {
+            const int B = I[0], Pn = I[1], K = I[2], ldz = I[3];
+            WD_REQUIRE(B > 0 && B <= 65535 && Pn > 0 && K > 0 && ldz >= K && P[0] && P[3], "retr_reduce: bad arguments");
+            const float *z = (const float*)P[0], *bias = (const float*)P[1];
+            const int* cnt = (const int*)P[2];
+            float* o = (float*)P[3];
+            f->fn = [=](cudaStream_t s) {
+                launch_pdl(retr_reduce_kernel, dim3((K + 127) / 128, B), dim3(128, kRetrJ), (size_t)0, s, 1, z, ldz, bias, cnt, Pn, K, o);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
                 return 0;

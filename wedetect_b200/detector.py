@@ -209,17 +209,23 @@ def letterbox_params(w, h, new_shape):
 
 
 class SimpleYOLOWorldDetector:
-    """WeDetect-Uni proposal generator facade (generate_proposal.py:1052-1218)."""
+    """WeDetect-Uni proposal generator facade (generate_proposal.py:1052-1218).
 
-    def __init__(self, backbone_size, prompt_dim=768, num_prompts=512, num_proposals=300, *, device="cuda:0", precise=False):
+    extract=True is the variant of eval_retrieval/extract_embedding.py:1088-1260: every result dict also carries
+    `labels`, `scales` and `bias` (the logit_scale / bias of each kept proposal's pyramid level), and `score_text`
+    computes the image x class retrieval scores of the last batch on the device (retrieval_metric.py:365-373)."""
+
+    def __init__(self, backbone_size, prompt_dim=768, num_prompts=512, num_proposals=300, *, device="cuda:0", precise=False, extract=False):
         L.load(require_gpu=True)
         if backbone_size not in ("base", "large", "tiny"):
             raise ValueError(backbone_size)
         assert prompt_dim == schema.EMBED_DIM
         self.size, self.num_prompts, self.num_proposals = backbone_size, num_prompts, num_proposals
         self.img_size = (1280, 1280) if backbone_size == "large" else (640, 640)
-        self.device, self.precise = torch.device(device), precise
+        self.device, self.precise, self.extract = torch.device(device), precise, bool(extract)
         self._sd, self._vw, self._plans = None, None, {}
+        self._scorers, self._cur = {}, None
+        self.last_batch_result = None
 
     def eval(self):
         return self
@@ -236,7 +242,7 @@ class SimpleYOLOWorldDetector:
         if missing:
             raise RuntimeError(f"checkpoint lacks {len(missing)} tensors needed for inference, e.g. {missing[:3]}")
         self._sd = {k: v.detach().float().cpu() for k, v in sd.items()}
-        self._vw, self._plans = None, {}
+        self._vw, self._plans, self._scorers, self._cur = None, {}, {}, None
         return "<All keys matched successfully>"
 
     def _plan(self, B, H, W):
@@ -245,7 +251,7 @@ class SimpleYOLOWorldDetector:
             if self._vw is None:
                 self._vw = weights.prepare_vision(self._sd, self.size, self.device, input_format="f32_rgb", precise=self.precise)
             self._plans[key] = plan.VisionPlan(self._vw, self.size, B, H, W, K=self.num_prompts, uni=True, score_thr=0.0, nms_pre=30000,
-                                               iou_thr=0.7, max_per_img=self.num_proposals, nms_mode=1, device=self.device)
+                                               iou_thr=0.7, max_per_img=self.num_proposals, nms_mode=1, extract=self.extract, device=self.device)
         return self._plans[key]
 
     def forward_tensor(self, inputs, ratios=None, offsets=None, ori_shapes=None, rescale=True):
@@ -267,9 +273,31 @@ class SimpleYOLOWorldDetector:
         p.image.copy_(inputs, non_blocking=True)
         p.run()
         r = p.results()
+        self.last_batch_result, self._cur = r, (B, H, W)
         counts = r["counts"].cpu().tolist()
-        return [dict(bboxes=r["boxes"][b, :counts[b]], embeddings=r["embeddings"][b, :counts[b]], scores=r["scores"][b, :counts[b]])
-                for b in range(B)]
+        out = [dict(bboxes=r["boxes"][b, :counts[b]], embeddings=r["embeddings"][b, :counts[b]], scores=r["scores"][b, :counts[b]])
+               for b in range(B)]
+        if self.extract:
+            labels64 = r["labels"].long()
+            for b, d in enumerate(out):
+                d.update(labels=labels64[b, :counts[b]], scales=r["scales"][b, :counts[b]], bias=r["bias"][b, :counts[b]])
+        return out
+
+    def score_text(self, text_embedding):
+        """Retrieval scores [B, K] of the LAST batch against `text_embedding` [K, 768] (L2-normalised by the caller, as
+        extract_embedding.py:1713 does): max over the image's proposals of sigmoid(emb . text * exp(scale) + bias)
+        (retrieval_metric.py:365-373), computed on the device from the live result buffers."""
+        from .retrieval import RetrievalScorer
+        if not self.extract or self._cur is None:
+            raise RuntimeError("score_text needs extract=True and a previous forward")
+        key = (self._cur, id(text_embedding))
+        if key not in self._scorers:
+            p = self._plans[self._cur]
+            r = p.results()
+            sc = RetrievalScorer(text_embedding, p.B, p.max_per_img, device=self.device, precise=self.precise, emb=r["embeddings"],
+                                 scale=r["scales"], bias=r["bias"], counts=r["counts"])
+            self._scorers = {key: (sc, text_embedding)}      # one live text set at a time (keeps the id() key valid)
+        return self._scorers[key][0].run()
 
     def forward(self, image_paths, rescale=True):
         from PIL import Image

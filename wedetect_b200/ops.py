@@ -379,7 +379,9 @@ def fold_text(text, bn_g, bn_h, logit_scale, bias, Wout, bout, normalize):
     return op
 
 
-def gather_embed(embeds, keep_anchor, counts, bn_g, bn_h, out):
+def gather_embed(embeds, keep_anchor, counts, bn_g, bn_h, out, *, lvl_scale=None, lvl_bias=None, out_scale=None, out_bias=None):
+    """out[b, j] = BN(embed row of kept proposal j); optionally the proposal's per-level logit_scale / bias
+    (the `scales` / `bias` results of eval_retrieval/extract_embedding.py:1181-1190,1253-1260)."""
     B, max_keep, C = out.shape
     op = WdOp()
     op.kind = L.OP_GATHER_EMBED
@@ -390,6 +392,47 @@ def gather_embed(embeds, keep_anchor, counts, bn_g, bn_h, out):
         op.i[30 + l] = e_ps
         op.p[l] = _ptr(e)
     for k, t in ((3, keep_anchor), (4, counts), (5, bn_g), (6, bn_h), (7, out)):
+        op.p[k] = _ptr(t)
+    if out_scale is not None:
+        assert lvl_scale.dtype == lvl_bias.dtype == torch.float32 and lvl_scale.numel() == lvl_bias.numel() == len(embeds)
+        assert out_scale.shape == out_bias.shape == (B, max_keep) and out_scale.is_contiguous() and out_bias.is_contiguous()
+        for k, t in ((8, lvl_scale), (9, lvl_bias), (10, out_scale), (11, out_bias)):
+            op.p[k] = _ptr(t)
+    return op
+
+
+def scale_rows(x, out, *, scale=None, counts=None):
+    """out[b*P + j, :] = bf16(x[b, j, :] * exp(scale[b, j])) for j < counts[b], else 0 (retrieval_metric.py:372)."""
+    out, o_ps = _tp(out)
+    _chk(x, torch.float32, "x")
+    B, Pn, C = x.shape
+    assert x.is_contiguous() and out.shape == (B * Pn, C) and out.is_contiguous()
+    op = WdOp()
+    op.kind = L.OP_SCALE_ROWS
+    op.i[0], op.i[1], op.i[2] = B, Pn, C
+    op.i[30] = o_ps
+    if scale is not None:
+        assert scale.dtype == torch.float32 and scale.numel() == B * Pn and scale.is_contiguous()
+    if counts is not None:
+        assert counts.dtype == torch.int32 and counts.numel() == B
+    for k, t in enumerate((x, scale, counts, out)):
+        op.p[k] = _ptr(t)
+    return op
+
+
+def retr_reduce(z, out, *, P, bias=None, counts=None):
+    """out[b, k] = max_{j < counts[b]} sigmoid(z[b*P + j, k] + bias[b, j]) (retrieval_metric.py:372-373)."""
+    _chk(z, torch.float32, "z")
+    B, K = out.shape
+    assert z.shape[0] == B * P and z.shape[1] >= K and out.dtype == torch.float32 and out.is_contiguous()
+    op = WdOp()
+    op.kind = L.OP_RETR_REDUCE
+    op.i[0], op.i[1], op.i[2], op.i[3] = B, P, K, z.stride(0)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == B * P and bias.is_contiguous()
+    if counts is not None:
+        assert counts.dtype == torch.int32 and counts.numel() == B
+    for k, t in enumerate((z, bias, counts, out)):
         op.p[k] = _ptr(t)
     return op
 

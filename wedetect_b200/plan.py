@@ -54,11 +54,13 @@ class Act:
 
 class VisionPlan:
     def __init__(self, weights, size, B, H, W, *, K, uni=False, input_dtype=torch.float32, score_thr=0.001,
-                 nms_pre=30000, iou_thr=0.7, max_per_img=300, nms_mode=0, tv_numel_thr=20000, device="cuda:0"):
+                 nms_pre=30000, iou_thr=0.7, max_per_img=300, nms_mode=0, tv_numel_thr=20000, extract=False, device="cuda:0"):
         assert H % 32 == 0 and W % 32 == 0
         self.Wt, self.size, self.B, self.H, self.W, self.K, self.uni = weights, size, B, H, W, K, uni
         self.dev = torch.device(device)
         self.precise = weights.precise
+        self.extract = bool(extract)
+        assert uni or not extract, "extract (labels / scales / bias per proposal) is a Uni-path output"
         self.cfg = schema.SIZES[size]
         self.ops = []
         self.keep = []
@@ -261,8 +263,15 @@ class VisionPlan:
         self.max_per_img = max_per_img
         if self.uni:
             self.kept_embed = torch.zeros(B, max_per_img, schema.EMBED_DIM, dtype=F32, device=self.dev)
+            kw = {}
+            if self.extract:   # eval_retrieval/extract_embedding.py:1181-1190: per-proposal logit_scale / bias of its level
+                self.kept_scale = torch.zeros(B, max_per_img, dtype=F32, device=self.dev)
+                self.kept_bias = torch.zeros(B, max_per_img, dtype=F32, device=self.dev)
+                self.lvl_scale = torch.cat([self.Wt[f"head.contrast.{l}.logit_scale"] for l in range(3)]).contiguous()
+                self.lvl_bias = torch.cat([self.Wt[f"head.contrast.{l}.bias"] for l in range(3)]).contiguous()
+                kw = dict(lvl_scale=self.lvl_scale, lvl_bias=self.lvl_bias, out_scale=self.kept_scale, out_bias=self.kept_bias)
             self.ops.append(ops.gather_embed([e.p3 for e in self.embeds], self.post.anchors, self.post.counts, self.Wt["head.contrast.g_all"],
-                                             self.Wt["head.contrast.h_all"], self.kept_embed))
+                                             self.Wt["head.contrast.h_all"], self.kept_embed, **kw))
 
     # ------------------------------------------------------------------ run-time API
     def set_text(self, text_feats, normalize=True):
@@ -308,6 +317,8 @@ class VisionPlan:
         out = dict(boxes=p.boxes, scores=p.scores, labels=p.labels, anchors=p.anchors, counts=p.counts)
         if self.uni:
             out["embeddings"] = self.kept_embed
+        if self.extract:
+            out["scales"], out["bias"] = self.kept_scale, self.kept_bias
         return out
 
 
