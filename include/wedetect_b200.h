@@ -139,6 +139,21 @@ enum wd_op_kind {
      * i: 0 B 1 P 2 K 3 ldz
      * p: 0 z f32 [B*P, ldz]  1 bias f32 [B*P] (nullable: 0)  2 counts i32 [B] (nullable: P)  3 out f32 [B, K] */
     WD_OP_RETR_REDUCE = 15,
+    /* Letterbox a batch of decoded RGB images into the detector's planar uint8 input: PIL-exact BILINEAR resize
+     * (Pillow Resample.c: 22-bit fixed-point triangle filter, horizontal pass into an 8-bit intermediate, then vertical)
+     * + centred paste on a `pad`-grey canvas.  generate_proposal.py:17-82 (letterbox), :1087-1101 (forward).
+     * i: 0 B 1 H 2 W (canvas) 3 pad value (114)
+     * p: 0 src u8: the images back to back, each [h, w, 3] RGB interleaved
+     *    1 desc i32 [B, 16] per image: 0,1 byte offset of the image in src (lo, hi)  2 src_w  3 src_h  4 new_w  5 new_h
+     *      6 left  7 top (paste position)  8 first source row the vertical pass needs  9 rows of the intermediate image
+     *      10,11 byte offset of the intermediate image in tmp (lo, hi)  12 offset (int32 words) of the image's tables in coef
+     *      13 ksize_h  14 ksize_v  15 vertical_first (Pillow >= 12 for h > 100 w when the height shrinks: the intermediate
+     *      image is then [new_h, src_w] and desc[8] is 0).   new_w == 0: the whole canvas is padding (unused batch slot)
+     *    2 coef i32: per image  bounds_h [new_w, 2] (first, count), kk_h [new_w, ksize_h], bounds_v [new_h, 2] (first row is
+     *      relative to desc[8]), kk_v [new_h, ksize_v]; weights are PIL's (int)(0.5 + w * 2^22)
+     *    3 tmp u8 workspace (sum over images of rows * new_w * 3 bytes)  4 out u8 [B, 3, H, W]
+     * desc / coef / src are re-filled by the host before every run (the pointers are fixed, so the op can sit in a graph). */
+    WD_OP_LETTERBOX = 16,
 };
 
 enum wd_act { WD_ACT_NONE = 0, WD_ACT_RELU = 1, WD_ACT_SILU = 2, WD_ACT_GELU = 3 };

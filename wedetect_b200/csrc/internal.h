@@ -64,5 +64,6 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
 int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out);
 int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out);  // LN / dwconv / stem / im2col / cast / text
 int compile_postprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out);
+int compile_preprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out);   // letterbox (PIL-exact resize + paste)
 
 }  // namespace wd

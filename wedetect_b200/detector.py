@@ -16,6 +16,7 @@ import torch
 
 from . import _lib as L
 from . import plan, schema, weights
+from .preprocess import Letterbox, letterbox_params  # noqa: F401
 from .structures import DetDataSample, InstanceData
 
 _DEF_TEST_CFG = dict(multi_label=True, nms_pre=30000, score_thr=0.001, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300)
@@ -199,15 +200,6 @@ class YOLOWorldDetector:
     __call__ = test_step
 
 
-def letterbox_params(w, h, new_shape):
-    """Scale / offsets of generate_proposal.py:17-82 (scale_up=True) without touching pixels."""
-    nw, nh = new_shape[1], new_shape[0]
-    r = min(nw / w, nh / h)
-    unpad = (int(round(w * r)), int(round(h * r)))
-    dw, dh = nw - unpad[0], nh - unpad[1]
-    return r, unpad, (dw // 2, dh // 2), (dw / 2, dh / 2)
-
-
 class SimpleYOLOWorldDetector:
     """WeDetect-Uni proposal generator facade (generate_proposal.py:1052-1218).
 
@@ -223,8 +215,8 @@ class SimpleYOLOWorldDetector:
         self.size, self.num_prompts, self.num_proposals = backbone_size, num_prompts, num_proposals
         self.img_size = (1280, 1280) if backbone_size == "large" else (640, 640)
         self.device, self.precise, self.extract = torch.device(device), precise, bool(extract)
-        self._sd, self._vw, self._plans = None, None, {}
-        self._scorers, self._cur = {}, None
+        self._sd, self._vw, self._plans = None, {}, {}
+        self._scorers, self._cur, self._letterbox = {}, None, {}
         self.last_batch_result = None
 
     def eval(self):
@@ -242,22 +234,21 @@ class SimpleYOLOWorldDetector:
         if missing:
             raise RuntimeError(f"checkpoint lacks {len(missing)} tensors needed for inference, e.g. {missing[:3]}")
         self._sd = {k: v.detach().float().cpu() for k, v in sd.items()}
-        self._vw, self._plans, self._scorers, self._cur = None, {}, {}, None
+        self._vw, self._plans, self._scorers, self._cur, self._letterbox = {}, {}, {}, None, {}
         return "<All keys matched successfully>"
 
-    def _plan(self, B, H, W):
-        key = (B, H, W)
+    def _plan(self, B, H, W, dtype=torch.float32):
+        key = (B, H, W, dtype)
         if key not in self._plans:
-            if self._vw is None:
-                self._vw = weights.prepare_vision(self._sd, self.size, self.device, input_format="f32_rgb", precise=self.precise)
-            self._plans[key] = plan.VisionPlan(self._vw, self.size, B, H, W, K=self.num_prompts, uni=True, score_thr=0.0, nms_pre=30000,
-                                               iou_thr=0.7, max_per_img=self.num_proposals, nms_mode=1, extract=self.extract, device=self.device)
+            fmt = "u8_rgb" if dtype == torch.uint8 else "f32_rgb"
+            if fmt not in self._vw:
+                self._vw[fmt] = weights.prepare_vision(self._sd, self.size, self.device, input_format=fmt, precise=self.precise)
+            self._plans[key] = plan.VisionPlan(self._vw[fmt], self.size, B, H, W, K=self.num_prompts, uni=True, input_dtype=dtype, score_thr=0.0,
+                                               nms_pre=30000, iou_thr=0.7, max_per_img=self.num_proposals, nms_mode=1, extract=self.extract,
+                                               device=self.device)
         return self._plans[key]
 
-    def forward_tensor(self, inputs, ratios=None, offsets=None, ori_shapes=None, rescale=True):
-        """inputs: fp32 [B,3,H,W] RGB in [0,1] (already letterboxed).  Returns the reference's list of dicts."""
-        B, _, H, W = inputs.shape
-        p = self._plan(B, H, W)
+    def _run(self, p, key, B, H, W, ratios, offsets, ori_shapes, rescale):
         meta = torch.zeros(B, 8)
         meta[:, 2:4] = 1.0
         meta[:, 6] = 1.0
@@ -270,10 +261,9 @@ class SimpleYOLOWorldDetector:
             if ori_shapes is not None:
                 clamp[b, 0], clamp[b, 1] = float(ori_shapes[b][1]), float(ori_shapes[b][0])
         p.set_meta(meta.to(self.device), clamp.to(self.device))
-        p.image.copy_(inputs, non_blocking=True)
         p.run()
         r = p.results()
-        self.last_batch_result, self._cur = r, (B, H, W)
+        self.last_batch_result, self._cur = r, key
         counts = r["counts"].cpu().tolist()
         out = [dict(bboxes=r["boxes"][b, :counts[b]], embeddings=r["embeddings"][b, :counts[b]], scores=r["scores"][b, :counts[b]])
                for b in range(B)]
@@ -282,6 +272,35 @@ class SimpleYOLOWorldDetector:
             for b, d in enumerate(out):
                 d.update(labels=labels64[b, :counts[b]], scales=r["scales"][b, :counts[b]], bias=r["bias"][b, :counts[b]])
         return out
+
+    def forward_tensor(self, inputs, ratios=None, offsets=None, ori_shapes=None, rescale=True):
+        """inputs: fp32 [B,3,H,W] RGB in [0,1] (already letterboxed).  Returns the reference's list of dicts."""
+        B, _, H, W = inputs.shape
+        key = (B, H, W, torch.float32)
+        p = self._plan(*key)
+        p.image.copy_(inputs, non_blocking=True)
+        return self._run(p, key, B, H, W, ratios, offsets, ori_shapes, rescale)
+
+    def forward(self, image_paths, rescale=True):
+        """image_paths: list of file names, PIL images or uint8 [h,w,3] RGB arrays (generate_proposal.py:1082-1117).
+        Decoding stays with PIL; the letterbox (BILINEAR resize + 114 padding) runs on the device, bit-exact with PIL."""
+        from PIL import Image
+        arrays = []
+        for ip in image_paths:
+            if isinstance(ip, str):
+                ip = Image.open(ip).convert("RGB")
+            if isinstance(ip, Image.Image):
+                ip = np.asarray(ip if ip.mode == "RGB" else ip.convert("RGB"))
+            arrays.append(ip)
+        B, (H, W) = len(arrays), self.img_size
+        key = (B, H, W, torch.uint8)
+        p = self._plan(*key)
+        if key not in self._letterbox:
+            self._letterbox[key] = Letterbox(p.image)
+        ratios, offsets, ori_shapes = self._letterbox[key].run(arrays)
+        return self._run(p, key, B, H, W, ratios, offsets, ori_shapes, rescale)
+
+    __call__ = forward
 
     def score_text(self, text_embedding):
         """Retrieval scores [B, K] of the LAST batch against `text_embedding` [K, 768] (L2-normalised by the caller, as
@@ -298,20 +317,3 @@ class SimpleYOLOWorldDetector:
                                  scale=r["scales"], bias=r["bias"], counts=r["counts"])
             self._scorers = {key: (sc, text_embedding)}      # one live text set at a time (keeps the id() key valid)
         return self._scorers[key][0].run()
-
-    def forward(self, image_paths, rescale=True):
-        from PIL import Image
-        inputs, ratios, offsets, ori_shapes = [], [], [], []
-        for ip in image_paths:
-            img = Image.open(ip).convert("RGB") if isinstance(ip, str) else ip
-            w, h = img.size
-            ori_shapes.append((h, w))
-            r, unpad, (left, top), off = letterbox_params(w, h, self.img_size)
-            canvas = Image.new("RGB", (self.img_size[1], self.img_size[0]), (114, 114, 114))
-            canvas.paste(img.resize(unpad, Image.Resampling.BILINEAR), (left, top))
-            inputs.append(torch.from_numpy(np.array(canvas)).permute(2, 0, 1).float() / 255.0)
-            ratios.append(r)
-            offsets.append(off)
-        return self.forward_tensor(torch.stack(inputs), ratios, offsets, ori_shapes, rescale)
-
-    __call__ = forward

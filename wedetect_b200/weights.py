@@ -73,6 +73,8 @@ def prepare_vision(sd, size, device, *, input_format="f32_rgb", precise=False):
     w = sd[bb + "downsample_layers.0.0.weight"].double()          # [C0, 3, 4, 4]
     if input_format == "u8_bgr":
         w = w.flip(1) / 255.0                                       # kernel sees raw uint8 BGR
+    elif input_format == "u8_rgb":
+        w = w / 255.0                                               # Uni path: letterboxed uint8 RGB (generate_proposal.py:1098-1099)
     elif input_format != "f32_rgb":
         raise ValueError(input_format)
     ws = torch.zeros(dims[0], 64, dtype=torch.float64)
