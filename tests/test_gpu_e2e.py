@@ -24,7 +24,7 @@ def _err(got, ref):
     return dict(max_abs=float(d.max()), rel_rms=float(d.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-12)), ref_absmax=float(ref.abs().max()))
 
 
-def run_case(size, B, H, W, K, *, uni, precise, regime, seed=0):
+def run_case(size, B, H, W, K, *, uni, precise, regime, seed=0, max_per_img=300):
     from oracle import functional as Fn, synth
     from oracle.postprocess import postprocess_ref, identity_meta
     from wedetect_b200 import plan, schema, weights
@@ -35,7 +35,7 @@ def run_case(size, B, H, W, K, *, uni, precise, regime, seed=0):
     with torch.no_grad():
         ref = Fn.vision_forward(sd, size, imgs, text=text, prompts=sd.get("embeddings"))
     Wt = weights.prepare_vision(sd, size, D, precise=precise)
-    kw = dict(score_thr=0.0, nms_mode=1, max_per_img=300) if uni else dict(score_thr=0.001, nms_mode=0, max_per_img=300)
+    kw = dict(score_thr=0.0, nms_mode=1, max_per_img=max_per_img) if uni else dict(score_thr=0.001, nms_mode=0, max_per_img=max_per_img)
     p = plan.VisionPlan(Wt, size, B, H, W, K=K, uni=uni, **kw)
     if not uni:
         p.set_text(text.to(D))
@@ -56,7 +56,7 @@ def run_case(size, B, H, W, K, *, uni, precise, regime, seed=0):
     meta, clamp = identity_meta(B, H, W)
     lhw = schema.level_hw(H, W)
     det_ref = postprocess_ref([lv["logits"].reshape(-1, K) for lv in ref["levels"]], [lv["dist"].reshape(-1, 4) for lv in ref["levels"]], lhw,
-                              list(schema.STRIDES), K=K, B=B, score_thr=kw["score_thr"], nms_pre=30000, iou_thr=0.7, max_per_img=300,
+                              list(schema.STRIDES), K=K, B=B, score_thr=kw["score_thr"], nms_pre=30000, iou_thr=0.7, max_per_img=max_per_img,
                               nms_mode=kw["nms_mode"], img_meta=meta, clamp_wh=clamp)
     det = {k: v.cpu() for k, v in p.results().items()}
     same = []
@@ -68,7 +68,7 @@ def run_case(size, B, H, W, K, *, uni, precise, regime, seed=0):
     errs["det_overlap"] = same
     errs["det_counts"] = [det["counts"].tolist(), det_ref["counts"].tolist()]
     os.makedirs(OUT, exist_ok=True)
-    tag = f"{size}_{'uni' if uni else 'text'}_{'precise' if precise else 'fast'}_{regime}_{H}x{W}_B{B}_K{K}"
+    tag = f"{size}_{'uni' if uni else 'text'}_{'precise' if precise else 'fast'}_{regime}_{H}x{W}_B{B}_K{K}" + (f"_P{max_per_img}" if max_per_img != 300 else "")
     with open(os.path.join(OUT, f"e2e_{tag}.json"), "w") as f:
         json.dump(errs, f, indent=1)
     print(tag, json.dumps({k: (round(v["max_abs"], 5), round(v["rel_rms"], 6)) if isinstance(v, dict) else v for k, v in errs.items()}))
@@ -89,17 +89,21 @@ def test_e2e_fast(size, K):
     assert min(errs["det_overlap"]) > 0.6, errs["det_overlap"]
 
 
-@pytest.mark.parametrize("size,K,uni", [("tiny", 5, False), ("base", 80, False), ("base", 256, True)])
-def test_e2e_precise_north_star(size, K, uni):
+# (size, K, uni, B, res, max_per_img): C1 / C2 / C4-default shapes, then the BASELINE config-3 shape (WeDetect-Large against the
+# 1203-class LVIS-sized text set: similarity as a dense GEMM with a ragged last tile, > nms_pre candidates per image so the
+# top-k cut is exercised) and the config-4 shape (Uni, 1000 proposals kept per image)
+@pytest.mark.parametrize("size,K,uni,B,res,max_per_img", [("tiny", 5, False, 2, 320, 300), ("base", 80, False, 2, 320, 300), ("base", 256, True, 2, 320, 300),
+                                                          ("large", 1203, False, 1, 256, 300), ("base", 256, True, 2, 320, 1000)])
+def test_e2e_precise_north_star(size, K, uni, B, res, max_per_img):
     """bf16x3 path: logits within 1e-3 of the fp32 reference and identical kept indices / labels."""
-    errs, det, det_ref, p, ref = run_case(size, 2, 320, 320, K, uni=uni, precise=True, regime="sparse")
+    errs, det, det_ref, p, ref = run_case(size, B, res, res, K, uni=uni, precise=True, regime="sparse", max_per_img=max_per_img)
     for l in range(3):
         assert errs[f"logit{l}"]["max_abs"] <= 1e-3, errs[f"logit{l}"]
         assert errs[f"dist{l}"]["max_abs"] <= 1e-3, errs[f"dist{l}"]
     # exact on box indices / class assignment: the kept (anchor, class) SET is identical per image; the order may differ
     # only between detections whose scores are closer than the float tolerance (score-sorted, so compare after keying)
     assert torch.equal(det["counts"], det_ref["counts"])
-    for b in range(2):
+    for b in range(B):
         n = int(det_ref["counts"][b])
         ka = (det["anchors"][b, :n].long() * 4096 + det["labels"][b, :n].long())
         kr = (det_ref["anchors"][b, :n].long() * 4096 + det_ref["labels"][b, :n].long())
@@ -119,7 +123,7 @@ def test_e2e_precise_north_star(size, K, uni):
                                  f"ours {float(det['scores'][b, i]):.6f} ref {float(det_ref['scores'][b, j]):.6f}; swapped positions {swapped.tolist()[:20]}")
     if uni:
         lv = torch.cat([l_["embed"] for l_ in ref["levels"]], 1)
-        for b in range(2):
+        for b in range(B):
             n = int(det_ref["counts"][b])
             want = lv[b, det["anchors"][b, :n].long()]
             assert float((det["embeddings"][b, :n] - want).abs().max()) <= 1e-2
