@@ -49,23 +49,63 @@ def parse():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML in-process every 5 ms (a 10-step region lasts
+    ~0.2 s, too short for more than one `nvidia-smi` fork), `nvidia-smi` polling as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self._nvml, self._h, self.source = None, None, "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid is not None:
+                for cand in (f"GPU-{uuid}", str(uuid)):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if hasattr(cand, "encode") else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml, self._h, self.source = pynvml, h, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._h
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = [getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = 0.0
+        return [str(sm), str(mx), f"{pw:.1f}"] + ["Active" if (r & b) else "Not Active" for b in bits]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.005 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -79,9 +119,10 @@ class ClockSampler:
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(self.rows))
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_min_mhz=sm[0] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows), power_w_max=max(pw) if pw else None, source=self.source)
 
 
 def host_threads():
@@ -219,7 +260,11 @@ def run_ours(args):
     barrier()
     l0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    try:
+        gpu_uuid = torch.cuda.get_device_properties(dev).uuid
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local, gpu_uuid) as clk:
         barrier()
         e0.record()
         for _ in range(args.steps):

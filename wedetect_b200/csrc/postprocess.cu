@@ -13,7 +13,12 @@
 // Pipeline (all sizes live on the device):
 //   1 pp_candidates   : one pass over the logits, warp-aggregated append of 64-bit keys
 //                       key = image | (0x3FFFFFFF - score_bits) | flat_index
-//   2 radix sort #1   : stable LSD radix sort (8-bit digits, warp match_any multisplit) of the keys
+//   1b top-k select   : images with more than nms_pre candidates (score_thr 0 of the Uni path, dense score maps, 1203
+//                       classes) keep only the keys whose 16 leading score bits reach the nms_pre-th best: two 8-bit
+//                       radix-select histograms over the keys + one compaction.  Everything dropped scores strictly below
+//                       everything kept and at least nms_pre keys are kept, so the sorted top nms_pre is unchanged - but the
+//                       sort now sees ~nms_pre keys per image instead of anchors x classes (2.15 M per image for Uni).
+//   2 radix sort #1   : stable LSD radix sort (8-bit digits, warp match_any multisplit) of the kept keys
 //   3 pp_segments     : per-image segment starts, n_sel = min(count, nms_pre)
 //   4 pp_decode       : box decode / rescale of the selected candidates, max coordinate (mmcv offsets),
 //                       second key = image | class | rank
@@ -37,7 +42,7 @@ struct PPCtrl {  // lives in device memory
     unsigned int total;      // candidates appended
     unsigned int total2;     // selected candidates (sum of n_sel)
     unsigned int overflow;
-    unsigned int pad;
+    unsigned int totalc;     // candidates left after the top-k select
 };
 
 struct PPDev {
@@ -53,6 +58,9 @@ struct PPDev {
     unsigned int* totals;   // [32][256] per-pass digit totals (zeroed by pp_reset)
     PPCtrl* ctrl;
     unsigned int *counts, *seg, *nsel, *seg2;
+    unsigned int* shist;    // [2][B][256] radix-select histograms (leading / second score digit)
+    unsigned int* sel;      // [B][4]: keep_all, leading digit of the cut, candidates still needed inside it, 16-bit cut prefix
+    unsigned int* counts2;  // [B] candidates per image after the select
     unsigned int* maxc;     // per image max coordinate (order-preserving uint encoding of float)
     float4* cand_box;
     float* cand_score;
@@ -80,12 +88,15 @@ __global__ void pp_reset_kernel(PPDev d) {
         d.ctrl->total = 0;
         d.ctrl->total2 = 0;
         d.ctrl->overflow = 0;
+        d.ctrl->totalc = 0;
     }
     if (t < d.p.B) {
         d.counts[t] = 0;
+        d.counts2[t] = 0;
         d.maxc[t] = 0;  // smaller than the encoding of any float
     }
     if (t < 32 * 256) d.totals[t] = 0;
+    for (int i = t; i < 2 * d.p.B * 256; i += gridDim.x * blockDim.x) d.shist[i] = 0;
 }
 
 // One warp per contiguous range of anchor rows (image, anchor-in-level): lanes stride over the classes (coalesced, no
@@ -274,6 +285,161 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
     }
 }
 
+// ---------------- top-k select: drop keys that cannot be among an image's nms_pre best ----------------
+// inv = 0x3FFFFFFF - score_bits (30 bits, smaller = better).  Pass 0 histograms inv >> 22 per image, the scan finds the digit
+// that holds the nms_pre-th best key; pass 1 histograms (inv >> 14) & 255 inside that digit; the compaction keeps
+// inv >> 14 <= cut.  Images with at most nms_pre candidates keep everything.  Histograms are block-private in shared memory
+// for a window of 32 images (warp-aggregated with match_any), flushed with one global atomic per non-empty bin.
+constexpr int SEL_WIN = 32;
+__global__ void __launch_bounds__(256) pp_sel_hist_kernel(PPDev d, int pass) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ unsigned int h[SEL_WIN * 256];
+    const unsigned int n = d.ctrl->total < d.cap ? d.ctrl->total : (unsigned int)d.cap;
+    const int lane = threadIdx.x & 31;
+    unsigned int* gh = d.shist + (size_t)pass * d.p.B * 256;
+    const unsigned int tile_keys = 256 * 16;
+    const unsigned int num_tiles = (n + tile_keys - 1) / tile_keys;
+    for (unsigned int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int i = threadIdx.x; i < SEL_WIN * 256; i += 256) h[i] = 0;
+        __syncthreads();
+        const unsigned int base = tile * tile_keys;
+        const int win0 = d.p.B <= SEL_WIN ? 0 : (int)(d.keys0[base] >> (d.idx_bits + 30));
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+            const unsigned int i = base + it * 256 + threadIdx.x;
+            unsigned int id = 0xFFFFFFFFu;
+            if (i < n) {
+                const unsigned long long key = d.keys0[i];
+                const int b = (int)(key >> (d.idx_bits + 30));
+                const unsigned int inv = (unsigned int)(key >> d.idx_bits) & 0x3FFFFFFFu;
+                const unsigned int* sl = d.sel + b * 4;
+                if (pass == 0) {
+                    if (d.counts[b] > (unsigned int)d.p.nms_pre) id = (unsigned int)b * 256u + (inv >> 22);
+                } else if (!sl[0] && (inv >> 22) == sl[1]) {
+                    id = (unsigned int)b * 256u + ((inv >> 14) & 255u);
+                }
+            }
+            const unsigned int peers = __match_any_sync(0xffffffffu, id);
+            if (id != 0xFFFFFFFFu && (peers & ((1u << lane) - 1)) == 0) {
+                const int bw = (int)(id >> 8) - win0;
+                if (bw >= 0 && bw < SEL_WIN) atomicAdd(&h[bw * 256 + (id & 255u)], (unsigned int)__popc(peers));
+                else atomicAdd(&gh[id], (unsigned int)__popc(peers));
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEL_WIN * 256; i += 256) {
+            const int b = win0 + (i >> 8);
+            if (h[i] && b < d.p.B) atomicAdd(&gh[(size_t)b * 256 + (i & 255)], h[i]);
+        }
+        __syncthreads();
+    }
+}
+
+// one warp per image: smallest digit whose cumulative count reaches the number still needed
+__global__ void __launch_bounds__(256) pp_sel_scan_kernel(PPDev d, int pass) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= d.p.B) return;
+    unsigned int* sl = d.sel + b * 4;
+    if (pass == 0) {
+        if (d.counts[b] <= (unsigned int)d.p.nms_pre) {
+            if (lane == 0) { sl[0] = 1; sl[1] = 0; sl[2] = 0; sl[3] = 0xFFFFu; }
+            return;
+        }
+    } else if (sl[0]) {
+        return;
+    }
+    const unsigned int need = pass == 0 ? (unsigned int)d.p.nms_pre : sl[2];
+    const unsigned int* hrow = d.shist + ((size_t)pass * d.p.B + b) * 256;
+    unsigned int v[8], part = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = hrow[lane * 8 + j];
+        part += v[j];
+    }
+    unsigned int incl = part;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    const unsigned int before = incl - part;            // keys in digits below this lane's 8 digits
+    const bool mine = before < need && incl >= need;    // exactly one lane (the total is >= need by construction)
+    if (mine) {
+        unsigned int run = before;
+        int dsel = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (run < need && run + v[j] >= need) { dsel = lane * 8 + j; break; }
+            run += v[j];
+        }
+        if (pass == 0) { sl[0] = 0; sl[1] = (unsigned int)dsel; sl[2] = need - run; sl[3] = 0; }
+        else sl[3] = (sl[1] << 8) | (unsigned int)dsel;
+    }
+}
+
+// keys0 -> keys1: keep inv >> 14 <= cut (per image); same per-warp buffered append as pp_candidates
+__global__ void __launch_bounds__(256) pp_sel_compact_kernel(PPDev d) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ unsigned long long wbuf[8][PP_WBUF];
+    const unsigned int n = d.ctrl->total < d.cap ? d.ctrl->total : (unsigned int)d.cap;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned int nwarps = gridDim.x * 8, gw = blockIdx.x * 8 + w;
+    const unsigned int per = ((n + nwarps - 1) / nwarps + 31) / 32 * 32;   // contiguous range per warp: long runs of one image
+    const unsigned int i0 = gw * per, i1 = i0 + per < n ? i0 + per : n;
+    unsigned int cnt = 0, img_cnt = 0;
+    int cur_b = -1;
+    auto flush = [&]() {
+        if (cnt) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&d.ctrl->totalc, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (unsigned int i = lane; i < cnt; i += 32) d.keys1[base + i] = wbuf[w][i];   // totalc <= total <= cap
+            cnt = 0;
+            __syncwarp();
+        }
+    };
+    for (unsigned int i = i0; i < i1; i += 32) {
+        const unsigned int k = i + lane;
+        bool pass = false;
+        unsigned long long key = 0;
+        int b = -1;
+        if (k < i1) {
+            key = d.keys0[k];
+            b = (int)(key >> (d.idx_bits + 30));
+            const unsigned int inv = (unsigned int)(key >> d.idx_bits) & 0x3FFFFFFFu;
+            pass = (inv >> 14) <= d.sel[b * 4 + 3];
+        }
+        // per-image counts: the common case is one image per 32 keys; otherwise count image by image
+        const int b0 = __shfl_sync(0xffffffffu, b, 0);
+        const bool uniform = __all_sync(0xffffffffu, b == b0 || b < 0);
+        const unsigned int m = __ballot_sync(0xffffffffu, pass);
+        if (uniform) {
+            if (b0 != cur_b) {
+                if (lane == 0 && img_cnt) atomicAdd(&d.counts2[cur_b], img_cnt);
+                img_cnt = 0;
+                cur_b = b0;
+            }
+            img_cnt += __popc(m);
+        } else {
+            // a chunk that straddles images: one atomic per image present (an atomic per key serialises on B addresses)
+            const unsigned int peers = __match_any_sync(0xffffffffu, pass ? b : -1);
+            if (pass && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&d.counts2[b], (unsigned int)__popc(peers));
+        }
+        if (m) {
+            if (pass) wbuf[w][cnt + __popc(m & ((1u << lane) - 1))] = key;
+            cnt += __popc(m);
+            __syncwarp();
+            if (cnt > PP_WBUF - 32) flush();
+        }
+    }
+    flush();
+    if (lane == 0 && img_cnt && cur_b >= 0) atomicAdd(&d.counts2[cur_b], img_cnt);
+}
+
 // ---------------- segments, decode ----------------
 __global__ void pp_segments_kernel(PPDev d) {
     pdl_launch_dependents();
@@ -283,7 +449,7 @@ __global__ void pp_segments_kernel(PPDev d) {
         for (int b = 0; b < d.p.B; ++b) {
             d.seg[b] = run;
             d.seg2[b] = run2;
-            const unsigned int c = d.counts[b];
+            const unsigned int c = d.counts2[b];   // after the top-k select: min(c, nms_pre) equals min(all candidates, nms_pre)
             const unsigned int ns = c < (unsigned int)d.p.nms_pre ? c : (unsigned int)d.p.nms_pre;
             d.nsel[b] = ns;
             run += c;
@@ -517,7 +683,7 @@ static unsigned long long align256(unsigned long long x) { return (x + 255) & ~2
 
 struct PPLayout {
     unsigned long long off_keys0, off_keys1, off_hist, off_ctrl, off_counts, off_seg, off_nsel, off_seg2, off_maxc, off_box, off_score, off_label,
-        off_anchor, off_keys2a, off_keys2b, off_keep, off_kept, total;
+        off_anchor, off_keys2a, off_keys2b, off_keep, off_kept, off_shist, off_sel, off_counts2, total;
 };
 static PPLayout pp_layout(int B, int A, int K, int nms_pre) {
     PPLayout L;
@@ -542,6 +708,9 @@ static PPLayout pp_layout(int B, int A, int K, int nms_pre) {
     L.off_keys2b = o; o = align256(o + sel * 8);
     L.off_keep = o; o = align256(o + sel);
     L.off_kept = o; o = align256(o + sel * 16);
+    L.off_shist = o; o = align256(o + 2ull * B * 256 * 4);
+    L.off_sel = o; o = align256(o + (B + 1) * 16ull);
+    L.off_counts2 = o; o = align256(o + (B + 1) * 4ull);
     L.total = o;
     return L;
 }
@@ -566,7 +735,7 @@ struct PostOp : CompiledOp {
     int launch(cudaStream_t s) override {
         // WD_PP_PROFILE=1: synchronous per-phase timing printed to stderr (debug / tuning aid, never in benchmarks)
         static const bool prof = getenv("WD_PP_PROFILE") != nullptr;
-        cudaEvent_t ev[8];
+        cudaEvent_t ev[10];
         int ne = 0;
         auto mark = [&]() {
             if (prof) {
@@ -586,9 +755,17 @@ struct PostOp : CompiledOp {
             count_launch();
         }
         mark();
-        if (sort(d.keys0, d.keys1, &d.ctrl->total, passes1, 0, s)) return -2;
+        // top-k select (keys0 -> keys1), then the sort ping-pongs starting from keys1
+        for (int pass = 0; pass < 2; ++pass) {
+            launch_pdl(pp_sel_hist_kernel, dim3(RS_GRID), dim3(256), (size_t)0, s, 1, d, pass);
+            launch_pdl(pp_sel_scan_kernel, dim3((d.p.B + 7) / 8), dim3(256), (size_t)0, s, 1, d, pass);
+        }
+        launch_pdl(pp_sel_compact_kernel, dim3(RS_GRID), dim3(256), (size_t)0, s, 1, d);
+        count_launch(5);
         mark();
-        const unsigned long long* sorted1 = (passes1 & 1) ? d.keys1 : d.keys0;
+        if (sort(d.keys1, d.keys0, &d.ctrl->totalc, passes1, 0, s)) return -2;
+        mark();
+        const unsigned long long* sorted1 = (passes1 & 1) ? d.keys0 : d.keys1;
         launch_pdl(pp_segments_kernel, dim3(1), dim3(32), (size_t)0, s, 1, d);
         launch_pdl(pp_decode_kernel, dim3(dim3(32, d.p.B)), dim3(256), (size_t)0, s, 1, d, sorted1);
         count_launch(2);
@@ -604,7 +781,7 @@ struct PostOp : CompiledOp {
         WD_CHECK_CUDA(cudaGetLastError());
         if (prof) {
             cudaStreamSynchronize(s);
-            static const char* names[] = {"candidates", "sort1", "segments+decode", "sort2", "nms", "finalize"};
+            static const char* names[] = {"candidates", "select", "sort1", "segments+decode", "sort2", "nms", "finalize"};
             float tot = 0.f;
             for (int i = 0; i + 1 < ne; ++i) {
                 float ms = 0.f;
@@ -614,7 +791,8 @@ struct PostOp : CompiledOp {
             }
             PPCtrl hc;
             cudaMemcpy(&hc, d.ctrl, sizeof(hc), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[pp] total %.3f ms (passes %d + %d), candidates %u, selected %u\n", tot, passes1, passes2, hc.total, hc.total2);
+            fprintf(stderr, "[pp] total %.3f ms (passes %d + %d), candidates %u, after top-k select %u, selected %u\n", tot, passes1, passes2, hc.total,
+                    hc.totalc, hc.total2);
             for (int i = 0; i < ne; ++i) cudaEventDestroy(ev[i]);
         }
         return 0;
@@ -680,9 +858,12 @@ int compile_postprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     o->d.keys2b = (unsigned long long*)(w + L.off_keys2b);
     o->d.keep = (unsigned char*)(w + L.off_keep);
     o->kept = (float4*)(w + L.off_kept);
+    o->d.shist = (unsigned int*)(w + L.off_shist);
+    o->d.sel = (unsigned int*)(w + L.off_sel);
+    o->d.counts2 = (unsigned int*)(w + L.off_counts2);
     o->passes1 = (o->d.idx_bits + 30 + o->d.b_bits + 7) / 8;
     o->passes2 = (16 + o->d.cls_bits + o->d.b_bits + 7) / 8;
-    o->kernels = 1 + p.nlevels + 3 * (o->passes1 + o->passes2) + 4;
+    o->kernels = 1 + p.nlevels + 5 + 3 * (o->passes1 + o->passes2) + 4;
     out = std::move(o);
     return 0;
 }

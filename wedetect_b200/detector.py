@@ -10,6 +10,7 @@ Same names, argument meaning and error behaviour; the arithmetic runs in libwede
 the CUDA library or an sm_100 device raises.
 """
 import itertools
+import os
 
 import numpy as np
 import torch
@@ -29,8 +30,9 @@ def _size_from_cfg(model_cfg):
 class YOLOWorldDetector:
     """Text-conditioned detector facade.  `model_cfg` is the `model=` dict of config/wedetect_*.py."""
 
-    def __init__(self, model_cfg=None, *, size=None, test_cfg=None, device="cuda:0", precise=False, tokenizer=None):
+    def __init__(self, model_cfg=None, *, size=None, test_cfg=None, device="cuda:0", precise=False, tokenizer=None, cuda_graph=True):
         L.load(require_gpu=True)
+        self.cuda_graph = bool(cuda_graph) and not os.environ.get("WD_NO_GRAPH")
         self.model_cfg = model_cfg
         self.size = size or _size_from_cfg(model_cfg)
         if self.size not in schema.SIZES:
@@ -180,7 +182,7 @@ class YOLOWorldDetector:
                        torch.tensor(clamp_rows, dtype=torch.float32).to(self.device, non_blocking=True))
             p._meta_key = key
         p.image.copy_(batch_inputs, non_blocking=True)
-        p.run()
+        _run_plan(p, self.cuda_graph)
         r = p.results()
         self.last_batch_result = r            # packed device tensors [B,max,...] + counts: bulk readers copy these once
         labels64 = r["labels"].long()         # one conversion for the batch (the reference's labels are int64)
@@ -200,6 +202,15 @@ class YOLOWorldDetector:
     __call__ = test_step
 
 
+def _run_plan(p, use_graph):
+    """First run of a plan is eager (lazy attribute setup inside the library); from the second on the whole forward is one
+    CUDA-graph launch (all buffers are static, per-batch inputs are copied into them before the launch)."""
+    if use_graph and not p._graph and getattr(p, "_ran_eager", False):
+        p.capture()
+    p.run()
+    p._ran_eager = True
+
+
 class SimpleYOLOWorldDetector:
     """WeDetect-Uni proposal generator facade (generate_proposal.py:1052-1218).
 
@@ -207,8 +218,10 @@ class SimpleYOLOWorldDetector:
     `labels`, `scales` and `bias` (the logit_scale / bias of each kept proposal's pyramid level), and `score_text`
     computes the image x class retrieval scores of the last batch on the device (retrieval_metric.py:365-373)."""
 
-    def __init__(self, backbone_size, prompt_dim=768, num_prompts=512, num_proposals=300, *, device="cuda:0", precise=False, extract=False):
+    def __init__(self, backbone_size, prompt_dim=768, num_prompts=512, num_proposals=300, *, device="cuda:0", precise=False, extract=False,
+                 cuda_graph=True):
         L.load(require_gpu=True)
+        self.cuda_graph = bool(cuda_graph) and not os.environ.get("WD_NO_GRAPH")
         if backbone_size not in ("base", "large", "tiny"):
             raise ValueError(backbone_size)
         assert prompt_dim == schema.EMBED_DIM
@@ -261,7 +274,7 @@ class SimpleYOLOWorldDetector:
             if ori_shapes is not None:
                 clamp[b, 0], clamp[b, 1] = float(ori_shapes[b][1]), float(ori_shapes[b][0])
         p.set_meta(meta.to(self.device), clamp.to(self.device))
-        p.run()
+        _run_plan(p, self.cuda_graph)
         r = p.results()
         self.last_batch_result, self._cur = r, key
         counts = r["counts"].cpu().tolist()

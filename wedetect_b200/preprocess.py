@@ -9,7 +9,10 @@ Host work per image is only what PIL's precompute_coeffs / normalize_coeffs_8bpc
 the window and 22-bit fixed-point weights of every output column and row, computed in double precision in the same
 operation order.  Pixels go pageable -> pinned -> HBM untouched.  There is no CPU resize path.
 """
+import functools
 import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -30,9 +33,11 @@ def letterbox_params(w, h, new_shape):
     return r, unpad, (dw // 2, dh // 2), (dw / 2, dh / 2)
 
 
+@functools.lru_cache(maxsize=256)
 def resample_tables(in_size, out_size):
     """(ksize, bounds int32 [out, 2] = (first, count), weights int32 [out, ksize]) of PIL's 8-bit BILINEAR resampler for
-    the full source range; in_size == out_size gives identity tables (the pass PIL skips)."""
+    the full source range; in_size == out_size gives identity tables (the pass PIL skips).  Cached per (in, out): datasets
+    repeat a handful of sizes; callers must not modify the returned arrays."""
     if in_size == out_size:
         b = np.stack([np.arange(out_size, dtype=np.int32), np.ones(out_size, dtype=np.int32)], 1)
         return 1, b, np.full((out_size, 1), 1 << PRECISION_BITS, dtype=np.int32)
@@ -56,9 +61,22 @@ def resample_tables(in_size, out_size):
     return ksize, np.stack([xmin, xmax], 1).astype(np.int32), kk
 
 
-def pack_batch(images, H, W):
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(8, n)))
+    return _POOL
+
+
+def pack_batch(images, H, W, with_src=True):
     """Host side of WD_OP_LETTERBOX for one batch: geometry + PIL tables per image, packed the way the kernels read them.
-    Returns dict(desc int32 [n,16], coef int32 [...], src uint8 [...], tmp_bytes, ratios, offsets, shapes)."""
+    Returns dict(desc int32 [n,16], coef int32 [...], src_parts [(byte offset, flat uint8 view)], src_bytes, tmp_bytes,
+    ratios, offsets, shapes) and, with_src, `src`: the concatenated source bytes (tests; the device path copies the parts
+    straight into pinned memory instead)."""
     desc = np.zeros((len(images), DESC_WORDS), dtype=np.int32)
     coef_parts, src_parts = [], []
     src_bytes = coef_words = tmp_bytes = 0
@@ -85,19 +103,22 @@ def pack_batch(images, H, W):
         tables = np.concatenate([bh.reshape(-1), kh.reshape(-1), bv.reshape(-1), kv.reshape(-1)])
         # byte offsets are (lo, hi) int32 pairs in the ABI; one batch of decoded images stays below 2 GiB (checked below)
         desc[b] = (src_bytes, 0, w, h, nw, nh, left, top, first, rows, tmp_bytes, 0, coef_words, ksh, ksv, vfirst)
-        pad = (-im.size) % 16
-        src_parts.append(im.reshape(-1))
-        if pad:
-            src_parts.append(np.zeros(pad, dtype=np.uint8))
+        src_parts.append((src_bytes, im.reshape(-1)))
         coef_parts.append(tables)
-        src_bytes += im.size + pad
+        src_bytes += (im.size + 15) // 16 * 16
         coef_words += tables.size
         tmp_bytes += (rows * tmp_cols * 3 + 15) // 16 * 16
         if src_bytes >= 2 ** 31 or tmp_bytes >= 2 ** 31:
             raise ValueError("batch of source images exceeds 2 GiB")
         ratios.append(r); offsets.append(off); shapes.append((h, w))
-    return dict(desc=desc, coef=np.concatenate(coef_parts), src=np.concatenate(src_parts), tmp_bytes=tmp_bytes, ratios=ratios, offsets=offsets,
-                shapes=shapes)
+    out = dict(desc=desc, coef=np.concatenate(coef_parts), src_parts=src_parts, src_bytes=src_bytes, tmp_bytes=tmp_bytes, ratios=ratios,
+               offsets=offsets, shapes=shapes)
+    if with_src:
+        src = np.zeros(src_bytes, dtype=np.uint8)
+        for off, flat in src_parts:
+            src[off: off + flat.size] = flat
+        out["src"] = src
+    return out
 
 
 class Letterbox:
@@ -133,8 +154,8 @@ class Letterbox:
             raise ValueError(f"{len(images)} images for a batch of {self.B}")
         if self._copied is not None:
             self._copied.synchronize()           # the previous batch's H2D must have left the pinned buffers
-        pk = pack_batch(images, self.H, self.W)
-        n_src, n_coef = pk["src"].size, pk["coef"].size
+        pk = pack_batch(images, self.H, self.W, with_src=False)
+        n_src, n_coef = pk["src_bytes"], pk["coef"].size
         grew = self._ensure("src", n_src, torch.uint8)
         grew |= self._ensure("coef", n_coef, torch.int32)
         grew |= self._ensure("tmp", pk["tmp_bytes"], torch.uint8, host=False)
@@ -148,7 +169,9 @@ class Letterbox:
         desc = self._desc_host.numpy()
         desc[:] = 0
         desc[: len(images)] = pk["desc"]
-        self._host["src"].numpy()[:n_src] = pk["src"]
+        src_np = self._host["src"].numpy()
+        # pageable -> pinned: one memcpy per image, spread over a few threads (numpy releases the GIL for the copy)
+        list(_pool().map(lambda part: np.copyto(src_np[part[0]: part[0] + part[1].size], part[1]), pk["src_parts"]))
         self._host["coef"].numpy()[:n_coef] = pk["coef"]
         self._devb["src"][:n_src].copy_(self._host["src"][:n_src], non_blocking=True)
         self._devb["coef"][:n_coef].copy_(self._host["coef"][:n_coef], non_blocking=True)
