@@ -61,6 +61,7 @@ struct PPDev {
     unsigned int* shist;    // [2][B][256] radix-select histograms (leading / second score digit)
     unsigned int* sel;      // [B][4]: keep_all, leading digit of the cut, candidates still needed inside it, 16-bit cut prefix
     unsigned int* counts2;  // [B] candidates per image after the select
+    unsigned int* kept_hist;  // [B][256] confirmed NMS survivors per bucket of 256 ranks (cross-class early exit)
     unsigned int* maxc;     // per image max coordinate (order-preserving uint encoding of float)
     float4* cand_box;
     float* cand_score;
@@ -97,6 +98,7 @@ __global__ void pp_reset_kernel(PPDev d) {
     }
     if (t < 32 * 256) d.totals[t] = 0;
     for (int i = t; i < 2 * d.p.B * 256; i += gridDim.x * blockDim.x) d.shist[i] = 0;
+    for (int i = t; i < d.p.B * 256; i += gridDim.x * blockDim.x) d.kept_hist[i] = 0;
 }
 
 // One warp per contiguous range of anchor rows (image, anchor-in-level): lanes stride over the classes (coalesced, no
@@ -534,6 +536,7 @@ __global__ void __launch_bounds__(128) pp_nms_kernel(PPDev d, const unsigned lon
     __shared__ unsigned int cmask[128][4];
     __shared__ unsigned char calive[128];
     __shared__ int s_nk;
+    __shared__ unsigned int s_sum;
     const int cls = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const unsigned int lo_b = d.seg2[b], hi_b = d.seg2[b + 1];
     if (lo_b == hi_b) return;
@@ -569,12 +572,30 @@ __global__ void __launch_bounds__(128) pp_nms_kernel(PPDev d, const unsigned lon
         // a class can contribute at most max_per_img detections to the image's final top-max_per_img (its kept
         // candidates are in score order), so the rest of the segment cannot matter: exact early exit
         if (s_nk >= d.p.max_per_img) break;
+        // Exact cross-class early exit: the image's output is its first max_per_img survivors in rank (= score) order.  Every
+        // block publishes its confirmed survivors per bucket of 256 ranks; once max_per_img survivors are known in buckets that
+        // lie entirely before this chunk's first rank, nothing this block could still keep can reach the output.  (Which
+        // blocks get to skip work depends on timing; the output does not.)
+        {
+            const unsigned int lim = (unsigned int)(sorted2[s0 + base] & 0xFFFFu) >> 8;
+            if (tid == 0) s_sum = 0;
+            __syncthreads();
+            const volatile unsigned int* kh = d.kept_hist + b * 256;
+            unsigned int v = 0;
+            if ((unsigned int)tid < lim) v += kh[tid];
+            if ((unsigned int)tid + 128u < lim) v += kh[tid + 128];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0 && v) atomicAdd(&s_sum, v);
+            __syncthreads();
+            if (s_sum >= (unsigned int)d.p.max_per_img) break;
+        }
         const int t = base + tid;
         const bool valid = t < n;
         float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-        unsigned int slot = 0;
+        unsigned int slot = 0, r = 0;
         if (valid) {
-            const unsigned int r = (unsigned int)(sorted2[s0 + t] & 0xFFFFu);
+            r = (unsigned int)(sorted2[s0 + t] & 0xFFFFu);
             slot = lo_b + r;
             const float4 bx = d.cand_box[slot];
             mine = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
@@ -612,7 +633,10 @@ __global__ void __launch_bounds__(128) pp_nms_kernel(PPDev d, const unsigned lon
             s_nk = nk2;
         }
         __syncthreads();
-        if (valid && calive[tid] == 2) d.keep[slot] = 1;
+        if (valid && calive[tid] == 2) {
+            d.keep[slot] = 1;
+            atomicAdd(&d.kept_hist[b * 256 + (r >> 8)], 1u);
+        }
         __syncthreads();
     }
 }
@@ -683,7 +707,7 @@ static unsigned long long align256(unsigned long long x) { return (x + 255) & ~2
 
 struct PPLayout {
     unsigned long long off_keys0, off_keys1, off_hist, off_ctrl, off_counts, off_seg, off_nsel, off_seg2, off_maxc, off_box, off_score, off_label,
-        off_anchor, off_keys2a, off_keys2b, off_keep, off_kept, off_shist, off_sel, off_counts2, total;
+        off_anchor, off_keys2a, off_keys2b, off_keep, off_kept, off_shist, off_sel, off_counts2, off_kept_hist, total;
 };
 static PPLayout pp_layout(int B, int A, int K, int nms_pre) {
     PPLayout L;
@@ -711,6 +735,7 @@ static PPLayout pp_layout(int B, int A, int K, int nms_pre) {
     L.off_shist = o; o = align256(o + 2ull * B * 256 * 4);
     L.off_sel = o; o = align256(o + (B + 1) * 16ull);
     L.off_counts2 = o; o = align256(o + (B + 1) * 4ull);
+    L.off_kept_hist = o; o = align256(o + (unsigned long long)B * 256 * 4);
     L.total = o;
     return L;
 }
@@ -861,6 +886,7 @@ int compile_postprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     o->d.shist = (unsigned int*)(w + L.off_shist);
     o->d.sel = (unsigned int*)(w + L.off_sel);
     o->d.counts2 = (unsigned int*)(w + L.off_counts2);
+    o->d.kept_hist = (unsigned int*)(w + L.off_kept_hist);
     o->passes1 = (o->d.idx_bits + 30 + o->d.b_bits + 7) / 8;
     o->passes2 = (16 + o->d.cls_bits + o->d.b_bits + 7) / 8;
     o->kernels = 1 + p.nlevels + 5 + 3 * (o->passes1 + o->passes2) + 4;
