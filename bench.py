@@ -19,7 +19,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -56,8 +55,8 @@ class ClockSampler:
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index, uuid=None):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
-        self._nvml, self._h, self.source = None, None, "nvidia-smi"
+        self.index, self.rows = index, []
+        self._nvml, self._h, self.source, self._max, self.errors = None, None, "nvidia-smi", None, 0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -80,7 +79,9 @@ class ClockSampler:
     def _sample_nvml(self):
         n, h = self._nvml, self._h
         sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
-        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        if self._max is None:
+            self._max = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)   # ~2 ms per call: query once
+        mx = self._max
         try:
             r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
         except Exception:
@@ -93,28 +94,33 @@ class ClockSampler:
             pw = 0.0
         return [str(sm), str(mx), f"{pw:.1f}"] + ["Active" if (r & b) else "Not Active" for b in bits]
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                if self._nvml is not None:
-                    self.rows.append(self._sample_nvml())
-                else:
-                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                         capture_output=True, text=True, timeout=5).stdout.strip()
-                    if out:
-                        self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.005 if self._nvml is not None else 0.2)
+    def sample(self):
+        """One sample, taken inline by the caller (the timed loop polls its end event and samples between polls, so the
+        samples are guaranteed to fall inside the region regardless of how Python schedules threads)."""
+        try:
+            if self._nvml is not None:
+                self.rows.append(self._sample_nvml())
+            else:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+        except Exception:
+            self.errors += 1
+
+    def poll_until(self, event):
+        """Sample every ~3 ms until the CUDA event has completed."""
+        while not event.query():
+            self.sample()
+            time.sleep(0.003)
+        if not self.rows:
+            self.sample()
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        return False
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -122,7 +128,7 @@ class ClockSampler:
         pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_min_mhz=sm[0] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(self.rows), power_w_max=max(pw) if pw else None, source=self.source)
+                    samples=len(self.rows), power_w_max=max(pw) if pw else None, source=self.source, sample_errors=self.errors)
 
 
 def host_threads():
@@ -272,6 +278,7 @@ def run_ours(args):
             if world > 1:
                 all_gather_dets()
         e1.record()
+        clk.poll_until(e1)      # the steps are enqueued asynchronously: sample clocks while the device works through them
         barrier()
     ms = e0.elapsed_time(e1)
     launches = L.launch_count() - l0

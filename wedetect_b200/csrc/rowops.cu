@@ -706,13 +706,19 @@ __global__ void __launch_bounds__((kDwConsumerWarps + 1) * 32, 1) dwconv7_tma_ke
     }
     __syncthreads();
     const int per_img = p.nty * p.ntx * p.nchunks;
+    // each CTA walks a contiguous range of items (chunk fastest, then x tile, y tile, image): the coordinates advance by
+    // counters, the divisions of the decode happen once per CTA instead of once per item and warp
+    const int ipc = (p.num_items + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int it0 = min((int)blockIdx.x * ipc, p.num_items), it1 = min(it0 + ipc, p.num_items);
     if (warp == kDwConsumerWarps) {
         if (lane == 0) {
             int slot = 0, phase = 0;
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-                const int bi = item / per_img, r0 = item - bi * per_img;
-                const int ck = r0 % p.nchunks, r1 = r0 / p.nchunks;
-                const int xt = r1 % p.ntx, yt = r1 / p.ntx;
+            int bi = it0 / per_img, ck, xt, yt;
+            {
+                const int r0 = it0 - bi * per_img, r1 = r0 / p.nchunks;
+                ck = r0 % p.nchunks; xt = r1 % p.ntx; yt = r1 / p.ntx;
+            }
+            for (int item = it0; item < it1; ++item) {
                 mbar_wait(&bars[2 + slot], phase ^ 1);
                 mbar_arrive_expect_tx(&bars[slot], (uint32_t)(halo_bytes + 49 * kDw2CK * 4));
                 uint8_t* dst = dsm8 + slot * slot_bytes;
@@ -722,6 +728,7 @@ __global__ void __launch_bounds__((kDwConsumerWarps + 1) * 32, 1) dwconv7_tma_ke
                     slot = 0;
                     phase ^= 1;
                 }
+                if (++ck == p.nchunks) { ck = 0; if (++xt == p.ntx) { xt = 0; if (++yt == p.nty) { yt = 0; ++bi; } } }
             }
         }
         return;
@@ -730,10 +737,12 @@ __global__ void __launch_bounds__((kDwConsumerWarps + 1) * 32, 1) dwconv7_tma_ke
     const bool active = tile < p.tx * p.ty;
     const int tix = tile % p.tx, tiy = tile / p.tx;
     int slot = 0, phase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int bi = item / per_img, r0 = item - bi * per_img;
-        const int ck = r0 % p.nchunks, r1 = r0 / p.nchunks;
-        const int xt = r1 % p.ntx, yt = r1 / p.ntx;
+    int bi = it0 / per_img, ck, xt, yt;
+    {
+        const int r0 = it0 - bi * per_img, r1 = r0 / p.nchunks;
+        ck = r0 % p.nchunks; xt = r1 % p.ntx; yt = r1 / p.ntx;
+    }
+    for (int item = it0; item < it1; ++item) {
         const int c0 = ck * kDw2CK, x0 = xt * 8 * p.tx, y0 = yt * 4 * p.ty;
         mbar_wait(&bars[slot], phase);
         if (active && c0 + pair * 2 < p.C && y0 + tiy * 4 < p.H && x0 + tix * 8 < p.W) {
@@ -778,14 +787,34 @@ __global__ void __launch_bounds__((kDwConsumerWarps + 1) * 32, 1) dwconv7_tma_ke
             }
             const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + c0 + pair * 2));
             float* obase = p.yscr + (((long long)bi * p.H + y0 + tiy * 4) * p.W + x0 + tix * 8) * p.C + c0 + pair * 2;
+            if (y0 + tiy * 4 + 3 < p.H && x0 + tix * 8 + 7 < p.W) {
+                // interior thread tile (every tile of the 160 / 80 / 40 maps): unchecked 8-byte stores off two running pointers
+                uint64_t b2p;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(b2p) : "f"(b2.x), "f"(b2.y));
+                const long long cs = p.C, rs = (long long)p.W * p.C;
+                float* prow = obase;
 #pragma unroll
-            for (int oy = 0; oy < 4; ++oy) {
-                if (y0 + tiy * 4 + oy < p.H) {
+                for (int oy = 0; oy < 4; ++oy) {
+                    float* pp = prow;
 #pragma unroll
                     for (int ox = 0; ox < 8; ++ox) {
-                        if (x0 + tix * 8 + ox < p.W)
-                            *reinterpret_cast<float2*>(obase + ((long long)oy * p.W + ox) * p.C) =
-                                make_float2(unpack_lo(acc[oy][ox]) + b2.x, unpack_hi(acc[oy][ox]) + b2.y);
+                        uint64_t v;
+                        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(acc[oy][ox]), "l"(b2p));
+                        *reinterpret_cast<uint64_t*>(pp) = v;
+                        pp += cs;
+                    }
+                    prow += rs;
+                }
+            } else {
+#pragma unroll
+                for (int oy = 0; oy < 4; ++oy) {
+                    if (y0 + tiy * 4 + oy < p.H) {
+#pragma unroll
+                        for (int ox = 0; ox < 8; ++ox) {
+                            if (x0 + tix * 8 + ox < p.W)
+                                *reinterpret_cast<float2*>(obase + ((long long)oy * p.W + ox) * p.C) =
+                                    make_float2(unpack_lo(acc[oy][ox]) + b2.x, unpack_hi(acc[oy][ox]) + b2.y);
+                        }
                     }
                 }
             }
@@ -796,6 +825,7 @@ __global__ void __launch_bounds__((kDwConsumerWarps + 1) * 32, 1) dwconv7_tma_ke
             slot = 0;
             phase ^= 1;
         }
+        if (++ck == p.nchunks) { ck = 0; if (++xt == p.ntx) { xt = 0; if (++yt == p.nty) { yt = 0; ++bi; } } }
     }
 }
 
