@@ -131,6 +131,15 @@ class ClockSampler:
                     samples=len(self.rows), power_w_max=max(pw) if pw else None, source=self.source, sample_errors=self.errors)
 
 
+def workload_names(args):
+    """(metric string, workload label): the default flags are BASELINE configs[1]; other flag sets are side measurements."""
+    key = (args.size, args.batch, args.res, args.classes)
+    tag = {("base", 32, 640, 80): " (BASELINE configs[1])", ("large", 16, 800, 1203): " (BASELINE configs[2])",
+           ("tiny", 1, 640, 5): " (BASELINE configs[0])"}.get(key, " (side measurement, not a BASELINE config)")
+    metric = f"images/sec at {args.res}x{args.res} bs{args.batch} WeDetect-{args.size.capitalize()}"
+    return metric, f"WeDetect-{args.size.capitalize()} bs{args.batch}/GPU {args.res}x{args.res} K={args.classes}{tag}"
+
+
 def host_threads():
     """CPU threads we may actually use: affinity mask, capped by the cgroup quota (a 128-core box with an 8-core
     quota thrashes if torch spawns 128 workers) and by 32."""
@@ -191,14 +200,15 @@ def run_reference(args):
     times = [step(n) for _ in range(args.steps)]
     tot = sum(times)
     val = n * len(times) / tot
-    line = dict(metric="images/sec at 640x640 bs32 WeDetect-Base", value=val, unit="images/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
+    metric, label = workload_names(args)
+    line = dict(metric=metric, value=val, unit="images/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1000 * tot / len(times), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic",
-                config=dict(workload=f"WeDetect-{args.size.capitalize()} bs{args.batch} {args.res}x{args.res} K={args.classes} (configs[1])",
+                config=dict(workload=label,
                             note="reference algorithm (oracle/functional.py fp32 + oracle/postprocess_ref.c) on host cores; each step is a bounded sample"),
                 cpu_baseline=dict(value=val, unit="images/s", cores=threads, kind="port", sample=f"{n} images of the bs{args.batch} workload per step"),
                 e2e=dict(value=val, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    _emit(line)
 
 
 def run_ours(args):
@@ -406,9 +416,10 @@ def run_ours(args):
             parity = dict(error=str(e)[:300])
 
     h2d = host.numel() * host.element_size()
-    line = dict(metric="images/sec at 640x640 bs32 WeDetect-Base", value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+    metric, label = workload_names(args)
+    line = dict(metric=metric, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                config=dict(workload=f"WeDetect-{args.size.capitalize()} bs{B}/GPU {H}x{W} K={K} (BASELINE configs[1])", parallelism=f"dp{world}",
+                config=dict(workload=label, parallelism=f"dp{world}",
                             mode="fast: bf16 operands, fp32 accumulate / residual stream (parity_mode = the same step with bf16x3 operands)",
                             weights="seeded synthetic, BN-calibrated, sparse score regime" if args.regime == "sparse" else "seeded synthetic, dense score regime",
                             text_tower="cached once per text set (not in the timed region)", l2="inputs + activations (GBs per step) far exceed the 126 MB L2",
@@ -416,12 +427,23 @@ def run_ours(args):
                 e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h // args.steps,
                          api="YOLOWorldDetector.test_step(pinned uint8 BGR batch) + last_batch_result -> host"),
                 gpu_launches=int(launches), clocks=clk.summary(), roofline=roofline, cpu_baseline=cpu, parity_mode=parity)
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The ONE JSON line goes to the process's original stdout."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner under NCCL_DEBUG=VERSION,
+    # torchrun notices) is sent to stderr instead
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
