@@ -424,7 +424,7 @@ def run_ours(args):
                             weights="seeded synthetic, BN-calibrated, sparse score regime" if args.regime == "sparse" else "seeded synthetic, dense score regime",
                             text_tower="cached once per text set (not in the timed region)", l2="inputs + activations (GBs per step) far exceed the 126 MB L2",
                             cuda_graph=True, all_gather="one NCCL all_gather of [B,300,6] detections per step" if world > 1 else None),
-                e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h // args.steps,
+                e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=world * (d2h // args.steps),
                          api="YOLOWorldDetector.test_step(pinned uint8 BGR batch) + last_batch_result -> host"),
                 gpu_launches=int(launches), clocks=clk.summary(), roofline=roofline, cpu_baseline=cpu, parity_mode=parity)
     _emit(line)
