@@ -147,3 +147,49 @@ def test_cuda_graph_replay_matches_eager():
     torch.cuda.synchronize()
     for k, v in p.results().items():
         assert torch.equal(v, eager[k]), k
+
+
+def test_full_size_batch_invariance_and_output_properties():
+    """BASELINE configs[1] at full size (Base, bs 32, 640x640, K = 80, fast mode): size-independent properties.
+    (1) image sharding is exact: the detections of an image do not depend on which batch it travels in (the basis of the
+        multi-GPU partitioning: rank r of N gets a contiguous shard and the all-gather just concatenates);
+    (2) per image: counts <= max_per_img, scores descending and above score_thr, labels in range, boxes inside the image and
+        well formed, anchors valid, padding rows zeroed / -1."""
+    from oracle import synth
+    from wedetect_b200 import plan, schema, weights
+    size, B, H, W, K = "base", 32, 640, 640, 80
+    sd = synth.synth_state_dict(size, seed=0, with_text=False, regime="sparse")
+    Wt = weights.prepare_vision(sd, size, D, input_format="u8_bgr")
+    text = torch.randn(K, schema.EMBED_DIM, generator=torch.Generator().manual_seed(5)).to(D)
+    imgs = (synth.synth_images(B, H, W, seed=2) * 255).to(torch.uint8).flip(1).contiguous().to(D)
+    out = {}
+    for b in (32, 16):
+        p = plan.VisionPlan(Wt, size, b, H, W, K=K, input_dtype=torch.uint8, score_thr=0.001, nms_mode=0)
+        p.set_text(text)
+        res = []
+        for s in range(0, B, b):
+            p.image.copy_(imgs[s:s + b])
+            p.run()
+            torch.cuda.synchronize()
+            res.append({k: v.clone() for k, v in p.results().items()})
+        out[b] = {k: torch.cat([r[k] for r in res]) for k in res[0]}
+        del p
+        torch.cuda.empty_cache()
+    for k in out[32]:
+        assert torch.equal(out[32][k], out[16][k]), f"{k}: a batch of 32 and two batches of 16 disagree"
+    r = {k: v.cpu() for k, v in out[32].items()}
+    A = sum(h * w for h, w in schema.level_hw(H, W))
+    assert int(r["counts"].max()) <= 300 and int(r["counts"].min()) >= 1
+    for b in range(B):
+        n = int(r["counts"][b])
+        s = r["scores"][b, :n]
+        assert bool((s[:-1] >= s[1:]).all()) and float(s.min()) > 0.001 and float(s.max()) <= 1.0
+        assert int(r["labels"][b, :n].min()) >= 0 and int(r["labels"][b, :n].max()) < K
+        assert int(r["anchors"][b, :n].min()) >= 0 and int(r["anchors"][b, :n].max()) < A
+        bx = r["boxes"][b, :n]
+        assert float(bx.min()) >= 0.0 and float(bx[:, 0::2].max()) <= W and float(bx[:, 1::2].max()) <= H
+        assert bool((bx[:, 2] >= bx[:, 0]).all()) and bool((bx[:, 3] >= bx[:, 1]).all())
+        assert float(r["scores"][b, n:].abs().sum()) == 0.0 and bool((r["labels"][b, n:] == -1).all())
+        # (anchor, class) pairs are unique inside an image
+        key = r["anchors"][b, :n].long() * K + r["labels"][b, :n].long()
+        assert key.unique().numel() == n

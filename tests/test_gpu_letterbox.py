@@ -73,3 +73,14 @@ def test_uni_forward_with_device_letterbox_matches_tensor_path():
         h, w = imgs[b].shape[:2]
         bb = res[b]["bboxes"]
         assert float(bb[:, 0::2].max()) <= w and float(bb[:, 1::2].max()) <= h and float(bb.min()) >= 0.0
+
+
+def test_letterbox_full_size_sources():
+    """Camera-sized sources (the shapes tools/bench_aux.py times): 1280x960 and 1920x1080 -> 640x640, bit-exact."""
+    from wedetect_b200.preprocess import Letterbox
+    rng = np.random.default_rng(11)
+    out = torch.zeros(4, 3, 640, 640, dtype=torch.uint8, device=D)
+    lb = Letterbox(out)
+    imgs = [rng.integers(0, 256, (960, 1280, 3), dtype=np.uint8), rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8),
+            rng.integers(0, 256, (1280, 960, 3), dtype=np.uint8)]
+    _check(lb, imgs, 640, 640)
