@@ -154,6 +154,13 @@ enum wd_op_kind {
      *    3 tmp u8 workspace (sum over images of rows * new_w * 3 bytes)  4 out u8 [B, 3, H, W]
      * desc / coef / src are re-filled by the host before every run (the pointers are fixed, so the op can sit in a graph). */
     WD_OP_LETTERBOX = 16,
+    /* ConvNeXt block MLP in one kernel (fast path, C = 128 / hidden 512 only: WeDetect-Base stage 0):
+     *   x[m,:] += gamma * (W2 . GELU(W1 . t[m,:] + b1) + b2)      mm_backbone.py:117-124 (pwconv1, act, pwconv2, gamma, residual)
+     * The 4C-wide hidden activation stays on chip (TMEM -> bf16 shared-memory operand), weights are resident in the
+     * shared memory of a CTA pair.  Same arithmetic as two WD_OP_GEMM records (bf16 operands, fp32 accumulation, bf16 hidden).
+     * i: 0 M 1 C 2 H 3 ld of t (0 = C)
+     * p: 0 t bf16 [M, C]  1 W1 bf16 [H, C]  2 W2 bf16 [C, H]  3 b1 f32[H]  4 b2 f32[C]  5 gamma f32[C]  6 x f32 [M, C] (in place) */
+    WD_OP_MLP_FUSED = 17,
 };
 
 enum wd_act { WD_ACT_NONE = 0, WD_ACT_RELU = 1, WD_ACT_SILU = 2, WD_ACT_GELU = 3 };

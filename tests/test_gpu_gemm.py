@@ -234,3 +234,34 @@ def test_deconv_and_im2col_precise():
     col = P3.zeros((B * 5 * 5, 9 * Cin), d, True)
     _run(ops.im2col_s2(Ap, col))
     report_close("im2col precise", col.value(), R.im2col_s2_ref(A), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("M", [256, 2048, 256 * 75 + 128, 160 * 160 * 4])
+def test_mlp_fused_matches_two_gemms(M):
+    """WD_OP_MLP_FUSED (ConvNeXt block MLP in one kernel, C = 128 / hidden 512) against the two WD_OP_GEMM records it replaces
+    (same bf16 operands, bf16 hidden, fp32 accumulation in the same k order) and against an fp32 torch reference."""
+    from wedetect_b200 import _lib as L, ops
+    from wedetect_b200.ops import P3
+    g = torch.Generator().manual_seed(M)
+    C, H = 128, 512
+    D = "cuda:0"
+    t = (torch.randn(M, C, generator=g)).to(torch.bfloat16).to(D)
+    W1 = (torch.randn(H, C, generator=g) / C ** 0.5).to(torch.bfloat16).to(D)
+    W2 = (torch.randn(C, H, generator=g) / H ** 0.5).to(torch.bfloat16).to(D)
+    b1 = (torch.randn(H, generator=g) * 0.1).to(D)
+    b2 = (torch.randn(C, generator=g) * 0.1).to(D)
+    gamma = (torch.rand(C, generator=g) * 0.45 + 0.05).to(D)
+    x0 = torch.randn(M, C, generator=g).to(D)
+    # reference path: the two GEMM ops
+    x_ref = x0.clone()
+    hid = torch.zeros(M, H, dtype=torch.bfloat16, device=D)
+    L.run_op(ops.linear(P3(t), P3(W1), P3(hid), bias=b1, act=L.ACT_GELU))
+    L.run_op(ops.linear(P3(hid), P3(W2), x_ref, bias=b2, gamma=gamma, resid=x_ref, alpha=1.0))
+    x_fused = x0.clone()
+    assert ops.mlp_fused_ok(P3(t), P3(W1), P3(W2), x_fused)
+    L.run_op(ops.mlp_fused(P3(t), P3(W1), P3(W2), b1, b2, gamma, x_fused))
+    torch.cuda.synchronize()
+    report_close("fused vs two GEMMs", x_fused, x_ref, rtol=0.0, atol=1e-5)
+    h32 = torch.nn.functional.gelu(t.float() @ W1.float().t() + b1).to(torch.bfloat16).float()
+    want = x0 + gamma * (h32 @ W2.float().t() + b2)
+    report_close("fused vs torch", x_fused, want, rtol=2e-2, atol=2e-2)

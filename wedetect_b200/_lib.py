@@ -14,7 +14,7 @@ WD_OP_NI, WD_OP_NF, WD_OP_NP = 40, 8, 16
 # enum wd_op_kind
 OP_GEMM, OP_LN_ROWS, OP_DWCONV_LN, OP_STEM_PATCH, OP_IM2COL_S2, OP_CAST_BF16 = 1, 2, 3, 4, 5, 6
 OP_TEXT_EMBED, OP_ATTN_SMALL, OP_L2NORM_ROWS, OP_GATHER_ROWS, OP_FOLD_TEXT, OP_POSTPROCESS, OP_GATHER_EMBED = 7, 8, 9, 10, 11, 12, 13
-OP_SCALE_ROWS, OP_RETR_REDUCE, OP_LETTERBOX = 14, 15, 16
+OP_SCALE_ROWS, OP_RETR_REDUCE, OP_LETTERBOX, OP_MLP_FUSED = 14, 15, 16, 17
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
 
 EXPORTS = [

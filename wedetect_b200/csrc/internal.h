@@ -64,6 +64,7 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
 int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out);
 int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out);  // LN / dwconv / stem / im2col / cast / text
 int compile_postprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out);
-int compile_preprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out);   // letterbox (PIL-exact resize + paste)
+int compile_preprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out);
+int compile_mlp_fused(const wd_op& op, std::unique_ptr<CompiledOp>& out);    // ConvNeXt block MLP in one kernel (C = 128)   // letterbox (PIL-exact resize + paste)
 
 }  // namespace wd

@@ -213,6 +213,31 @@ def deconv2x2(A, W, C, bias2):
     return ops
 
 
+MLP_FUSED = _os.environ.get("WD_NO_FUSED_MLP") != "1"   # A/B switch: ConvNeXt stage-0 MLP as one kernel
+
+
+def mlp_fused_ok(t, W1, W2, x):
+    """The fused block-MLP kernel covers single-plane bf16 operands with C = 128, hidden = 512 (WeDetect-Base stage 0)."""
+    return (MLP_FUSED and not t.ps and not W1.ps and not W2.ps and tuple(W1.t.shape) == (512, 128) and tuple(W2.t.shape) == (128, 512)
+            and x.shape[1] == 128 and x.is_contiguous() and W1.t.is_contiguous() and W2.t.is_contiguous())
+
+
+def mlp_fused(t, W1, W2, b1, b2, gamma, x):
+    """x += gamma * (W2 . GELU(W1 . t + b1) + b2) in one kernel (hidden activation stays on chip)."""
+    (t, _), (W1, _), (W2, _) = _tp(t), _tp(W1), _tp(W2)
+    _chk(t, torch.bfloat16, "t"); _chk(W1, torch.bfloat16, "W1"); _chk(W2, torch.bfloat16, "W2"); _chk(x, torch.float32, "x")
+    M, C = t.shape
+    H = W1.shape[0]
+    assert W1.shape == (H, C) and W2.shape == (C, H) and x.shape == (M, C) and x.is_contiguous()
+    assert b1.numel() == H and b2.numel() == C and gamma.numel() == C
+    op = WdOp()
+    op.kind = L.OP_MLP_FUSED
+    op.i[0], op.i[1], op.i[2], op.i[3] = M, C, H, t.stride(0)
+    for k, v in enumerate((t, W1, W2, b1, b2, gamma, x)):
+        op.p[k] = _ptr(v)
+    return op
+
+
 def ln_rows(x, w, b, eps, *, out_bf16=None, out_f32=None, s2d_hw=None):
     out_bf16, o_ps = _tp(out_bf16)
     _chk(x, torch.float32, "x")

@@ -150,6 +150,10 @@ class VisionPlan:
             for j in range(depths[s]):
                 q = f"s{s}.b{j}."
                 self.ops.append(ops.dwconv_ln(x4, t_ln.p3, W_[q + "dw_w"], W_[q + "dw_b"], W_[q + "ln_w"], W_[q + "ln_b"], schema.LN_EPS, scratch=scratch_dw))
+                if ops.mlp_fused_ok(t_ln.p3, self._mat(q + "w1"), self._mat(q + "w2"), x):
+                    # C = 128: pw1 -> GELU -> pw2 -> LayerScale -> residual in one kernel, the hidden tile stays on chip
+                    self.ops.append(ops.mlp_fused(t_ln.p3, self._mat(q + "w1"), self._mat(q + "w2"), W_[q + "b1"], W_[q + "b2"], W_[q + "gamma"], x))
+                    continue
                 self._linear(t_ln, q + "w1", t_hid, bias=W_[q + "b1"], act=L.ACT_GELU)
                 self._linear(t_hid, q + "w2", x, bias=W_[q + "b2"], gamma=W_[q + "gamma"], resid=x, alpha=1.0)
             c = self._act(f"c{s + 1}", B, hs[s], ws[s], C)
