@@ -287,8 +287,6 @@ def run_ours(args):
             plan.run()
             if world > 1:
                 all_gather_dets()
-            if clk.source == "nvml":
-                clk.sample()    # ~10 us in-process query: the device is inside the timed region whenever this runs
         e1.record()
         clk.poll_until(e1)      # the steps are enqueued asynchronously: sample clocks while the device works through them
         barrier()
