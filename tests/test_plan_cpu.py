@@ -52,13 +52,17 @@ def test_plan_builds_for_all_sizes_on_cpu(monkeypatch):
     monkeypatch.setattr(L, "Program", FakeProg)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda: types.SimpleNamespace(cuda_stream=0))
     from wedetect_b200 import plan, weights
-    for size, res, K, precise in (("tiny", 320, 5, False), ("base", 320, 80, True), ("large", 160, 16, False)):
+    for size, res, K, precise in (("tiny", 320, 5, False), ("base", 320, 80, True), ("base", 320, 80, False), ("large", 160, 16, False)):
         sd = synth.synth_state_dict(size, seed=0, uni=True, num_prompts=K, with_text=False, calibrate=False)
         Wt = weights.prepare_vision(sd, size, "cpu", precise=precise)
-        p = plan.VisionPlan(Wt, size, 2, res, res, K=K, uni=True, nms_mode=1, score_thr=0.0, device="cpu")
+        p = plan.VisionPlan(Wt, size, 2, res, res, K=K, uni=True, nms_mode=1, score_thr=0.0, extract=(size == "large"), device="cpu")
         kinds = [op.kind for op in p.ops]
         assert kinds.count(L.OP_DWCONV_LN) == sum({"tiny": (3, 3, 9, 3)}.get(size, (3, 3, 27, 3)))
         assert kinds[-2:] == [L.OP_POSTPROCESS, L.OP_GATHER_EMBED]
+        # the fused block-MLP kernel covers exactly the C = 128 stage of the fast path (Base stage 0: 3 blocks, 6 GEMMs fewer)
+        assert kinds.count(L.OP_MLP_FUSED) == (3 if (size == "base" and not precise) else 0)
+        # extract variant: the gather op also emits per-proposal logit_scale / bias rows
+        assert bool(p.ops[-1].p[10]) == (size == "large") and ("scales" in p.results()) == (size == "large")
         for op in p.ops:
             if op.kind == L.OP_GEMM:
                 assert op.i[30] == (3 if precise else 1) and op.i[6] % 64 == 0 and op.i[8] % 8 == 0
