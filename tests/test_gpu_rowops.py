@@ -19,7 +19,7 @@ def _g(seed):
     return torch.Generator().manual_seed(seed)
 
 
-@pytest.mark.parametrize("rows,C", [(1000, 128), (333, 96), (257, 512), (64, 1536), (100, 768)])
+@pytest.mark.parametrize("rows,C", [(1000, 128), (333, 96), (1001, 256), (7, 192), (3, 128), (257, 512), (64, 1536), (100, 768)])
 def test_ln_rows(rows, C):
     from wedetect_b200 import ops
     g = _g(1)

@@ -14,8 +14,8 @@
 //     GEMM1 (M 256, N 256, K 128) -> TMEM acc1 -> epilogue (bias, GELU, bf16) -> smem Hs (4 sub-tiles of 64 hidden units
 //     = the 4 K-blocks of GEMM2) -> GEMM2 (M 256, N 128, K 256) accumulates into TMEM acc2; final epilogue
 //     x + gamma * (acc2 + b2) -> fp32 -> swizzled staging (the Hs bytes) -> per-warp TMA stores;
-//   * warp roles as in gemm_tc.cu: warp 0 TMA producer, warp 1 MMA issuer (pair leader only), warp 2 TMEM allocator,
-//     warps 4..11 two epilogue warpgroups (sub-tiles / column chunks wg, wg + 2).
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (pair leader only), warp 2 TMEM allocator, warps 4..19 sixteen
+//     epilogue warps = (64-column sub-tile / 32-column output chunk) x (TMEM lane quarter).
 // HBM traffic per layer: t 210 MB + x read 419 MB + x write 419 MB (was 2.7 GB for the two GEMMs).
 #include "internal.h"
 #include "epi_math.cuh"
@@ -25,7 +25,11 @@ namespace wd {
 
 constexpr int kMC = 128;          // channels
 constexpr int kMH = 512;          // hidden units
-constexpr int kMThreads = 384;
+// Epilogue width: the GELU epilogue is latency bound with two warps per scheduler; sixteen epilogue warps (four per
+// scheduler, one 64-column sub-tile / one 32-column output chunk each) hide it.  Register budget: 640 threads are compiled
+// for 96 registers; the four service warps drop to 56, the epilogue warps rise to 104.
+constexpr int kMEpiWarps = 16;
+constexpr int kMThreads = 128 + 32 * kMEpiWarps;
 constexpr int kW1Bytes = 4 * 16384;   // [chunk 0..1][k-block 0..1][128 rows x 128 B]
 constexpr int kW2Bytes = 8 * 8192;    // [k-block 0..7][64 rows x 128 B]
 constexpr int kABytes = 2 * 16384;    // [k-block 0..1][128 rows x 128 B]
@@ -66,11 +70,11 @@ __global__ void __launch_bounds__(kMThreads, 1) mlp_fused_kernel(const __grid_co
     uint64_t* bar_a_full = bars + 1;       // leader: both halves of the A tile landed
     uint64_t* bar_a_empty = bars + 2;      // both: GEMM1 of the tile's last chunk retired -> A may be overwritten
     uint64_t* bar_acc1_full = bars + 3;    // both: a GEMM1 retired
-    uint64_t* bar_acc1_empty = bars + 4;   // leader: all 16 epilogue warps have read acc1
+    uint64_t* bar_acc1_empty = bars + 4;   // leader: all epilogue warps of both CTAs have read acc1
     uint64_t* bar_hs_full = bars + 5;      // leader, [4]: sub-tile s of Hs written by both CTAs (8 warps)
     uint64_t* bar_hs_empty = bars + 9;     // both: GEMM2 of chunk 0 retired -> Hs may be overwritten
     uint64_t* bar_acc2_full = bars + 10;   // both: GEMM2 of the tile's last chunk retired
-    uint64_t* bar_acc2_empty = bars + 11;  // leader: all 16 epilogue warps have read acc2
+    uint64_t* bar_acc2_empty = bars + 11;  // leader: all epilogue warps of both CTAs have read acc2
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,11 +92,11 @@ __global__ void __launch_bounds__(kMThreads, 1) mlp_fused_kernel(const __grid_co
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
         mbar_init(bar_acc1_full, 1);
-        mbar_init(bar_acc1_empty, 16);
+        mbar_init(bar_acc1_empty, 2 * kMEpiWarps);
         for (int s = 0; s < 4; ++s) mbar_init(&bar_hs_full[s], 8);
         mbar_init(bar_hs_empty, 1);
         mbar_init(bar_acc2_full, 1);
-        mbar_init(bar_acc2_empty, 16);
+        mbar_init(bar_acc2_empty, 2 * kMEpiWarps);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(kMThreads, 1) mlp_fused_kernel(const __grid_co
     const uint32_t lead = 0;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0) {
             // ================= TMA producer =================
             const uint32_t lead_w = mapa_u32(smem_u32(bar_w_full), lead), lead_a = mapa_u32(smem_u32(bar_a_full), lead);
@@ -189,13 +193,15 @@ __global__ void __launch_bounds__(kMThreads, 1) mlp_fused_kernel(const __grid_co
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        // ================= epilogue warpgroups =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ================= epilogue warps: warp = (sub-tile / output chunk `sub`, TMEM lane quarter) =================
         pdl_wait();
-        const int wg = (warp - 4) >> 2, quarter = warp & 3;
+        const int sub = (warp - 4) >> 2, quarter = warp & 3;
         const int r = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const uint32_t acc1_empty_c = mapa_u32(smem_u32(bar_acc1_empty), lead), acc2_empty_c = mapa_u32(smem_u32(bar_acc2_empty), lead);
+        const uint32_t hs_full_c = mapa_u32(smem_u32(&bar_hs_full[sub]), lead);
+        const uint32_t srow = smem_u32(sHs) + sub * 16384 + r * 128;
         uint32_t it = 0, n1 = 0;
         for (int tile = t_first; tile < p.num_pairs; tile += t_step, ++it) {
             const long long row = (long long)(tile * 2 + crank) * 128 + r;
@@ -204,93 +210,69 @@ __global__ void __launch_bounds__(kMThreads, 1) mlp_fused_kernel(const __grid_co
             for (int j = 0; j < 2; ++j, ++n1) {
                 mbar_wait(bar_acc1_full, n1 & 1);
                 tc_fence_after();
-                // both of this warp's sub-tiles (wg, wg + 2) leave TMEM first, so acc1 goes back to the MMA warp before any math
-                float v[2][64];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    tmem_ld_32x32(lane_base + (wg + 2 * i) * 64, reinterpret_cast<uint32_t*>(v[i]));
-                    tmem_ld_32x32(lane_base + (wg + 2 * i) * 64 + 32, reinterpret_cast<uint32_t*>(v[i] + 32));
-                }
+                // this warp's 64 columns leave TMEM first, so acc1 goes back to the MMA warp before any math
+                float v[64];
+                tmem_ld_32x32(lane_base + sub * 64, reinterpret_cast<uint32_t*>(v));
+                tmem_ld_32x32(lane_base + sub * 64 + 32, reinterpret_cast<uint32_t*>(v + 32));
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc1_empty_c);
+                const int n_base = j * 256 + sub * 64;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int n_base = j * 256 + (wg + 2 * i) * 64;
-#pragma unroll
-                    for (int c = 0; c < 64; c += 2) {
-                        const uint64_t b = pk2(p.b1[n_base + c], p.b1[n_base + c + 1]);
-                        upk2(act2_fast<WD_ACT_GELU>(add2(pk2(v[i][c], v[i][c + 1]), b)), v[i][c], v[i][c + 1]);
-                    }
+                for (int c = 0; c < 64; c += 2) {
+                    const uint64_t b = pk2(p.b1[n_base + c], p.b1[n_base + c + 1]);
+                    upk2(act2_fast<WD_ACT_GELU>(add2(pk2(v[c], v[c + 1]), b)), v[c], v[c + 1]);
                 }
                 if (j == 0) {
-                    // Hs is also this warp's output staging of the previous tile: its TMA stores must have read it
+                    // Hs is also this warp's output staging of the previous tile: its TMA store must have read it
                     if (lane == 0) tma_store_wait_read<0>();
                     __syncwarp();
                 } else {
                     mbar_wait(bar_hs_empty, it & 1);   // GEMM2 of chunk 0 has consumed Hs (the wait hid behind the math above)
                 }
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const uint32_t srow = smem_u32(sHs) + (wg + 2 * i) * 16384 + r * 128;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        uint4 w;
-                        w.x = pack_bf16x2(v[i][q * 8 + 0], v[i][q * 8 + 1]);
-                        w.y = pack_bf16x2(v[i][q * 8 + 2], v[i][q * 8 + 3]);
-                        w.z = pack_bf16x2(v[i][q * 8 + 4], v[i][q * 8 + 5]);
-                        w.w = pack_bf16x2(v[i][q * 8 + 6], v[i][q * 8 + 7]);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((q ^ (r & 7)) << 4)), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-                    }
+                for (int q = 0; q < 8; ++q) {
+                    uint4 w;
+                    w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                    w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                    w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                    w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((q ^ (r & 7)) << 4)), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
                 }
                 fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_release_cluster(mapa_u32(smem_u32(&bar_hs_full[wg]), lead));
-                    mbar_arrive_release_cluster(mapa_u32(smem_u32(&bar_hs_full[wg + 2]), lead));
-                }
+                if (lane == 0) mbar_arrive_release_cluster(hs_full_c);
             }
-            // ---- output: x + gamma * (acc2 + b2) ----
-            uint4 rq[2][8];
+            // ---- output chunk `sub` (32 fp32 columns): x + gamma * (acc2 + b2) ----
+            uint4 rq[8];
+            {
+                const float* rp = p.x + row * kMC + sub * 32;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float* rp = p.x + row * kMC + (wg + 2 * i) * 32;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) rq[i][q] = row_ok ? *reinterpret_cast<const uint4*>(rp + q * 4) : make_uint4(0u, 0u, 0u, 0u);
+                for (int q = 0; q < 8; ++q) rq[q] = row_ok ? *reinterpret_cast<const uint4*>(rp + q * 4) : make_uint4(0u, 0u, 0u, 0u);
             }
             mbar_wait(bar_acc2_full, it & 1);
             tc_fence_after();
-            float o[2][32];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) tmem_ld_32x32(lane_base + 256 + (wg + 2 * i) * 32, reinterpret_cast<uint32_t*>(o[i]));
+            float o[32];
+            tmem_ld_32x32(lane_base + 256 + sub * 32, reinterpret_cast<uint32_t*>(o));
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc2_empty_c);
             // acc2_full means GEMM2 of the last chunk has retired: Hs is free and becomes the output staging
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int c = wg + 2 * i;
-                const uint32_t srow = smem_u32(sHs) + c * 16384 + r * 128;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int n = c * 32 + q * 4;
-                    const float y0 = fmaf(p.gamma[n + 0], o[i][q * 4 + 0] + p.b2[n + 0], __uint_as_float(rq[i][q].x));
-                    const float y1 = fmaf(p.gamma[n + 1], o[i][q * 4 + 1] + p.b2[n + 1], __uint_as_float(rq[i][q].y));
-                    const float y2 = fmaf(p.gamma[n + 2], o[i][q * 4 + 2] + p.b2[n + 2], __uint_as_float(rq[i][q].z));
-                    const float y3 = fmaf(p.gamma[n + 3], o[i][q * 4 + 3] + p.b2[n + 3], __uint_as_float(rq[i][q].w));
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((q ^ (r & 7)) << 4)), "f"(y0), "f"(y1), "f"(y2), "f"(y3) : "memory");
-                }
+            for (int q = 0; q < 8; ++q) {
+                const int n = sub * 32 + q * 4;
+                const float y0 = fmaf(p.gamma[n + 0], o[q * 4 + 0] + p.b2[n + 0], __uint_as_float(rq[q].x));
+                const float y1 = fmaf(p.gamma[n + 1], o[q * 4 + 1] + p.b2[n + 1], __uint_as_float(rq[q].y));
+                const float y2 = fmaf(p.gamma[n + 2], o[q * 4 + 2] + p.b2[n + 2], __uint_as_float(rq[q].z));
+                const float y3 = fmaf(p.gamma[n + 3], o[q * 4 + 3] + p.b2[n + 3], __uint_as_float(rq[q].w));
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((q ^ (r & 7)) << 4)), "f"(y0), "f"(y1), "f"(y2), "f"(y3) : "memory");
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int c = wg + 2 * i;
-                    tma_store_2d(&p.tmX, sHs + c * 16384 + quarter * 4096, c * 32, (tile * 2 + crank) * 128 + quarter * 32);
-                }
+                tma_store_2d(&p.tmX, sHs + sub * 16384 + quarter * 4096, sub * 32, (tile * 2 + crank) * 128 + quarter * 32);
                 tma_store_commit();
             }
         }

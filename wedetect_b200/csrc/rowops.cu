@@ -8,6 +8,7 @@
 #include <functional>
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 namespace wd {
 
@@ -173,9 +174,88 @@ __global__ void __launch_bounds__(256) ln_rows_multi_kernel(const float* __restr
     }
 }
 
+// Narrow rows (C <= 256): a row is shared by LPR lanes holding NV float4 each, a warp works on 32 / LPR rows at a time.
+// The one-warp-per-row mapping spends ~65 instructions per 16 bytes on the two 5-step warp reductions (ncu: 2.9 IPC, 48 %
+// of DRAM bandwidth at C = 128: issue bound); here a reduction is log2(LPR) steps over 4x the data per lane, the weights
+// stay in registers across the grid-stride loop over rows, and the kernel goes back to being HBM bound.
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256) ln_rows_group_kernel(const float* __restrict__ in, int rows, int C, int ld_in, const float* __restrict__ w,
+                                                            const float* __restrict__ b, float eps, __nv_bfloat16* out_hi, long long out_ps,
+                                                            float* out_f32, int ld_out, int s2d, int W, int H) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane % LPR, rw = lane / LPR;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (long long)gridDim.x * (blockDim.x >> 5);
+    float4 ww[NV], bb[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * LPR + sub) * 4;
+        ww[i] = bb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C) {
+            ww[i] = __ldg(reinterpret_cast<const float4*>(w + c));
+            bb[i] = __ldg(reinterpret_cast<const float4*>(b + c));
+        }
+    }
+    const float inv_c = 1.f / (float)C;
+    for (long long base = gw * RPW; base < rows; base += nw * RPW) {   // warp-uniform bound: every lane reaches the shuffles
+        const long long row = base + rw;
+        const bool ok = row < rows;
+        float4 v[NV];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * LPR + sub) * 4;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && c < C) v[i] = *reinterpret_cast<const float4*>(in + row * ld_in + c);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * inv_c;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * LPR + sub) * 4;
+            if (c < C) {
+                const float a = v[i].x - mean, bq = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+                sq += (a * a + bq * bq) + (cc * cc + d * d);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = 1.f / sqrtf(sq * inv_c + eps);
+        if (!ok) continue;
+        long long orow = row;
+        int coff = 0;
+        if (s2d) {
+            const int xx = (int)(row % W), yy = (int)((row / W) % H), bi = (int)(row / ((long long)W * H));
+            orow = ((long long)bi * (H / 2) + yy / 2) * (W / 2) + xx / 2;
+            coff = ((yy & 1) * 2 + (xx & 1)) * C;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * LPR + sub) * 4;
+            if (c >= C) continue;
+            const float y0 = (v[i].x - mean) * rstd * ww[i].x + bb[i].x, y1 = (v[i].y - mean) * rstd * ww[i].y + bb[i].y;
+            const float y2 = (v[i].z - mean) * rstd * ww[i].z + bb[i].z, y3 = (v[i].w - mean) * rstd * ww[i].w + bb[i].w;
+            if (out_hi) store_bf16x4(out_hi, out_ps, orow * ld_out + coff + c, y0, y1, y2, y3);
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c) = make_float4(y0, y1, y2, y3);
+        }
+    }
+}
+
 static void launch_ln_rows(cudaStream_t s, const float* in, int rows, int C, int ld_in, const float* w, const float* b, float eps, __nv_bfloat16* oh,
                            long long ol, float* of, int ld_out, int s2d, int W, int H) {
-    if (C <= 128) {
+    static const bool grouped = getenv("WD_LN_NO_GROUP") == nullptr;   // A/B switch
+    if (grouped && C <= 256) {
+        // 8 lanes x 4 float4 (C <= 128) or 16 lanes x 4 float4 (C <= 256) per row; grid-stride so the weights load once per warp
+        const int rpw = C <= 128 ? 4 : 2;
+        const long long groups = ((long long)rows + rpw - 1) / rpw;
+        const int blocks = (int)std::min<long long>((groups + 7) / 8, (long long)device_sm_count() * 16);
+        if (C <= 128) launch_pdl(ln_rows_group_kernel<8, 4>, dim3(blocks), dim3(256), (size_t)(0), s, 1, in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+        else launch_pdl(ln_rows_group_kernel<16, 4>, dim3(blocks), dim3(256), (size_t)(0), s, 1, in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
+    } else if (C <= 128) {
         const int warps = (rows + 3) / 4;
         launch_pdl(ln_rows_multi_kernel<1, 4>, dim3((warps + 7) / 8), dim3(256), (size_t)(0), s, 1, in, rows, C, ld_in, w, b, eps, oh, ol, of, ld_out, s2d, W, H);
     } else if (C <= 256) {
