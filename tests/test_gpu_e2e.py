@@ -129,10 +129,11 @@ def test_e2e_precise_north_star(size, K, uni, B, res, max_per_img):
             assert float((det["embeddings"][b, :n] - want).abs().max()) <= 1e-2
 
 
-def test_cuda_graph_replay_matches_eager():
+@pytest.mark.parametrize("size", ["tiny", "base"])     # base: the plan contains the cluster-launched fused block-MLP kernel
+def test_cuda_graph_replay_matches_eager(size):
     from oracle import synth
     from wedetect_b200 import plan, schema, weights
-    size, B, H, W, K = "tiny", 2, 320, 320, 16
+    B, H, W, K = 2, 320, 320, 16
     sd = synth.synth_state_dict(size, seed=3, with_text=False, regime="sparse")
     Wt = weights.prepare_vision(sd, size, D)
     p = plan.VisionPlan(Wt, size, B, H, W, K=K)
