@@ -132,3 +132,24 @@ def test_packed_batch_drives_kernel_model_to_oracle_result():
         assert (got[len(imgs)] == 114).all()            # unused slot: padding only
     with pytest.raises(ValueError):                     # the reference fails too (PIL: height and width must be > 0)
         pack_batch([np.zeros((400, 3, 3), dtype=np.uint8)], 32, 32)
+
+
+def test_decode_images_accepts_paths_pil_and_arrays(tmp_path):
+    """Host-side input handling of SimpleYOLOWorldDetector.forward (generate_proposal.py:1087-1092): paths are opened and
+    converted to RGB, PIL images of any mode become RGB, arrays pass through; order is kept by the thread pool."""
+    from PIL import Image
+    from wedetect_b200.preprocess import decode_images
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    p_png, p_jpg = str(tmp_path / "a.png"), str(tmp_path / "b.jpg")
+    Image.fromarray(a).save(p_png)
+    Image.fromarray(a).save(p_jpg, quality=90)
+    gray = Image.fromarray(a[..., 0], mode="L")
+    rgba = Image.fromarray(np.dstack([a, a[..., :1]]), mode="RGBA")
+    out = decode_images([p_png, p_jpg, gray, rgba, a, tmp_path / "a.png"])
+    assert [o.shape for o in out] == [(37, 53, 3)] * 6 and all(o.dtype == np.uint8 for o in out)
+    assert np.array_equal(out[0], a) and np.array_equal(out[4], a) and np.array_equal(out[5], a)
+    assert np.array_equal(out[1], np.asarray(Image.open(p_jpg).convert("RGB")))
+    assert np.array_equal(out[2], np.asarray(gray.convert("RGB"))) and np.array_equal(out[3], np.asarray(rgba.convert("RGB")))
+    with pytest.raises(TypeError):
+        decode_images([np.zeros((4, 4), dtype=np.uint8), a])

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib as L
 from . import plan, schema, weights
-from .preprocess import Letterbox, letterbox_params  # noqa: F401
+from .preprocess import Letterbox, decode_images, letterbox_params  # noqa: F401
 from .structures import DetDataSample, InstanceData
 
 _DEF_TEST_CFG = dict(multi_label=True, nms_pre=30000, score_thr=0.001, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300)
@@ -297,14 +297,7 @@ class SimpleYOLOWorldDetector:
     def forward(self, image_paths, rescale=True):
         """image_paths: list of file names, PIL images or uint8 [h,w,3] RGB arrays (generate_proposal.py:1082-1117).
         Decoding stays with PIL; the letterbox (BILINEAR resize + 114 padding) runs on the device, bit-exact with PIL."""
-        from PIL import Image
-        arrays = []
-        for ip in image_paths:
-            if isinstance(ip, str):
-                ip = Image.open(ip).convert("RGB")
-            if isinstance(ip, Image.Image):
-                ip = np.asarray(ip if ip.mode == "RGB" else ip.convert("RGB"))
-            arrays.append(ip)
+        arrays = decode_images(image_paths)
         B, (H, W) = len(arrays), self.img_size
         key = (B, H, W, torch.uint8)
         p = self._plan(*key)

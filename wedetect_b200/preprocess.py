@@ -72,6 +72,29 @@ def _pool():
     return _POOL
 
 
+def load_rgb(item):
+    """One input of SimpleYOLOWorldDetector.forward -> uint8 [h, w, 3] RGB: a file name is opened and converted to RGB
+    (generate_proposal.py:1089-1090), a PIL image is taken as is (converted if it is not RGB), an array is passed through."""
+    from PIL import Image
+    if isinstance(item, (str, bytes)) or hasattr(item, "__fspath__"):
+        item = Image.open(item).convert("RGB")
+    if isinstance(item, Image.Image):
+        item = np.asarray(item if item.mode == "RGB" else item.convert("RGB"))
+    item = np.asarray(item)
+    if item.dtype != np.uint8 or item.ndim != 3 or item.shape[2] != 3:
+        raise TypeError(f"expected a file name, a PIL image or a uint8 [h, w, 3] RGB array, got {item.dtype} {item.shape}")
+    return item
+
+
+def decode_images(items):
+    """Decode a batch on the host thread pool (PIL releases the GIL while decoding): at >1000 images/s per GPU a serial
+    decode loop would be the bottleneck of the Uni entry points."""
+    items = list(items)
+    if len(items) <= 1:
+        return [load_rgb(it) for it in items]
+    return list(_pool().map(load_rgb, items))
+
+
 def pack_batch(images, H, W, with_src=True):
     """Host side of WD_OP_LETTERBOX for one batch: geometry + PIL tables per image, packed the way the kernels read them.
     Returns dict(desc int32 [n,16], coef int32 [...], src_parts [(byte offset, flat uint8 view)], src_bytes, tmp_bytes,
