@@ -35,6 +35,8 @@ class InstanceData:
         return 0
 
     def __getitem__(self, idx):
+        if isinstance(idx, str):          # mmengine's InstanceData also answers field names (infer_wedetect.py:126-128: pred_instances['bboxes'])
+            return self._fields[idx]
         return InstanceData(**{k: v[idx] for k, v in self._fields.items()})
 
     def _map(self, fn):
