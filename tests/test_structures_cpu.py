@@ -28,3 +28,25 @@ def test_infer_tail_on_instance_data():
     assert isinstance(xyxy, np.ndarray) and xyxy.shape == (len(want), 4) and class_id.dtype == np.int64
     assert np.array_equal(confidence, want.numpy()) and len(pred_instances) == len(want)
     assert "bboxes" in pred_instances and sorted(pred_instances.keys()) == ["bboxes", "labels", "scores"]
+
+
+def test_instances_for_picks_the_sample_flavour(monkeypatch):
+    """Real mmdet samples type-check `pred_instances`: they get mmengine's InstanceData, ours get ours."""
+    import sys
+    import types
+    from wedetect_b200.structures import DetDataSample, InstanceData, instances_for
+    ours = instances_for(DetDataSample(), scores=torch.zeros(2))
+    assert isinstance(ours, InstanceData) and isinstance(instances_for(None, scores=torch.zeros(1)), InstanceData)
+    # a stand-in for mmengine (not installable offline): the function must import and use ITS class for mmdet-typed samples
+    fake = types.ModuleType("mmengine.structures")
+
+    class MMInstanceData(dict):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+    fake.InstanceData = MMInstanceData
+    monkeypatch.setitem(sys.modules, "mmengine", types.ModuleType("mmengine"))
+    monkeypatch.setitem(sys.modules, "mmengine.structures", fake)
+    MMSample = type("DetDataSample", (), {})
+    MMSample.__module__ = "mmdet.structures.det_data_sample"
+    got = instances_for(MMSample(), scores=torch.ones(3))
+    assert isinstance(got, MMInstanceData) and got["scores"].shape == (3,)

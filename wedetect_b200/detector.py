@@ -18,7 +18,7 @@ import torch
 from . import _lib as L
 from . import plan, schema, weights
 from .preprocess import Letterbox, decode_images, letterbox_params  # noqa: F401
-from .structures import DetDataSample, InstanceData
+from .structures import DetDataSample, InstanceData, instances_for  # noqa: F401
 
 _DEF_TEST_CFG = dict(multi_label=True, nms_pre=30000, score_thr=0.001, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300)
 
@@ -190,9 +190,8 @@ class YOLOWorldDetector:
         out = []
         for b in range(B):
             n = counts[b]
-            inst = InstanceData(bboxes=r["boxes"][b, :n], scores=r["scores"][b, :n], labels=labels64[b, :n])
             s = batch_data_samples[b] if batch_data_samples else DetDataSample()
-            s.pred_instances = inst
+            s.pred_instances = instances_for(s, bboxes=r["boxes"][b, :n], scores=r["scores"][b, :n], labels=labels64[b, :n])
             out.append(s)
         return out
 

@@ -3,7 +3,8 @@
 Only the surface that the reference's entry points touch (infer_wedetect.py:113-126): attribute access,
 boolean / index `__getitem__` applied to every field, `.cpu()`, `.numpy()`, `len()`; a data sample exposes
 its metainfo keys as attributes (yolo_world.py:94 relies on `hasattr(sample, 'texts')`).
-If the real mmengine is installed the detector converts to the real classes instead (api.to_mm_samples).
+When the caller hands in real mmdet / mmengine samples (the unchanged mmcv test pipeline produces them), predictions are
+attached as real `mmengine.structures.InstanceData` (`instances_for`), because `DetDataSample.pred_instances` type-checks.
 """
 import torch
 
@@ -84,3 +85,12 @@ class DetDataSample:
             return getattr(self, k)
         except AttributeError:
             return default
+
+
+def instances_for(sample, **fields):
+    """InstanceData of the flavour `sample` expects: mmengine's own class for real mmdet / mmengine samples, ours otherwise."""
+    mod = type(sample).__module__ if sample is not None else ""
+    if mod.startswith(("mmdet", "mmengine")):
+        from mmengine.structures import InstanceData as MMInstanceData
+        return MMInstanceData(**fields)
+    return InstanceData(**fields)
