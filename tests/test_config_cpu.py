@@ -75,3 +75,20 @@ def test_init_detector_needs_the_gpu_library_loudly(tmp_path):
     bad = _write(tmp_path, "d.py", "model = dict(type='SomethingElse')\n")
     with pytest.raises(NotImplementedError):
         init_detector(bad)
+
+
+def test_text_state_dict_slicing():
+    """Checkpoint handling of the standalone text tower facade (extract_embedding.py:1293-1303): mmengine checkpoint, full
+    state dict and the already sliced `model.* / head.*` layout give the same `backbone.text_model.*` slice."""
+    import torch
+    from oracle import synth
+    from wedetect_b200 import schema
+    sd = synth.synth_state_dict("tiny", seed=0, with_text=True, text_vocab=64, calibrate=False)
+    a = schema.text_state_dict({"state_dict": sd, "meta": {}})
+    b = schema.text_state_dict(sd)
+    c = schema.text_state_dict({k[len("backbone.text_model."):]: v for k, v in sd.items() if k.startswith("backbone.text_model.")})
+    assert a.keys() == b.keys() == c.keys() and all(k.startswith("backbone.text_model.") for k in a)
+    assert all(torch.equal(a[k], c[k]) for k in a) and len(a) > 100
+    assert schema.text_size_of(a) == "base"
+    with pytest.raises(KeyError):
+        schema.text_state_dict({"neck.x": torch.zeros(1)})

@@ -66,3 +66,33 @@ def test_plan_builds_for_all_sizes_on_cpu(monkeypatch):
         for op in p.ops:
             if op.kind == L.OP_GEMM:
                 assert op.i[30] == (3 if precise else 1) and op.i[6] % 64 == 0 and op.i[8] % 8 == 0
+
+
+def test_standalone_text_tower_facade_wires_on_cpu(monkeypatch):
+    """XLMRobertaLanguageBackbone (extract_embedding.py:1267-1320 facade): checkpoint slicing, plan per (S, L), un-normalised head
+    output vs normalised features - with the library calls stubbed out (no kernels run on the CPU)."""
+    import wedetect_b200._lib as L
+    from oracle import synth
+
+    class FakeProg:
+        def __init__(self, ops_, keepalive=()):
+            self.ops = ops_
+
+        def run(self, s):
+            pass
+
+    monkeypatch.setattr(L, "Program", FakeProg)
+    monkeypatch.setattr(L, "load", lambda require_gpu=True: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda: types.SimpleNamespace(cuda_stream=0))
+    from wedetect_b200.detector import XLMRobertaLanguageBackbone
+    sd = synth.synth_state_dict("tiny", seed=0, with_text=True, text_vocab=64, calibrate=False)
+    tok = lambda text, return_tensors, padding: dict(input_ids=torch.tensor([[0, 5, 6, 2], [0, 7, 2, 1]]), attention_mask=torch.tensor([[1, 1, 1, 1], [1, 1, 1, 0]]))
+    m = XLMRobertaLanguageBackbone({"state_dict": sd}, tokenizer=tok, device="cpu").cuda().eval()
+    assert m.text == "base" and m.language_dim == 768
+    out = m(["a", "b"])
+    assert out.shape == (2, 768) and out.dtype == torch.float32
+    tp = m._plans[(2, 4)]
+    assert out.data_ptr() != tp.head_out.data_ptr()                          # a copy, the plan's buffers are reused per call
+    kinds = [op.kind for op in tp.program.ops]
+    assert kinds[0] == L.OP_TEXT_EMBED and kinds[-1] == L.OP_L2NORM_ROWS and kinds.count(L.OP_ATTN_SMALL) == 12
+    assert m.encode_tokens(torch.zeros(2, 4, dtype=torch.long), torch.ones(2, 4, dtype=torch.long), normalize=True).shape == (2, 768)

@@ -10,7 +10,7 @@ See INTEGRATION.md for the exact diffs.
 import torch
 
 from .config import Config, parse_cfg_options  # noqa: F401
-from .detector import SimpleYOLOWorldDetector, YOLOWorldDetector  # noqa: F401
+from .detector import SimpleYOLOWorldDetector, XLMRobertaLanguageBackbone, YOLOWorldDetector  # noqa: F401
 from .retrieval import (RetrievalScorer, evaluate_retrieval_per_class, extract_corpus, predictions_from_scores,  # noqa: F401
                         save_corpus, score_saved)
 from .structures import DetDataSample, InstanceData  # noqa: F401

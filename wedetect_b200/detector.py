@@ -322,3 +322,57 @@ class SimpleYOLOWorldDetector:
                                  scale=r["scales"], bias=r["bias"], counts=r["counts"])
             self._scorers = {key: (sc, text_embedding)}      # one live text set at a time (keeps the id() key valid)
         return self._scorers[key][0].run()
+
+
+class XLMRobertaLanguageBackbone:
+    """Standalone text tower facade (eval_retrieval/extract_embedding.py:1267-1320): `forward(List[str]) -> [n, 768]`, the
+    CLS token through the 768-d head, NOT normalised (the script normalises afterwards, :1713).  `ckpt` is a checkpoint path
+    (an mmengine `.pth` with 'state_dict'), or a state dict / its text slice.  The tokenizer comes from `model_name` (the
+    reference reads ../xlm-roberta-{base,large}/) unless one is passed in."""
+
+    def __init__(self, ckpt, *, model_name=None, tokenizer=None, device="cuda:0", precise=False):
+        L.load(require_gpu=True)
+        sd = torch.load(ckpt, map_location="cpu", weights_only=False) if isinstance(ckpt, (str, os.PathLike)) else ckpt
+        sd = schema.text_state_dict(sd)
+        self.text = schema.text_size_of(sd)                         # 'base' | 'large'
+        self.size = next(k for k, v in schema.SIZES.items() if v["text"] == self.text)
+        need = {k: v for k, v in schema.param_shapes(self.size, with_text=True).items() if k.startswith("backbone.text_model.")}
+        missing = [k for k in need if k not in sd]
+        bad = [k for k in need if k in sd and tuple(sd[k].shape) != tuple(need[k])
+               and not k.endswith("word_embeddings.weight")]        # vocabulary size is the checkpoint's
+        if missing or bad:
+            raise RuntimeError(f"text tower checkpoint: missing {missing[:3]} ({len(missing)}), size mismatch {bad[:3]}")
+        self.device, self.precise = torch.device(device), precise
+        self._sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+        self._tw, self._plans = None, {}
+        self._tokenizer, self._model_name = tokenizer, model_name or f"./xlm-roberta-{self.text}/"
+        self.language_dim = schema.TEXT[self.text]["hidden"]
+
+    def cuda(self):
+        return self
+
+    def eval(self):
+        return self
+
+    @property
+    def tokenizer(self):
+        if self._tokenizer is None:
+            from transformers import AutoTokenizer
+            self._tokenizer = AutoTokenizer.from_pretrained(self._model_name)
+        return self._tokenizer
+
+    def encode_tokens(self, ids, mask, normalize=False):
+        if self._tw is None:
+            self._tw = weights.prepare_text(self._sd, self.size, self.device, precise=self.precise)
+        key = tuple(ids.shape)
+        if key not in self._plans:
+            self._plans[key] = plan.TextPlan(self._tw, self.size, key[0], key[1], device=self.device)
+        tp = self._plans[key]
+        feats = tp.run(ids.to(self.device, torch.int32), mask.to(self.device, torch.int32))
+        return (feats if normalize else tp.head_out).clone()
+
+    def forward(self, text):
+        tok = self.tokenizer(text=list(text), return_tensors="pt", padding=True)
+        return self.encode_tokens(tok["input_ids"], tok["attention_mask"])
+
+    __call__ = forward

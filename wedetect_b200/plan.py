@@ -353,6 +353,7 @@ class TextPlan:
         qkv = torch.zeros(T, 3 * H, dtype=F32, device=dev)
         xb, att, hid, cls = bf(T, H), bf(T, H), bf(T, I), bf(S, H)
         ho = torch.zeros(S, schema.EMBED_DIM, dtype=F32, device=dev)
+        self.head_out = ho     # CLS -> Linear output before the L2 norm (what extract_embedding.py's standalone text tower returns)
         self.feats = torch.zeros(S, schema.EMBED_DIM, dtype=F32, device=dev)
         self._keep = [x, y, qkv, xb, att, hid, cls, ho, weights]
         o = []

@@ -194,3 +194,29 @@ def normalize_state_dict(sd):
 
 def level_hw(img_h, img_w):
     return [(img_h // s, img_w // s) for s in STRIDES]
+
+
+def text_state_dict(sd):
+    """The text-tower slice of a WeDetect checkpoint, keyed like the full model (`backbone.text_model.*`).  Accepts an
+    mmengine checkpoint ({'state_dict': ...}), a full state dict, or the slice the reference's standalone text tower loads
+    (`model.*` / `head.*`, eval_retrieval/extract_embedding.py:1293-1303)."""
+    if isinstance(sd, dict) and "state_dict" in sd and isinstance(sd["state_dict"], dict):
+        sd = sd["state_dict"]
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("backbone.text_model."):
+            out[k] = v
+        elif k.startswith(("model.", "head.")):
+            out["backbone.text_model." + k] = v
+    if not out:
+        raise KeyError("no text-tower tensors (backbone.text_model.* or model.* / head.*) in the checkpoint")
+    return out
+
+
+def text_size_of(sd):
+    """'base' / 'large' from the hidden width of the head Linear (768 -> 768 or 1024 -> 768)."""
+    w = sd["backbone.text_model.head.weight"]
+    for name, t in TEXT.items():
+        if t["hidden"] == w.shape[1]:
+            return name
+    raise ValueError(f"unknown text tower width {tuple(w.shape)}")
