@@ -1,5 +1,6 @@
 """The reference's inference tail (infer_wedetect.py:113-128) runs unchanged on our InstanceData / DetDataSample stand-ins."""
 import numpy as np
+import pytest
 import torch
 
 
@@ -50,3 +51,69 @@ def test_instances_for_picks_the_sample_flavour(monkeypatch):
     MMSample.__module__ = "mmdet.structures.det_data_sample"
     got = instances_for(MMSample(), scores=torch.ones(3))
     assert isinstance(got, MMInstanceData) and got["scores"].shape == (3,)
+
+
+def test_resolve_texts_branches():
+    """The text-source branches of YOLOWorldDetector.extract_feat (yolo_world.py:84-100) as a pure function."""
+    from wedetect_b200.detector import resolve_texts
+    from wedetect_b200.structures import DetDataSample
+    infer_style = [["person"], ["dog"], [" "]]                      # infer_wedetect.py:163-167
+    assert resolve_texts(None) is None and resolve_texts([]) is None and resolve_texts({}) is None
+    assert resolve_texts([DetDataSample(dict(ori_shape=(4, 4)))]) is None                      # no texts: cached features
+    assert resolve_texts([DetDataSample(dict(texts=infer_style))] * 2) == ["person", "dog", " "]
+    assert resolve_texts(dict(texts=[["a", "b"], ["a", "b"]])) == ["a", "b"]                   # dict form, one list per image
+    assert resolve_texts(dict(texts=["a", "b"])) == ["a", "b"]                                 # dict form, one shared list
+    with pytest.raises(NotImplementedError):
+        resolve_texts([DetDataSample(dict(texts=["a"])), DetDataSample(dict(texts=["b"]))])
+
+
+def test_predict_host_logic_with_a_stub_plan(monkeypatch):
+    """YOLOWorldDetector.predict around a stubbed plan: text source, rescale metadata (pad / scale_factor before NMS, clamp to
+    ori_shape: yolo_world_head.py:728-746), unchanged-metadata caching, per-image slicing by counts, int64 labels."""
+    import wedetect_b200._lib as L
+    from wedetect_b200 import detector as det
+    from wedetect_b200.structures import DetDataSample
+    monkeypatch.setattr(L, "load", lambda require_gpu=True: None)
+    B, H, W = 2, 64, 96
+
+    class StubPlan:
+        def __init__(self):
+            self.image = torch.zeros(B, 3, H, W, dtype=torch.uint8)
+            self.meta_calls, self.text_calls, self._graph, self._text_key = [], 0, False, None
+
+        def set_text(self, f):
+            self.text_calls += 1
+            self.K = f.shape[0]
+
+        def set_meta(self, m, c):
+            self.meta_calls.append((m.clone(), c.clone()))
+
+        def run(self):
+            pass
+
+        def results(self):
+            return dict(boxes=torch.arange(B * 5 * 4, dtype=torch.float32).reshape(B, 5, 4), scores=torch.rand(B, 5), labels=torch.ones(B, 5, dtype=torch.int32),
+                        anchors=torch.zeros(B, 5, dtype=torch.int32), counts=torch.tensor([3, 0], dtype=torch.int32))
+
+    m = det.YOLOWorldDetector(size="tiny", device="cpu", cuda_graph=False)
+    m._sd = {}
+    stub = StubPlan()
+    monkeypatch.setattr(m, "_plan", lambda *a: stub)
+    imgs = torch.zeros(B, 3, H, W, dtype=torch.uint8)
+    samples = [DetDataSample(dict(ori_shape=(50, 80), scale_factor=(1.2, 1.2), pad_param=(7.0, 7.0, 8.0, 8.0))), DetDataSample(dict(ori_shape=(64, 96)))]
+    with pytest.raises(TypeError):
+        m.predict(imgs, samples)                                             # neither texts nor reparameterized features
+    m.set_text_features(torch.randn(4, 768))
+    out = m.test_step(dict(inputs=imgs, data_samples=samples))
+    assert stub.text_calls == 1 and stub.K == 4
+    meta, clamp = stub.meta_calls[-1]
+    assert meta[0].tolist() == pytest.approx([8.0, 7.0, 1.2, 1.2, 0.0, 0.0, 1.0, 0.0]) and meta[1].tolist() == [0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 1.0, 0.0]
+    assert clamp.tolist() == [[80.0, 50.0], [96.0, 64.0]]
+    assert [len(s.pred_instances) for s in out] == [3, 0] and out[0].pred_instances.labels.dtype == torch.int64
+    assert out[0] is samples[0] and out[0].pred_instances.bboxes.shape == (3, 4)
+    m.predict(imgs, samples)                                                  # same text set, same metadata: nothing re-uploaded
+    assert stub.text_calls == 1 and len(stub.meta_calls) == 1
+    m.predict(imgs, samples, rescale=False)                                   # rescale off: identity pre-NMS mapping, clamp kept
+    assert stub.meta_calls[-1][0][0].tolist() == [0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 1.0, 0.0] and len(stub.meta_calls) == 2
+    out = m.predict(imgs, None)                                               # no samples at all: fresh DetDataSample per image
+    assert len(out) == B and len(out[0].pred_instances) == 3

@@ -27,6 +27,33 @@ def _size_from_cfg(model_cfg):
     return model_cfg["backbone"]["image_model"]["model_name"]
 
 
+def resolve_texts(batch_data_samples):
+    """The class prompts a batch carries, as one flat list of strings, or None when the caller relies on `reparameterize`.
+    Mirrors the branches of YOLOWorldDetector.extract_feat (yolo_world.py:84-100): None -> cached features; a dict with
+    'texts'; a list of samples with a `texts` attribute (one prompt list per image: they must agree inside a batch, the
+    similarity matrix is folded once per step).  Prompts may be strings or single-element lists (infer_wedetect.py:163-167)."""
+    if batch_data_samples is None:
+        return None
+    if isinstance(batch_data_samples, dict):
+        if "texts" not in batch_data_samples:
+            return None
+        texts = batch_data_samples["texts"]
+    elif isinstance(batch_data_samples, (list, tuple)) and len(batch_data_samples) and _sample_texts(batch_data_samples[0]) is not None:
+        texts = [_sample_texts(s) for s in batch_data_samples]
+    else:
+        return None
+    if texts and isinstance(texts[0], str):
+        texts = [texts]                        # a single prompt list for the whole batch
+    if any(t != texts[0] for t in texts):
+        raise NotImplementedError("per-image text sets that differ inside one batch are not supported")
+    return [t[0] if isinstance(t, (list, tuple)) else t for t in texts[0]]
+
+
+def _sample_texts(s):
+    get = getattr(s, "get", None)
+    return get("texts") if callable(get) else getattr(s, "texts", None)
+
+
 class YOLOWorldDetector:
     """Text-conditioned detector facade.  `model_cfg` is the `model=` dict of config/wedetect_*.py."""
 
@@ -143,12 +170,11 @@ class YOLOWorldDetector:
         if isinstance(batch_inputs, (list, tuple)):
             batch_inputs = torch.stack(list(batch_inputs))
         B, _, H, W = batch_inputs.shape
-        # text features: per-sample `texts` metainfo wins (yolo_world.py:94-96), else the reparameterized cache
-        if isinstance(batch_data_samples, list) and batch_data_samples and batch_data_samples[0].get("texts") is not None:
-            texts = [s.texts for s in batch_data_samples]
-            if any(t != texts[0] for t in texts):
-                raise NotImplementedError("per-image text sets that differ inside one batch are not supported")
-            flat = [t[0] if isinstance(t, (list, tuple)) else t for t in texts[0]]
+        # text features: texts carried by the samples win (yolo_world.py:88-96), else the reparameterized cache
+        flat = resolve_texts(batch_data_samples)
+        if isinstance(batch_data_samples, dict):
+            batch_data_samples = None          # the dict form carries texts only: no per-image metainfo
+        if flat is not None:
             feats = self.forward_text([flat])
         elif self.text_feats is not None:
             feats = self.text_feats
