@@ -100,3 +100,72 @@ def test_retrieval_metric_restatement():
     assert res["a"] == dict(precision=0.5, recall=1.0, f1=0.6667, support=1, n_pred=2)
     assert res["b"] == dict(precision=1.0, recall=0.6667, f1=0.8, support=3, n_pred=2)
     assert "c" not in res and res["d"]["recall"] == 0.0
+
+
+class _FakeExtractModel:
+    """Stands in for SimpleYOLOWorldDetector(extract=True) in the corpus loop: proposals / scores derived from the image's
+    first pixel so that order, padding of the last batch and per-image counts can be checked on the CPU."""
+    extract, num_proposals, device = True, 4, torch.device("cpu")
+
+    def forward_tensor(self, batch):
+        B = batch.shape[0]
+        v = batch[:, 0, 0, 0]                                        # image "id"
+        cnt = (v.long() % 5).clamp(max=4).int()                      # 0..4 proposals
+        emb = v[:, None, None].expand(B, 4, 768).clone()
+        self.last_batch_result = dict(embeddings=emb, scales=torch.full((B, 4), -1.0), bias=v[:, None].expand(B, 4).clone(), counts=cnt)
+        self.calls = getattr(self, "calls", 0) + 1
+
+    def score_text(self, text):
+        r = self.last_batch_result
+        return r["embeddings"][:, 0, :1] * torch.ones(1, text.shape[0])
+
+
+def test_extract_corpus_host_loop_single_process():
+    """extract_embedding.py:1718-1774 loop: batches of 3 over 7 images (last batch padded), .pth payload layout, scores rows."""
+    from wedetect_b200.retrieval import extract_corpus, predictions_from_scores
+    N = 7
+    imgs = torch.zeros(N, 3, 8, 8)
+    imgs[:, 0, 0, 0] = torch.arange(10, 10 + N).float()
+    text = torch.randn(5, 768)
+    m = _FakeExtractModel()
+    out = extract_corpus(m, imgs, list(range(100, 100 + N)), batch_size=3, text_embedding=text)
+    assert m.calls == 3 and out["image_ids"].tolist() == list(range(100, 107)) and out["scores"].shape == (N, 5)
+    assert out["scores"][:, 0].tolist() == [float(v) for v in range(10, 17)]
+    for i, it in enumerate(out["image_embedding"]):
+        n = (10 + i) % 5
+        assert it["image_id"] == 100 + i and it["embedding"].shape == (n, 768) and it["scale"].shape == (n,) and it["bias"].shape == (n,)
+        if n:
+            assert float(it["embedding"][0, 0]) == 10 + i and float(it["bias"][0]) == 10 + i and float(it["scale"][0]) == -1.0
+    assert out["text_embedding"] is text
+    light = extract_corpus(m, imgs, list(range(N)), batch_size=4, text_embedding=text, keep_embeddings=False)
+    assert "image_embedding" not in light and light["scores"].shape == (N, 5)
+    pred = predictions_from_scores(out["scores"], out["image_ids"].tolist(), [f"c{k}" for k in range(5)], thre=12.5)
+    assert pred["c0"] == [103, 104, 105, 106]
+
+
+def _extract_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from wedetect_b200.retrieval import extract_corpus
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    N = 7
+    imgs = torch.zeros(N, 3, 8, 8)
+    imgs[:, 0, 0, 0] = torch.arange(10, 10 + N).float()
+    out = extract_corpus(_FakeExtractModel(), imgs, list(range(100, 100 + N)), batch_size=2, text_embedding=torch.ones(3, 768))
+    q.put((rank, out["scores"][:, 0].tolist(), [int(it["embedding"].shape[0]) for it in out["image_embedding"]]))
+    dist.destroy_process_group()
+
+
+def test_extract_corpus_sharded_gloo():
+    """Config 5's multi-GPU shape on CPU: 7 images over 2 ranks (shards of 4 and 3), every rank ends with the full payload in
+    image order after ONE fixed-shape all-gather per array."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_extract_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = dict((r, (s, n)) for r, s, n in (q.get(timeout=180) for _ in range(2)))
+    for p in ps:
+        p.join(timeout=60)
+    for r in range(2):
+        assert got[r][0] == [float(v) for v in range(10, 17)] and got[r][1] == [(10 + i) % 5 for i in range(7)]

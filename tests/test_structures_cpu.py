@@ -117,3 +117,42 @@ def test_predict_host_logic_with_a_stub_plan(monkeypatch):
     assert stub.meta_calls[-1][0][0].tolist() == [0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 1.0, 0.0] and len(stub.meta_calls) == 2
     out = m.predict(imgs, None)                                               # no samples at all: fresh DetDataSample per image
     assert len(out) == B and len(out[0].pred_instances) == 3
+
+
+def test_uni_forward_tensor_host_logic_with_a_stub_plan(monkeypatch):
+    """SimpleYOLOWorldDetector glue (generate_proposal.py:1103-1117): boxes -= (dw/2, dh/2), /= ratio when rescale, clamp to the
+    original size - expressed as the post-NMS metadata row; extract variant adds labels / scales / bias; result slicing."""
+    import wedetect_b200._lib as L
+    from wedetect_b200 import detector as det
+    monkeypatch.setattr(L, "load", lambda require_gpu=True: None)
+    B, H, W, P = 2, 64, 64, 6
+
+    class StubPlan:
+        def __init__(self):
+            self.image = torch.zeros(B, 3, H, W)
+            self.meta, self._graph = None, False
+
+        def set_meta(self, m, c):
+            self.meta = (m.clone(), c.clone())
+
+        def run(self):
+            pass
+
+        def results(self):
+            return dict(boxes=torch.rand(B, P, 4), scores=torch.rand(B, P), labels=torch.zeros(B, P, dtype=torch.int32), anchors=torch.zeros(B, P, dtype=torch.int32),
+                        counts=torch.tensor([P, 2], dtype=torch.int32), embeddings=torch.rand(B, P, 768), scales=torch.full((B, P), -1.0), bias=torch.zeros(B, P))
+
+    m = det.SimpleYOLOWorldDetector("base", 768, 256, P, device="cpu", extract=True, cuda_graph=False)
+    stub = StubPlan()
+    monkeypatch.setattr(m, "_plan", lambda *a: stub)
+    x = torch.rand(B, 3, H, W)
+    out = m.forward_tensor(x, ratios=[0.5, 2.0], offsets=[(0.0, 8.0), (4.5, 0.0)], ori_shapes=[(96, 128), (32, 27)])
+    meta, clamp = stub.meta
+    assert meta[0].tolist() == [0.0, 0.0, 1.0, 1.0, 0.0, 8.0, 0.5, 0.0] and meta[1].tolist() == [0.0, 0.0, 1.0, 1.0, 4.5, 0.0, 2.0, 0.0]
+    assert clamp.tolist() == [[128.0, 96.0], [27.0, 32.0]]
+    assert [len(o["scores"]) for o in out] == [P, 2] and set(out[0]) == {"bboxes", "embeddings", "scores", "labels", "scales", "bias"}
+    assert out[1]["embeddings"].shape == (2, 768) and out[1]["labels"].dtype == torch.int64
+    m.forward_tensor(x, ratios=[0.5, 2.0], offsets=[(0.0, 8.0), (4.5, 0.0)], ori_shapes=[(96, 128), (32, 27)], rescale=False)
+    assert stub.meta[0][:, 6].tolist() == [1.0, 1.0] and stub.meta[0][0, 5] == 8.0       # offsets still removed, ratio not applied
+    with pytest.raises(RuntimeError):
+        det.SimpleYOLOWorldDetector("base", 768, 256, P, device="cpu").score_text(torch.zeros(3, 768))
