@@ -5,8 +5,10 @@
  * reference function(s) whose arithmetic it replaces (paths relative to the reference checkout).
  *
  * Conventions
- *   - bf16 tensors may be "3-plane" (precise bf16x3 mode): value = p0 + p1 + p2, planes `plane_stride`
- *     elements apart starting at the given pointer; a plane stride of 0 means an ordinary bf16 tensor;
+ *   - 16-bit GEMM operands come in two formats.  Plane stride 0: one bf16 plane (the opt-in fast mode).  Plane stride
+ *     > 0 (the default, parity-grade mode): two fp16 planes `plane_stride` elements apart starting at the given pointer,
+ *     hi + lo = value * s with s a power of two: WD_ACT_PLANE_SCALE for every activation the library writes, a
+ *     per-matrix value chosen by the host for weights (undone by the GEMM's `acc_scale`);
  *   - plain C types only; all pointers in `wd_op.p[]` are DEVICE pointers owned by the caller;
  *   - every call enqueues work on the caller's `cudaStream_t` (passed as void*), never syncs;
  *   - return 0 on success, negative on failure; `wd_last_error()` returns a thread-local message;
@@ -25,9 +27,10 @@
 extern "C" {
 #endif
 
-#define WD_OP_NI 40
+#define WD_OP_NI 48
 #define WD_OP_NF 8
 #define WD_OP_NP 16
+#define WD_ACT_PLANE_SCALE 4.0f
 
 typedef struct wd_op {
     int32_t kind;          /* enum wd_op_kind */
@@ -59,10 +62,11 @@ enum wd_op_kind {
      *           tile / D extents then describe the OUTPUT map); 0 = stride 1
      *    37 no_warp_store (1: one 128-row TMA store per epilogue warpgroup instead of one 32-row store per warp; A/B switch)
      *    35 exact_act (1: erf-GELU / exp-SiLU instead of the MUFU.TANH forms used for bf16 outputs of the fast path)
-     *    30 planes (0|1 fast, 3 precise)  31 A plane stride  32 B plane stride  33 C plane stride  34 resid plane stride
-     * f: 0 resid_alpha
-     * p: 0 A (bf16)  1 B (bf16 [N, ntaps*Kc])  2 C  3 bias f32[N]  4 gamma f32[N]  5 resid
-     * out = resid*alpha + gamma * act(acc + bias)        (each term optional) */
+     *    30 planes (0|1 bf16 fast mode, 2 fp16 hi/lo)  31 A plane stride  32 B plane stride  33 C plane stride  34 resid plane stride
+     *    40 lblk (fp16 hi/lo mode: 64-wide k-blocks accumulated in TMEM before the partial sum moves to fp32 registers, 0 = 1)
+     * f: 0 resid_alpha  1 acc_scale (fp16 hi/lo mode: 1 / (A scale * B scale), 0 = 1)
+     * p: 0 A  1 B [N, ntaps*Kc]  2 C  3 bias f32[N]  4 gamma f32[N]  5 resid
+     * out = resid*alpha + gamma * act(acc * acc_scale + bias)        (each term optional) */
     WD_OP_GEMM = 1,
     /* Row LayerNorm over C (biased variance, eps inside sqrt): mm_backbone.py:145-155, F.layer_norm.
      * i: 0 rows 1 C
@@ -110,7 +114,7 @@ enum wd_op_kind {
     /* Fold BNContrastiveHead into a GEMM weight: W'[k,c] = t[k,c]/max(||t[k]||,eps) * g[c] * exp(s),
      * b'[k] = exp(s) * sum_c h[c]*tn[k,c] + bias (yolo_world_head.py:90-108; Uni variant without
      * text normalisation: generate_proposal.py:1129-1131).
-     * i: 0 K 1 C 2 normalize (0|1) 3 K_pad 30 W' plane stride
+     * i: 0 K 1 C 2 normalize (0|1) 3 K_pad 30 W' plane stride    f: 0 power-of-two scale of W' (fp16 hi/lo planes; 0 = 1)
      * p: 0 text f32[K,C] 1 bn_g f32[C] 2 bn_h f32[C] 3 logit_scale f32[1] 4 bias f32[1]
      *    5 W' bf16 [K_pad,C]  6 b' f32[K_pad] */
     WD_OP_FOLD_TEXT = 11,
@@ -200,6 +204,8 @@ typedef struct wd_pp_params {
 /* ---- library-level ---------------------------------------------------------------------- */
 const char* wd_last_error(void);
 int wd_version(void);
+/* WD_ACT_PLANE_SCALE the library was built with (host mirrors must agree). */
+float wd_act_plane_scale(void);
 /* number of CUDA kernels launched by this library in this process (bench `gpu_launches`). */
 uint64_t wd_launch_count(void);
 /* device query: returns 0 and fills sm count / cc; fails loudly (negative) without a GPU. */

@@ -177,8 +177,58 @@ def test_dfl_epilogue():
     report_close("dfl", C, R.dfl_ref(A, Wt, bias), rtol=1e-4, atol=1e-4)
 
 
+def test_dfl_epilogue_split():
+    """DFL (softmax over 16 bins x 4 sides, expectation) in the fp16 hi/lo kernel: K = 64 and a long-K case (several blocks)."""
+    from wedetect_b200 import ops
+    from wedetect_b200.ops import P3
+    d = _dev()
+    for M, K in ((1111, 64), (300, 576)):
+        g = torch.Generator().manual_seed(26)
+        A, Wt, bias = torch.randn(M, K, generator=g), torch.randn(64, K, generator=g) * 0.3 / (K / 64) ** 0.5, torch.randn(64, generator=g)
+        C = torch.zeros(M, 4, dtype=torch.float32, device=d)
+        _run(ops.linear(P3.from_f32(A, d, scale=ops.ACT_SCALE), P3.from_f32(Wt, d), C, bias=bias.to(d), dfl=True))
+        z = (A.double() @ Wt.double().t() + bias.double()).view(-1, 4, 16).softmax(-1)
+        ref = (z * torch.arange(16, dtype=torch.float64)).sum(-1).float()
+        report_close(f"dfl split K={K}", C, ref, rtol=2e-6, atol=5e-6)
+
+
+SPLIT_SHAPES = [
+    (515, 256, 192, None),        # 5 m-tiles: pairs + ghost tile, BN=256 (N tail 192)
+    (128, 192, 80, None),         # one m-tile: non-pair BN=128, ragged N, K tail
+    (100, 64, 64, None),          # BN=64 (single active epilogue warpgroup)
+    (128 * 41, 512, 512, None),   # pair BN=256, many tiles per CTA pair (barrier phases wrap), odd m-tiles
+    (128 * 300, 128, 128, None),  # pair BN=128, many tiles per CTA
+    (640, 2048, 512, None),       # long K: 32 register-accumulated blocks
+    (128 * 9, 4096, 1024, None),  # K = 4096 (ConvNeXt stage-3 pw2 shape)
+    (1000, 768, 1208, None),      # similarity-like: N tail in the last 256 tile
+    (384, 320, 256, 128),         # forced BN=128 pair with 2 n-tiles
+]
+
+
+@pytest.mark.parametrize("lblk", [1, 2, 1000])
+@pytest.mark.parametrize("M,K,N,block_n", SPLIT_SHAPES)
+def test_linear_split_shapes(M, K, N, block_n, lblk):
+    """fp16 hi/lo mode against an fp64 GEMM: fp32-grade results for every tile configuration / accumulator block length."""
+    from wedetect_b200 import ops
+    from wedetect_b200.ops import P3
+    g = torch.Generator().manual_seed(31)
+    A, Wt = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    bias = torch.randn(N, generator=g)
+    d = _dev()
+    C = torch.full((M, N), 7.0, dtype=torch.float32, device=d)
+    op = ops.linear(P3.from_f32(A, d, scale=ops.ACT_SCALE), P3.from_f32(Wt, d), C, bias=bias.to(d), block_n=block_n)
+    op.i[40] = lblk
+    _run(op)
+    ref = A.double() @ Wt.double().t() + bias.double()
+    err = (C.cpu().double() - ref)
+    rel = float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    print(f"split linear {M}x{K}x{N} lblk={lblk}: rel-rms {rel:.3e} max-abs {float(err.abs().max()):.3e} mean (bias) {float(err.mean()):.3e}")
+    tol = 3e-6 if lblk <= 2 else 3e-5   # lblk = 1000: the whole K accumulates in the tensor pipe (truncating adds)
+    report_close(f"split linear {M}x{K}x{N}", C, ref.float(), rtol=tol, atol=tol * float(ref.abs().mean()) * 4)
+
+
 def test_linear_split_precise():
-    """bf16x3 three-plane mode reproduces an fp32 GEMM to fp32-level accuracy."""
+    """fp16 hi/lo mode reproduces an fp32 GEMM to fp32-level accuracy (activation, bias, fp16 hi/lo output and residual)."""
     from wedetect_b200 import ops
     from wedetect_b200.ops import P3
     M, K, N = 515, 256, 192
@@ -187,16 +237,22 @@ def test_linear_split_precise():
     bias = torch.randn(N, generator=g)
     resid = torch.randn(M, N, generator=g)
     d = _dev()
-    Ap, Wp, Rp = P3.from_f32(A, d), P3.from_f32(Wt, d), P3.from_f32(resid, d)
+    Ap, Wp, Rp = P3.from_f32(A, d, scale=ops.ACT_SCALE), P3.from_f32(Wt, d), P3.from_f32(resid, d, scale=ops.ACT_SCALE)
     C = torch.zeros(M, N, dtype=torch.float32, device=d)
     _run(ops.linear(Ap, Wp, C, bias=bias.to(d), act=3))
     ref = R.act_ref(A.double() @ Wt.double().t() + bias.double(), 3).float()
     report_close("linear precise f32", C, ref, rtol=2e-6, atol=2e-6)
-    # three-plane bf16 output + three-plane bf16 residual
+    # fp16 hi/lo output + fp16 hi/lo residual
     Cp = P3.zeros((M, N), d, True)
     _run(ops.linear(Ap, Wp, Cp, bias=bias.to(d), act=2, resid=Rp, alpha=0.5))
     ref2 = (R.act_ref(A.double() @ Wt.double().t() + bias.double(), 2) + 0.5 * resid.double()).float()
-    report_close("linear precise 3-plane out", Cp.value(), ref2, rtol=2e-6, atol=2e-6)
+    report_close("linear precise hi/lo out", Cp.value(), ref2, rtol=2e-6, atol=2e-6)
+    # fp32 residual in place (the ConvNeXt pw2 epilogue): x += gamma * (A W^T + b)
+    gamma = torch.rand(N, generator=g) + 0.5
+    X = resid.clone().to(d)
+    _run(ops.linear(Ap, Wp, X, bias=bias.to(d), gamma=gamma.to(d), resid=X, alpha=1.0))
+    ref3 = (resid.double() + gamma.double() * (A.double() @ Wt.double().t() + bias.double())).float()
+    report_close("linear precise f32 residual", X, ref3, rtol=2e-6, atol=2e-6)
 
 
 def test_conv3x3_split_precise():
@@ -207,10 +263,36 @@ def test_conv3x3_split_precise():
     A, Wt = torch.randn(B, H, W, Cin, generator=g), torch.randn(N, 9 * Cin, generator=g) * 0.04
     d = _dev()
     Cp = P3.zeros((B, H, W, N), d, True)
-    _run(ops.conv3x3(P3.from_f32(A, d), P3.from_f32(_pad_taps(Wt, Cin), d), Cp))
+    _run(ops.conv3x3(P3.from_f32(A, d, scale=ops.ACT_SCALE), P3.from_f32(_pad_taps(Wt, Cin), d), Cp))
     w = Wt.view(N, 3, 3, Cin).permute(0, 3, 1, 2).double()
     ref = torch.nn.functional.conv2d(A.permute(0, 3, 1, 2).double(), w, padding=1).permute(0, 2, 3, 1).float()
     report_close("conv3x3 precise", Cp.value().reshape(-1, N), ref.reshape(-1, N), rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N,stride", [(2, 16, 16, 64, 256, 1),    # (16,8,1) bricks: per-warp TMA stores, pair BN=256
+                                                 (4, 32, 32, 128, 128, 1),   # pair BN=128, several tiles per CTA pair
+                                                 (2, 10, 10, 192, 64, 1),    # 100-row bricks: direct-store fallback, BN=64
+                                                 (2, 32, 32, 96, 192, 2),    # stride 2 (TMA element strides), K tail per tap
+                                                 (1, 20, 12, 64, 320, 2)])
+def test_conv3x3_split_shapes(B, H, W, Cin, N, stride):
+    from wedetect_b200 import ops
+    from wedetect_b200.ops import P3
+    g = torch.Generator().manual_seed(27)
+    A, Wt = torch.randn(B, H, W, Cin, generator=g), torch.randn(N, 9 * Cin, generator=g) * 0.04
+    bias = torch.randn(N, generator=g) * 0.3
+    d = _dev()
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    Cp = P3.zeros((B, Ho, Wo, N), d, True)
+    Rp = None
+    resid = torch.randn(B, Ho, Wo, N, generator=g)
+    if stride == 1:
+        Rp = P3.from_f32(resid, d, scale=ops.ACT_SCALE)
+    _run(ops.conv3x3(P3.from_f32(A, d, scale=ops.ACT_SCALE), P3.from_f32(_pad_taps(Wt, Cin), d), Cp, bias=bias.to(d), act=2, stride=stride,
+                     resid=Rp, alpha=0.75))
+    w = Wt.view(N, 3, 3, Cin).permute(0, 3, 1, 2).double()
+    y = torch.nn.functional.conv2d(A.permute(0, 3, 1, 2).double(), w, bias=bias.double(), padding=1, stride=stride).permute(0, 2, 3, 1)
+    ref = torch.nn.functional.silu(y) + (0.75 * resid.double() if stride == 1 else 0.0)
+    report_close("conv3x3 split", Cp.value().reshape(-1, N), ref.float().reshape(-1, N), rtol=3e-6, atol=3e-6)
 
 
 def test_deconv_and_im2col_precise():
@@ -227,7 +309,7 @@ def test_deconv_and_im2col_precise():
     bp[:, :Co] = bias
     buf = P3.zeros((B, 2 * H, 2 * W, 2 * Co), d, True)
     Cs = buf.view(lambda t: t[..., Co:])
-    Ap = P3.from_f32(A, d)
+    Ap = P3.from_f32(A, d, scale=ops.ACT_SCALE)
     _run(ops.deconv2x2(Ap, P3.from_f32(Wp.view(4 * Cg, Cin), d), Cs, bp.view(-1).to(d)))
     ref = (A.double().reshape(-1, Cin) @ Wt.double().t()).view(B, H, W, 2, 2, Co).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, Co) + bias.double()
     report_close("deconv precise", Cs.value().reshape(-1, Co), ref.float().reshape(-1, Co), rtol=2e-6, atol=2e-6)

@@ -6,6 +6,7 @@ import re
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "wedetect_b200.h")
 
 
 def _declared():
@@ -29,9 +30,14 @@ def test_header_symbols_are_exported():
 
 def test_struct_layout_matches_header():
     from wedetect_b200 import _lib
-    assert ctypes.sizeof(_lib.WdOp) == 4 + 4 * 40 + 4 * 8 + 4 + 8 * 16  # kind, i[40], f[8], pad, p[16]
+    hdr = open(HEADER).read()
+    ni, nf, np_ = (int(re.search(rf"#define {k} (\d+)", hdr).group(1)) for k in ("WD_OP_NI", "WD_OP_NF", "WD_OP_NP"))
+    assert (ni, nf, np_) == (_lib.WD_OP_NI, _lib.WD_OP_NF, _lib.WD_OP_NP)
+    assert ctypes.sizeof(_lib.WdOp) == (4 + 4 * ni + 4 * nf + 7) // 8 * 8 + 8 * np_  # kind, i[], f[], pad, p[]
     lib = _lib.load(require_gpu=False)
-    assert lib.wd_version() == 100
+    assert lib.wd_version() == 200
+    # the power of two activations are stored at (fp16 hi/lo planes) is compiled into the library; the host mirrors it
+    assert float(re.search(r"#define WD_ACT_PLANE_SCALE ([0-9.]+)f", hdr).group(1)) == _lib.ACT_PLANE_SCALE == lib.wd_act_plane_scale()
     assert lib.wd_pp_workspace_bytes(2, 8400, 80, 30000) > 2 * 8400 * 80 * 16
 
 

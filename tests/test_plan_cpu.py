@@ -13,7 +13,7 @@ def test_pick_tile_and_block_n():
         tiles = -(-W // e0) * -(-H // e1) * -(-B // e2)
         assert W * H * B / (tiles * 128) > 0.6
     assert pick_block_n(2048) == 256 and pick_block_n(384) == 128 and pick_block_n(64) == 64 and pick_block_n(1208) == 256
-    assert pick_block_n(512, split=True) == 128
+    assert pick_block_n(512, split=True) == 256 and pick_block_n(512, split=True, m_tiles=1) == 128 and pick_block_n(80, split=True) == 128
 
 
 def test_bn_fold_and_layouts_match_conv_semantics():
@@ -65,7 +65,7 @@ def test_plan_builds_for_all_sizes_on_cpu(monkeypatch):
         assert bool(p.ops[-1].p[10]) == (size == "large") and ("scales" in p.results()) == (size == "large")
         for op in p.ops:
             if op.kind == L.OP_GEMM:
-                assert op.i[30] == (3 if precise else 1) and op.i[6] % 64 == 0 and op.i[8] % 8 == 0
+                assert op.i[30] == (2 if precise else 1) and op.i[6] % 64 == 0 and op.i[8] % 8 == 0
 
 
 def test_standalone_text_tower_facade_wires_on_cpu(monkeypatch):

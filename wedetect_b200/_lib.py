@@ -9,7 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwedetect_b200.so")
 
-WD_OP_NI, WD_OP_NF, WD_OP_NP = 40, 8, 16
+WD_OP_NI, WD_OP_NF, WD_OP_NP = 48, 8, 16
+ACT_PLANE_SCALE = 4.0    # WD_ACT_PLANE_SCALE of include/wedetect_b200.h
 
 # enum wd_op_kind
 OP_GEMM, OP_LN_ROWS, OP_DWCONV_LN, OP_STEM_PATCH, OP_IM2COL_S2, OP_CAST_BF16 = 1, 2, 3, 4, 5, 6
@@ -21,7 +22,7 @@ EXPORTS = [
     "wd_last_error", "wd_version", "wd_launch_count", "wd_device_info", "wd_op_run", "wd_program_create",
     "wd_program_run", "wd_program_capture", "wd_program_replay", "wd_program_num_launches",
     "wd_program_destroy", "wd_pp_workspace_bytes", "wd_program_num_ops", "wd_program_run_timed",
-    "wd_program_find_stuck_op",
+    "wd_program_find_stuck_op", "wd_act_plane_scale",
 ]
 
 
@@ -68,6 +69,7 @@ def load(require_gpu=True):
         lib = ctypes.CDLL(LIB_PATH)
         lib.wd_last_error.restype = ctypes.c_char_p
         lib.wd_version.restype = ctypes.c_int
+        lib.wd_act_plane_scale.restype = ctypes.c_float
         lib.wd_launch_count.restype = ctypes.c_uint64
         lib.wd_device_info.argtypes = [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
         lib.wd_op_run.argtypes = [ctypes.POINTER(WdOp), ctypes.c_void_p]

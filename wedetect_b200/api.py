@@ -16,7 +16,7 @@ from .retrieval import (RetrievalScorer, evaluate_retrieval_per_class, extract_c
 from .structures import DetDataSample, InstanceData  # noqa: F401
 
 
-def init_detector(config, checkpoint=None, palette="none", device="cuda:0", cfg_options=None, precise=False):
+def init_detector(config, checkpoint=None, palette="none", device="cuda:0", cfg_options=None, precise=True):
     """mmdet.apis.init_detector look-alike (infer_wedetect.py:156): config path or Config, checkpoint path."""
     cfg = Config.fromfile(config) if isinstance(config, str) else config
     if cfg_options:

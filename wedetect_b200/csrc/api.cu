@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <set>
 #include <time.h>
 
 namespace wd {
@@ -20,13 +21,15 @@ void set_last_error(const char* fmt, ...) {
 }
 
 int device_sm_count() {
-    static int sms = 0;
-    if (sms > 0) return sms;
+    static std::mutex mu;
+    static int sms[64] = {0};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
         set_last_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
         return -1;
     }
+    std::lock_guard<std::mutex> lk(mu);
+    if (sms[dev] > 0) return sms[dev];
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
         set_last_error("cudaGetDeviceProperties failed");
@@ -36,8 +39,21 @@ int device_sm_count() {
         set_last_error("libwedetect_b200 requires an sm_100 device (found sm_%d%d)", prop.major, prop.minor);
         return -1;
     }
-    sms = prop.multiProcessorCount;
-    return sms;
+    sms[dev] = prop.multiProcessorCount;
+    return sms[dev];
+}
+
+cudaError_t ensure_smem_attr(const void* func, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({func, dev})) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.insert({func, dev});
+    return e;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
@@ -129,7 +145,8 @@ struct wd_program {
 extern "C" {
 
 const char* wd_last_error(void) { return wd::g_err; }
-int wd_version(void) { return 100; }
+int wd_version(void) { return 200; }
+float wd_act_plane_scale(void) { return WD_ACT_PLANE_SCALE; }
 uint64_t wd_launch_count(void) { return wd::g_launch_count.load(); }
 
 int wd_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {

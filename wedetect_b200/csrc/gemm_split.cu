@@ -1,0 +1,503 @@
+// gemm_split.cu — the parity-grade tcgen05 GEMM / implicit-GEMM convolution (default mode of the library).
+//
+// Operands are fp32-grade numbers carried as two fp16 planes, x * s = hi + lo (s a power of two, hi = fp16(x s),
+// lo = fp16(x s - hi)): 11 + 11 mantissa bits plus the sign of lo, i.e. an fp32 significand.  A k-step issues the three
+// products whose weight is >= 2^-12, (a_lo b_hi), (a_hi b_lo), (a_hi b_hi), on the fp16 tensor pipe with fp32 accumulation
+// in TMEM: three UMMAs where an fp32 FMA pipe would need 2 x 16 x more issue slots (the dropped a_lo b_lo is 2^-24 relative).
+//
+// What makes the result match an fp32 reference to ~1e-7 instead of ~1e-5:
+//   * the tensor pipe TRUNCATES when it adds a k-step's products to the running fp32 accumulator, a bias of ~2^-24 per step
+//     relative to the accumulator.  So an accumulator only lives for `lblk` 64-wide k-blocks; it then moves to fp32 REGISTERS of
+//     the epilogue warps, which sum the blocks with round-to-nearest adds while the tensor pipe fills the other TMEM buffer.
+//   * inside a block the two small cross products are issued BEFORE the large one: they are added while the accumulator is still
+//     ~2^-11 of its final size, so their truncation is 2^-11 smaller too; one TMEM accumulator serves all three products,
+//     which is what lets a 256-column tile double-buffer in the 512 TMEM columns.
+//
+// Structure (same skeleton as gemm_tc.cu): warp 0 TMA producer (A hi/lo bricks, B hi/lo tiles, 128-byte swizzle), warp 1 UMMA
+// issuer, warp 2 TMEM allocator, warps 4..11 epilogue (per warp: 32 accumulator rows x BN/2 columns in registers; bias /
+// activation / LayerScale / residual in fp32 with the exact erf / exp forms; fp16 hi/lo or fp32 output staged in swizzled shared
+// memory and written by per-warp TMA stores).  128- and 256-wide tiles run as CTA pairs (cta_group::2, M = 256): each SM stages
+// its own A rows and half of the B rows, so a UMMA reads 6-8 KB of shared memory per 64-128 tensor-pipe cycles instead of 8-12.
+//
+// Reference arithmetic replaced: see include/wedetect_b200.h (WD_OP_GEMM).
+#include "gemm_params.h"
+#include "epi_math.cuh"
+#include <cuda_fp16.h>
+
+namespace wd {
+
+template <int BN, bool kPair>
+struct SCfg {
+    static constexpr int A_BYTES = kTileM * 128;                 // one plane of this CTA's A rows
+    static constexpr int B_ROWS = kPair ? BN / 2 : BN;
+    static constexpr int B_BYTES = B_ROWS * 128;                 // one plane of this CTA's B rows
+    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // [A hi][A lo][B hi][B lo]
+    static constexpr int EPI_BYTES = 8 * 4096;                   // 32 rows x 128 B per epilogue warp
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int kStagesRaw = (232448 - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
+    static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+    static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int ACTIVE_WG = BN == 64 ? 1 : 2;           // a warpgroup owns >= 64 accumulator columns
+    static constexpr int WCOLS = BN / ACTIVE_WG;
+    static_assert(kStages >= 3, "pipeline too shallow");
+    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols");
+};
+
+// UMMA instruction descriptor (kind::f16): fp32 accumulate, fp16 A/B (format 0), both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+
+// v[j] = gamma[n] * act(v[j] * s + bias[n]) over CH columns starting at n_base (exact activation forms; columns >= N: no bias / gamma)
+template <int CH, int ACT>
+__device__ __forceinline__ void split_bias_act(float* v, float s, const float* __restrict__ bias, const float* __restrict__ gamma, int n_base, int N) {
+#pragma unroll
+    for (int j = 0; j < CH; j += 4) {
+        const int n = n_base + j;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        v[j + 0] = act_fn<ACT, false>(fmaf(v[j + 0], s, b4.x));
+        v[j + 1] = act_fn<ACT, false>(fmaf(v[j + 1], s, b4.y));
+        v[j + 2] = act_fn<ACT, false>(fmaf(v[j + 2], s, b4.z));
+        v[j + 3] = act_fn<ACT, false>(fmaf(v[j + 3], s, b4.w));
+        if (gamma && n < N) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n));
+            v[j + 0] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
+        }
+    }
+}
+
+template <int BN, typename OutT, bool kPair>
+__global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int kClu = kPair ? 2 : 1;
+    pdl_launch_dependents();
+    using C = SCfg<BN, kPair>;
+    constexpr int CH = 128 / (int)sizeof(OutT);   // columns per output chunk (one 128 B swizzle row)
+    constexpr bool kOut16 = sizeof(OutT) == 2;
+    constexpr int WCOLS = C::WCOLS;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_epi = smem + C::kStages * C::STAGE_BYTES;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
+    uint64_t* bar_empty = bar_full + 8;
+    uint64_t* bar_tfull = bar_empty + 8;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA[0]);
+        tma_prefetch_desc(&p.tmA[1]);
+        tma_prefetch_desc(&p.tmB[0]);
+        tma_prefetch_desc(&p.tmB[1]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tfull[a], 1);
+            mbar_init(&bar_tempty[a], 4 * C::ACTIVE_WG * kClu);   // one arrival per epilogue warp (of both CTAs in pair mode)
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        if constexpr (kPair) {
+            tmem_alloc_2sm(tmem_ptr_smem, C::TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+            tmem_relinquish();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (kPair) {
+        __syncwarp();
+        cluster_sync_all();   // peer barriers initialised before any multicast can signal them
+    }
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int k_iters = p.kc_iters * p.ntaps;
+    const int lblk = p.lblk;
+    const int crank = kPair ? (int)(blockIdx.x & 1) : 0;
+    const int t_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int t_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int t_total = kPair ? p.num_pair_tiles : p.num_tiles;
+
+    pdl_wait();   // everything above overlapped the previous kernel's tail
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+        // ================= TMA producer =================
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx_bytes = 2u * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
+        for (int tile = t_first; tile < t_total; tile += t_step) {
+            const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
+            const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
+            const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;   // beyond the tensor for the odd pair's ghost tile
+            int kc = 0, tx_ = 0, dy = -p.pad;
+            for (int kit = 0; kit < k_iters; ++kit) {
+                const int dx = tx_ - p.pad;
+                mbar_wait(&bar_empty[stage], phase ^ 1);
+                __syncwarp();
+                if (elect_one()) {
+                    uint8_t* sA = smem + stage * C::STAGE_BYTES;
+                    uint8_t* sB = sA + 2 * C::A_BYTES;
+                    const int a0 = kc * kBlockK, a1 = o0 * p.a_step + dx, a2 = o1 * p.a_step + dy;
+                    if constexpr (kPair) {
+                        const uint32_t lead_full = mapa_u32(smem_u32(&bar_full[stage]), 0);
+                        if (crank == 0) mbar_arrive_expect_tx(&bar_full[stage], 2u * tx_bytes);
+                        const int b1 = n_blk * BN + crank * (BN / 2);
+                        tma_load_4d_2sm(&p.tmA[0], lead_full, sA, a0, a1, a2, o2);
+                        tma_load_4d_2sm(&p.tmA[1], lead_full, sA + C::A_BYTES, a0, a1, a2, o2);
+                        tma_load_2d_2sm(&p.tmB[0], lead_full, sB, kit * kBlockK, b1);
+                        tma_load_2d_2sm(&p.tmB[1], lead_full, sB + C::B_BYTES, kit * kBlockK, b1);
+                    } else {
+                        mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
+                        tma_load_4d(&p.tmA[0], &bar_full[stage], sA, a0, a1, a2, o2);
+                        tma_load_4d(&p.tmA[1], &bar_full[stage], sA + C::A_BYTES, a0, a1, a2, o2);
+                        tma_load_2d(&p.tmB[0], &bar_full[stage], sB, kit * kBlockK, n_blk * BN);
+                        tma_load_2d(&p.tmB[1], &bar_full[stage], sB + C::B_BYTES, kit * kBlockK, n_blk * BN);
+                    }
+                }
+                __syncwarp();
+                if (++kc == p.kc_iters) {
+                    kc = 0;
+                    if (++tx_ == p.tap_w) {
+                        tx_ = 0;
+                        ++dy;
+                    }
+                }
+                if (++stage == C::kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= UMMA issuer =================
+        if (crank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(kPair ? 2 * kTileM : kTileM, BN);
+            const uint32_t smem0 = smem_u32(smem);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = t_first; tile < t_total; tile += t_step) {
+                int inblk = 0;
+                for (int kit = 0; kit < k_iters; ++kit) {
+                    const bool fresh = inblk == 0;
+                    const bool last = inblk == lblk - 1 || kit == k_iters - 1;
+                    if (fresh) {
+                        mbar_wait(&bar_tempty[as], aphase ^ 1);   // the epilogue has moved this buffer's previous block to registers
+                        tc_fence_after();
+                    }
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after();
+                    __syncwarp();
+                    if (elect_one()) {
+                        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                        const uint32_t sbase = smem0 + (uint32_t)(stage * C::STAGE_BYTES);
+                        const uint32_t ah = (sbase >> 4) & 0x3FFFu, al = ((sbase + C::A_BYTES) >> 4) & 0x3FFFu;
+                        const uint32_t bh = ((sbase + 2 * C::A_BYTES) >> 4) & 0x3FFFu, bl = ((sbase + 2 * C::A_BYTES + C::B_BYTES) >> 4) & 0x3FFFu;
+                        // cross terms first (small: they meet a small accumulator), then the hi x hi products
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t dal = umma_desc_from_lo(al + 2 * k), dbh = umma_desc_from_lo(bh + 2 * k);
+                            const uint64_t dah = umma_desc_from_lo(ah + 2 * k), dbl = umma_desc_from_lo(bl + 2 * k);
+                            if constexpr (kPair) {
+                                umma_bf16_2sm(tmem_d, dal, dbh, idesc, (fresh && k == 0) ? 0u : 1u);
+                                umma_bf16_2sm(tmem_d, dah, dbl, idesc, 1u);
+                            } else {
+                                umma_bf16(tmem_d, dal, dbh, idesc, (fresh && k == 0) ? 0u : 1u);
+                                umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t dah = umma_desc_from_lo(ah + 2 * k), dbh = umma_desc_from_lo(bh + 2 * k);
+                            if constexpr (kPair) umma_bf16_2sm(tmem_d, dah, dbh, idesc, 1u);
+                            else umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                        }
+                        if constexpr (kPair) {
+                            umma_commit_2sm_mc(&bar_empty[stage], (uint16_t)3);
+                            if (last) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
+                        } else {
+                            umma_commit(&bar_empty[stage]);
+                            if (last) umma_commit(&bar_tfull[as]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    if (last) {
+                        inblk = 0;
+                        if (++as == 2) {
+                            as = 0;
+                            aphase ^= 1;
+                        }
+                    } else {
+                        ++inblk;
+                    }
+                }
+            }
+        }
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ================= epilogue warps =================
+        const int wg = (warp - 4) >> 2;
+        const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+        if (wg < C::ACTIVE_WG) {
+        const int r = quarter * 32 + lane;
+        uint8_t* wbuf = smem_epi + (warp - 4) * 4096;
+        const uint32_t srow_s = smem_u32(wbuf) + lane * 128;
+        const int nblk = (k_iters + lblk - 1) / lblk;
+        int as = 0;
+        uint32_t aphase = 0;
+        auto release_acc = [&](int a) {
+            if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[a]), 0));
+            else mbar_arrive(&bar_tempty[a]);
+        };
+        for (int tile = t_first; tile < t_total; tile += t_step) {
+            const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
+            const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
+            const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
+
+            // ---- sum the block accumulators in fp32 registers (packed round-to-nearest adds) ----
+            uint64_t acc2[WCOLS / 2];
+#pragma unroll
+            for (int j = 0; j < WCOLS / 2; ++j) acc2[j] = 0ull;
+            for (int b = 0; b < nblk; ++b) {
+                mbar_wait(&bar_tfull[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + wg * WCOLS);
+#pragma unroll
+                for (int j0 = 0; j0 < WCOLS; j0 += 32) {
+                    uint32_t t[32];
+                    tmem_ld_32x32(taddr + j0, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint64_t tv;
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(tv) : "r"(t[2 * j]), "r"(t[2 * j + 1]));
+                        acc2[j0 / 2 + j] = add2(acc2[j0 / 2 + j], tv);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) release_acc(as);
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+            float acc[WCOLS];
+#pragma unroll
+            for (int j = 0; j < WCOLS / 2; ++j) upk2(acc2[j], acc[2 * j], acc[2 * j + 1]);
+
+            // ---- this thread's output row ----
+            const int i0 = r % p.E0, i1 = (r / p.E0) % p.E1, i2 = r / (p.E0 * p.E1);
+            const int d0 = o0 + i0, d1 = o1 + i1, d2 = o2 + i2;
+            const bool row_ok = (i2 < p.E2) && d0 < p.D0 && d1 < p.D1 && d2 < p.D2;
+            const long long pix = ((long long)d2 * p.D1 + d1) * p.D0 + d0;
+
+            if (p.epi_mode == 1) {
+                // ---- DFL epilogue (BN == N == 64): softmax over 16 bins x 4 sides, expectation (yolo_world_head.py:283-291) ----
+                if constexpr (BN == 64) {
+                    float out4[4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            acc[s * 16 + j] = fmaf(acc[s * 16 + j], p.acc_scale, __ldg(p.bias + s * 16 + j));
+                            mx = fmaxf(mx, acc[s * 16 + j]);
+                        }
+                        float den = 0.f, num = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float e = expf(acc[s * 16 + j] - mx);
+                            den += e;
+                            num += e * (float)j;
+                        }
+                        out4[s] = num / den;
+                    }
+                    if (row_ok) *reinterpret_cast<float4*>(p.dfl_out + pix * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+                }
+                continue;
+            }
+
+            // first row of this warp's quarter inside the tile brick (per-warp TMA stores)
+            const int qr = quarter * 32;
+            const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
+            // ---- acc = gamma * act(acc * acc_scale + bias) over the warpgroup's columns (column guards inside) ----
+            {
+                const int nb = n_blk * BN + wg * WCOLS;
+                switch (p.act) {
+                    case WD_ACT_RELU: split_bias_act<WCOLS, WD_ACT_RELU>(acc, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                    case WD_ACT_SILU: split_bias_act<WCOLS, WD_ACT_SILU>(acc, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                    case WD_ACT_GELU: split_bias_act<WCOLS, WD_ACT_GELU>(acc, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                    default: split_bias_act<WCOLS, WD_ACT_NONE>(acc, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < WCOLS / CH; ++c) {
+                float* v = acc + c * CH;
+                const int n_base = n_blk * BN + wg * WCOLS + c * CH;
+                if (n_base >= p.N) continue;   // warp-uniform: nothing of this chunk exists
+                // ---- v += resid * alpha ----
+                if (p.resid_dtype == 2 && row_ok) {
+                    const float* rp = reinterpret_cast<const float*>(p.resid) + pix * p.ld_res + n_base;
+#pragma unroll
+                    for (int j = 0; j < CH; j += 4) {
+                        if (n_base + j < p.N) {
+                            const float4 x = *reinterpret_cast<const float4*>(rp + j);
+                            v[j + 0] = fmaf(p.alpha, x.x, v[j + 0]);
+                            v[j + 1] = fmaf(p.alpha, x.y, v[j + 1]);
+                            v[j + 2] = fmaf(p.alpha, x.z, v[j + 2]);
+                            v[j + 3] = fmaf(p.alpha, x.w, v[j + 3]);
+                        }
+                    }
+                } else if (p.resid_dtype == 1 && row_ok) {
+                    // fp16 hi (+ lo) planes; alpha already carries 1 / kPlaneScale
+                    const __half* rp = reinterpret_cast<const __half*>(p.resid) + pix * p.ld_res + n_base;
+#pragma unroll
+                    for (int j = 0; j < CH; j += 8) {
+                        if (n_base + j < p.N) {
+                            const uint4 x = *reinterpret_cast<const uint4*>(rp + j);
+                            const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+                            float xs[8];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 f = unpack_h2(xw[q]);
+                                xs[2 * q] = f.x;
+                                xs[2 * q + 1] = f.y;
+                            }
+                            if (p.resid_ps) {
+                                const uint4 y = *reinterpret_cast<const uint4*>(rp + p.resid_ps + j);
+                                const uint32_t yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 f = unpack_h2(yw[q]);
+                                    xs[2 * q] += f.x;
+                                    xs[2 * q + 1] += f.y;
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[j + q] = fmaf(p.alpha, xs[q], v[j + q]);
+                        }
+                    }
+                }
+                // ---- output: fp32, or fp16 hi / lo planes of v * kPlaneScale (one pass per plane) ----
+                const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
+                constexpr int kOutPlanes = kOut16 ? 2 : 1;
+                const long long grow = (long long)d0 * p.sc0 + (long long)d1 * p.sc1 + (long long)d2 * p.sc2 + (long long)g * p.scg + c0;
+#pragma unroll
+                for (int pl = 0; pl < kOutPlanes; ++pl) {
+                    uint4 w[8];
+                    if constexpr (kOut16) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            uint32_t ww[4];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                float a = v[q * 8 + 2 * h], b = v[q * 8 + 2 * h + 1];
+                                if (pl == 0) {
+                                    a = clamp_h(a * kPlaneScale);
+                                    b = clamp_h(b * kPlaneScale);
+                                }
+                                ww[h] = pack_h2(a, b);
+                                if (pl == 0) {   // keep the remainder for the low plane
+                                    const float2 f = unpack_h2(ww[h]);
+                                    v[q * 8 + 2 * h] = a - f.x;
+                                    v[q * 8 + 2 * h + 1] = b - f.y;
+                                }
+                            }
+                            w[q] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            w[q] = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+                    }
+                    if (p.warp_store) {
+                        if (lane == 0) tma_store_wait_read<0>();   // the staging buffer is no longer being read by the previous store
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + ((q ^ (lane & 7)) << 4)), "r"(w[q].x), "r"(w[q].y), "r"(w[q].z), "r"(w[q].w) : "memory");
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_5d(&p.tmCw[pl], wbuf, c0, o0 + q0, o1 + q1, o2 + q2, g);
+                            tma_store_commit();
+                        }
+                    } else if (row_ok) {
+                        // this warp's 32 rows are not a sub-brick of the tile: each thread writes its own row
+                        constexpr int EPV = 16 / (int)sizeof(OutT);
+                        OutT* op = reinterpret_cast<OutT*>(p.out) + (long long)pl * p.out_ps + grow;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (c0 + q * EPV < p.cols_valid) *reinterpret_cast<uint4*>(op + q * EPV) = w[q];
+                    }
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (kPair) {
+        __syncwarp();
+        cluster_sync_all();   // the peer may still be arriving on this CTA's barriers
+    }
+    if (warp == 2) {
+        if constexpr (kPair) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+        else tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, typename OutT, bool kPair>
+static int launch_split_inst(const GemmOp& g, cudaStream_t s) {
+    auto kern = gemm_split_kernel<BN, OutT, kPair>;
+    using C = SCfg<BN, kPair>;
+    WD_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
+    WD_CHECK_CUDA(launch_pdl(kern, dim3(g.grid), dim3(kNumThreads), (size_t)C::SMEM_BYTES, s, kPair ? 2 : 1, g.prm));
+    WD_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int launch_gemm_split(const GemmOp& g, cudaStream_t s) {
+    const bool pair = g.prm.clu == 2;
+    if (g.block_n == 64 && !pair) return g.out_f32 ? launch_split_inst<64, float, false>(g, s) : launch_split_inst<64, __half, false>(g, s);
+    if (g.block_n == 128 && !pair) return g.out_f32 ? launch_split_inst<128, float, false>(g, s) : launch_split_inst<128, __half, false>(g, s);
+    if (g.block_n == 128 && pair) return g.out_f32 ? launch_split_inst<128, float, true>(g, s) : launch_split_inst<128, __half, true>(g, s);
+    if (g.block_n == 256 && pair) return g.out_f32 ? launch_split_inst<256, float, true>(g, s) : launch_split_inst<256, __half, true>(g, s);
+    set_last_error("gemm (split): unsupported block_n=%d pair=%d", g.block_n, (int)pair);
+    return -1;
+}
+
+}  // namespace wd

@@ -14,67 +14,39 @@
 //   apply bias / activation / LayerScale / residual (or DFL), stage the tile in swizzled smem and
 //   write it back with TMA stores (which clip partial tiles and scatter into concat / upsample
 //   layouts through a rank-5 tensor map).
-// * kSplit = bf16x3 "precise" mode: every fp32 operand is carried as three bf16 planes p0 + p1 + p2
-//   (8 + 8 + 8 mantissa bits) and each k-step issues the six products whose weight is >= 2^-16
-//   (a0b0, a1b0, a0b1, a2b0, a1b1, a0b2), i.e. fp32-grade operands on the bf16 tensor pipe.
+// * the parity-grade mode (fp16 hi/lo operand pairs, three UMMAs per k-step) is a separate kernel: gemm_split.cu.
 //
 // Reference arithmetic replaced: see include/wedetect_b200.h (WD_OP_GEMM).
-#include "internal.h"
+#include "gemm_params.h"
 #include "epi_math.cuh"
 #include <stdio.h>
 #include <string.h>
 
 namespace wd {
 
-constexpr int kNumEpiWG = 2;
-constexpr int kNumThreads = 128 + 128 * kNumEpiWG;
-constexpr int kTileM = 128;
-constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle atom
-
-struct GemmParams {
-    CUtensorMap tmA[3], tmB[3], tmC[3];   // plane 0 (+ planes 1, 2 in the bf16x3 "precise" mode)
-    CUtensorMap tmCw[3];                  // C with a 32-row box: the quarter of the tile one epilogue warp owns (warp_store)
-    int warp_store, w0, w1, w2;           // warp_store: per-warp stores enabled; (w0, w1, w2) = the 32-row sub-brick
-    int D0, D1, D2, E0, E1, E2, nt0, nt1, nt2;
-    int kc_iters, ntaps, tap_w, pad;
-    int N, num_m_tiles, num_n_tiles, num_tiles;
-    int act, resid_dtype, ld_res, group_cols, epi_mode, rows_a, exact_act;
-    int a_step;          // 1, or 2 for a stride-2 tap walk (input pixel = 2 * output pixel + tap offset)
-    int clu, num_pair_tiles;   // clu == 2: clusters of two CTAs (same n-block, adjacent m-blocks) share B through TMA multicast
-    float alpha;
-    const float* bias;
-    const float* gamma;
-    const void* resid;
-    long long resid_ps;  // plane stride (elements) of a 3-plane bf16 residual, 0 = single plane
-    float* dfl_out;
-};
-
-template <int BN, bool kSplit>
+template <int BN>
 struct Cfg {
     static constexpr int A_BYTES = kTileM * 128;
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = (kSplit ? 3 : 1) * (A_BYTES + B_BYTES);
-    static constexpr int kStages = kSplit ? 2 : (BN == 256 ? 4 : (BN == 128 ? 5 : 6));
-    static constexpr int EPI_BUFS = (!kSplit && BN <= 128) ? 2 : 1;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 5 : 6);
+    static constexpr int EPI_BUFS = BN <= 128 ? 2 : 1;
     static constexpr int EPI_BUF_BYTES = 16384;
     static constexpr int EPI_BYTES = kNumEpiWG * EPI_BUFS * EPI_BUF_BYTES;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
-    // precise mode keeps two accumulators per buffer: the a0*b0 products and the five small cross terms, so the
-    // small terms are not truncated against the large running sum inside the tensor pipe
-    static constexpr int TMEM_COLS = (kSplit ? 4 : 2) * BN;
+    static constexpr int TMEM_COLS = 2 * BN;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols");
 };
 
-template <int BN, typename OutT, bool kSplit, bool kPair = false>
+template <int BN, typename OutT, bool kPair = false>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     // kPair: the kernel is launched in clusters of two CTAs and every tcgen05 instruction is the cta_group::2 form (a kernel
     // may not mix the two forms: ptxas tags it TCGEN05_2CTA_USED and the driver then refuses a launch without clusters)
-    static_assert(!kPair || !kSplit, "pair mode is bf16 single-plane only");
     constexpr int kClu = kPair ? 2 : 1;
     pdl_launch_dependents();
-    using C = Cfg<BN, kSplit>;
+    using C = Cfg<BN>;
     constexpr int CH = 128 / (int)sizeof(OutT);  // columns per epilogue chunk (one 128 B swizzle row)
     constexpr bool kOutBf16 = sizeof(OutT) == 2;
 
@@ -149,7 +121,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         // elected lane arms the barrier and issues.  Taps and k-chunks advance by counters: no division per k-step.
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx_bytes = (kSplit ? 3u : 1u) * (uint32_t)(p.rows_a * 128 + C::B_BYTES);
+        const uint32_t tx_bytes = (uint32_t)(p.rows_a * 128 + C::B_BYTES);
         for (int tile = t_first; tile < t_total; tile += t_step) {
             const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
             const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
@@ -168,12 +140,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         tma_load_2d_2sm(&p.tmB[0], lead_full, sA + C::A_BYTES, kit * kBlockK, n_blk * BN + crank * (BN / 2));
                     } else {
                         mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
-#pragma unroll
-                        for (int pl = 0; pl < (kSplit ? 3 : 1); ++pl) {
-                            uint8_t* sA = smem + stage * C::STAGE_BYTES + pl * (C::A_BYTES + C::B_BYTES);
-                            tma_load_4d(&p.tmA[pl], &bar_full[stage], sA, kc * kBlockK, o0 * p.a_step + dx, o1 * p.a_step + dy, o2);
-                            tma_load_2d(&p.tmB[pl], &bar_full[stage], sA + C::A_BYTES, kit * kBlockK, n_blk * BN);
-                        }
+                        uint8_t* sA = smem + stage * C::STAGE_BYTES;
+                        tma_load_4d(&p.tmA[0], &bar_full[stage], sA, kc * kBlockK, o0 * p.a_step + dx, o1 * p.a_step + dy, o2);
+                        tma_load_2d(&p.tmB[0], &bar_full[stage], sA + C::A_BYTES, kit * kBlockK, n_blk * BN);
                     }
                 }
                 __syncwarp();
@@ -203,17 +172,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             int as = 0;
             uint32_t aphase = 0;
             for (int tile = t_first; tile < t_total; tile += t_step) {
-                if constexpr (!kSplit) {
-                    mbar_wait(&bar_tempty[as], aphase ^ 1);
-                    tc_fence_after();
-                }
+                mbar_wait(&bar_tempty[as], aphase ^ 1);
+                tc_fence_after();
                 for (int kit = 0; kit < k_iters; ++kit) {
-                    if constexpr (kSplit) {
-                        // precise mode: a fresh accumulator per 64-wide k-block; the epilogue sums the blocks in fp32
-                        // registers (round-to-nearest), keeping the tensor pipe's truncating accumulation chains short
-                        mbar_wait(&bar_tempty[as], aphase ^ 1);
-                        tc_fence_after();
-                    }
                     const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
                     mbar_wait(&bar_full[stage], phase);
                     tc_fence_after();
@@ -222,31 +183,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         // descriptor low words: (address >> 4) in 14 bits; +32 bytes along K inside the swizzle atom = +2
                         const uint32_t a_lo = ((smem0 + (uint32_t)(stage * stage_bytes)) >> 4) & 0x3FFFu;
                         const uint32_t b_lo = ((smem0 + (uint32_t)(stage * stage_bytes) + C::A_BYTES) >> 4) & 0x3FFFu;
-                        constexpr uint32_t PL = (C::A_BYTES + C::B_BYTES) >> 4;
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
-                            if constexpr (!kSplit) {
-                                const uint64_t ad = umma_desc_from_lo(a_lo + 2 * k), bd = umma_desc_from_lo(b_lo + 2 * k);
-                                if constexpr (kPair) umma_bf16_2sm(tmem_d, ad, bd, idesc2, (kit | k) != 0 ? 1u : 0u);
-                                else umma_bf16(tmem_d, ad, bd, idesc, (kit | k) != 0 ? 1u : 0u);
-                            } else {
-                                const uint64_t a0 = umma_desc_from_lo(a_lo + 2 * k), b0 = umma_desc_from_lo(b_lo + 2 * k);
-                                const uint64_t a1 = umma_desc_from_lo(a_lo + PL + 2 * k), b1 = umma_desc_from_lo(b_lo + PL + 2 * k);
-                                const uint64_t a2 = umma_desc_from_lo(a_lo + 2 * PL + 2 * k), b2 = umma_desc_from_lo(b_lo + 2 * PL + 2 * k);
-                                const uint32_t tmem_s = tmem_d + 2 * BN;   // second accumulator: the small cross terms
-                                umma_bf16(tmem_s, a0, b2, idesc, k != 0 ? 1u : 0u);
-                                umma_bf16(tmem_s, a1, b1, idesc, 1u);
-                                umma_bf16(tmem_s, a2, b0, idesc, 1u);
-                                umma_bf16(tmem_s, a0, b1, idesc, 1u);
-                                umma_bf16(tmem_s, a1, b0, idesc, 1u);
-                                umma_bf16(tmem_d, a0, b0, idesc, k != 0 ? 1u : 0u);
-                            }
+                            const uint64_t ad = umma_desc_from_lo(a_lo + 2 * k), bd = umma_desc_from_lo(b_lo + 2 * k);
+                            if constexpr (kPair) umma_bf16_2sm(tmem_d, ad, bd, idesc2, (kit | k) != 0 ? 1u : 0u);
+                            else umma_bf16(tmem_d, ad, bd, idesc, (kit | k) != 0 ? 1u : 0u);
                         }
                         // frees the smem slot when these MMAs retire (in pair mode: tells BOTH CTAs' producers)
                         if constexpr (kPair) umma_commit_2sm_mc(&bar_empty[stage], (uint16_t)3);
                         else umma_commit(&bar_empty[stage]);
-                        if constexpr (kSplit) umma_commit(&bar_tfull[as]);
-                        else if (kit == k_iters - 1) {
+                        if (kit == k_iters - 1) {
                             // accumulator complete -> epilogue (of both CTAs in pair mode)
                             if constexpr (kPair) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
                             else umma_commit(&bar_tfull[as]);
@@ -257,18 +203,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         stage = 0;
                         phase ^= 1;
                     }
-                    if constexpr (kSplit) {
-                        if (++as == 2) {
-                            as = 0;
-                            aphase ^= 1;
-                        }
-                    }
                 }
-                if constexpr (!kSplit) {
-                    if (++as == 2) {
-                        as = 0;
-                        aphase ^= 1;
-                    }
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
                 }
             }
         }
@@ -327,7 +265,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 const int n_base = n_blk * BN + c * CH;
                 if (n_base < p.N) {  // warp-uniform: whole chunk beyond N is skipped (nothing to store)
                     // ---- math: v = resid*alpha + gamma * act(acc + bias); the activation is uniform per launch ----
-                    constexpr bool kFast = kOutBf16 && !kSplit;
+                    constexpr bool kFast = kOutBf16;
                     // warp-uniform: 1 / 2 = whole chunk inside N with bias (and gamma) -> unchecked forms
                     const int mode = (p.bias != nullptr && n_base + CH <= p.N) ? (p.gamma ? 2 : 1) : 0;
 #define WD_EPI(ACT, FAST)                                                                        \
@@ -381,36 +319,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                             }
                         } else {
                             const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix * p.ld_res + n_base;
-                            const __nv_bfloat16* rl = p.resid_ps ? rp + p.resid_ps : nullptr;
 #pragma unroll
                             for (int j = 0; j < CH; j += 8) {
                                 if (n_base + j < p.N) {
                                     const uint4 x = *reinterpret_cast<const uint4*>(rp + j);
-                                    float xs[8] = {bf16_lo(x.x), bf16_hi(x.x), bf16_lo(x.y), bf16_hi(x.y),
-                                                   bf16_lo(x.z), bf16_hi(x.z), bf16_lo(x.w), bf16_hi(x.w)};
-                                    if (rl) {
-#pragma unroll
-                                        for (int pl = 0; pl < 2; ++pl) {
-                                            const uint4 y = *reinterpret_cast<const uint4*>(rl + pl * p.resid_ps + j);
-                                            xs[0] += bf16_lo(y.x); xs[1] += bf16_hi(y.x);
-                                            xs[2] += bf16_lo(y.y); xs[3] += bf16_hi(y.y);
-                                            xs[4] += bf16_lo(y.z); xs[5] += bf16_hi(y.z);
-                                            xs[6] += bf16_lo(y.w); xs[7] += bf16_hi(y.w);
-                                        }
-                                    }
+                                    const float xs[8] = {bf16_lo(x.x), bf16_hi(x.x), bf16_lo(x.y), bf16_hi(x.y),
+                                                         bf16_lo(x.z), bf16_hi(x.z), bf16_lo(x.w), bf16_hi(x.w)};
 #pragma unroll
                                     for (int q = 0; q < 8; ++q) v[j + q] += p.alpha * xs[q];
                                 }
                             }
                         }
                     }
-                    // ---- stage into swizzled smem, then TMA store (precise bf16 output: one pass per plane) ----
+                    // ---- stage into swizzled smem, then TMA store ----
                     uint8_t* sbuf = wg_bufs + buf * C::EPI_BUF_BYTES;
                     const uint32_t srow_s = smem_u32(sbuf) + r * 128;   // explicit shared-space stores (STS), not generic ST
                     const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
-                    constexpr int kOutPlanes = (kSplit && kOutBf16) ? 3 : 1;
-#pragma unroll
-                    for (int pl = 0; pl < kOutPlanes; ++pl) {
+                    {
+                        constexpr int pl = 0;
                         // buffer `buf` no longer being read by an earlier store.  warp_store: every warp stages and stores its
                         // own 32 rows (4 KB of the buffer) with its own bulk groups, so the four warps never wait for each other
                         if (p.warp_store) {
@@ -429,12 +355,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                                 w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
                                 w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
                                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + ((q ^ (r & 7)) << 4)), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-                                if constexpr (kSplit) {  // keep the remainder for the next plane
-                                    v[q * 8 + 0] -= bf16_lo(w.x); v[q * 8 + 1] -= bf16_hi(w.x);
-                                    v[q * 8 + 2] -= bf16_lo(w.y); v[q * 8 + 3] -= bf16_hi(w.y);
-                                    v[q * 8 + 4] -= bf16_lo(w.z); v[q * 8 + 5] -= bf16_hi(w.z);
-                                    v[q * 8 + 6] -= bf16_lo(w.w); v[q * 8 + 7] -= bf16_hi(w.w);
-                                }
                             }
                         } else {
 #pragma unroll
@@ -482,7 +402,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 if (row_ok)
                     *reinterpret_cast<float4*>(p.dfl_out + pix * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
             };
-            if constexpr (!kSplit) {
+            {
                 if (p.epi_mode == 0) prefetch_resid(wg);
                 mbar_wait(&bar_tfull[as], aphase);
                 tc_fence_after();
@@ -524,65 +444,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     as = 0;
                     aphase ^= 1;
                 }
-            } else {
-                // ---- precise mode: sum the per-k-block accumulators in fp32 registers ----
-                constexpr int MY = (n_chunks + kNumEpiWG - 1) / kNumEpiWG;   // chunks a warpgroup can own
-                static_assert(MY * CH <= 64 && BN <= 128, "precise mode register budget");
-                float acc[64];
-#pragma unroll
-                for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-                const bool dfl = p.epi_mode == 1;
-                for (int kit = 0; kit < k_iters; ++kit) {
-                    mbar_wait(&bar_tfull[as], aphase);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
-                    float t[32];
-                    if (dfl) {
-                        if constexpr (BN == 64) if (wg == 0) {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                float t2[32];
-                                tmem_ld_32x32(taddr + h * 32, reinterpret_cast<uint32_t*>(t));
-                                tmem_ld_32x32(taddr + 2 * BN + h * 32, reinterpret_cast<uint32_t*>(t2));
-                                tmem_ld_wait();
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) acc[h * 32 + j] += t[j] + t2[j];
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < MY; ++i) {
-                            const int c = wg + i * kNumEpiWG;
-                            if (c < n_chunks) {
-#pragma unroll
-                                for (int j0 = 0; j0 < CH; j0 += 32) {
-                                    float t2[32];
-                                    tmem_ld_32x32(taddr + c * CH + j0, reinterpret_cast<uint32_t*>(t));
-                                    tmem_ld_32x32(taddr + 2 * BN + c * CH + j0, reinterpret_cast<uint32_t*>(t2));
-                                    tmem_ld_wait();
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) acc[i * CH + j0 + j] += t[j] + t2[j];
-                                }
-                            }
-                        }
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) release_acc(as);
-                    if (++as == 2) {
-                        as = 0;
-                        aphase ^= 1;
-                    }
-                }
-                if (dfl) {
-                    if constexpr (BN == 64) if (wg == 0) finish_dfl(acc);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < MY; ++i) {
-                        const int c = wg + i * kNumEpiWG;
-                        if (c < n_chunks) finish_chunk(acc + i * CH, c);
-                    }
-                }
             }
         }
         if (p.warp_store ? (lane == 0) : issuer) tma_store_wait_all<0>();
@@ -603,41 +464,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct GemmOp : CompiledOp {
-    GemmParams prm;
-    int block_n, out_f32, split, grid, smem;
-    int launch(cudaStream_t s) override;
-};
-
-template <int BN, typename OutT, bool kSplit, bool kPair = false>
+template <int BN, typename OutT, bool kPair = false>
 static int launch_inst(const GemmOp& g, cudaStream_t s) {
-    auto kern = gemm_tc_kernel<BN, OutT, kSplit, kPair>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        WD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, kSplit>::SMEM_BYTES));
-        attr_set = true;
-    }
-    WD_CHECK_CUDA(launch_pdl(kern, dim3(g.grid), dim3(kNumThreads), (size_t)Cfg<BN, kSplit>::SMEM_BYTES, s, kPair ? 2 : 1, g.prm));
+    auto kern = gemm_tc_kernel<BN, OutT, kPair>;
+    WD_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(kern), Cfg<BN>::SMEM_BYTES));
+    WD_CHECK_CUDA(launch_pdl(kern, dim3(g.grid), dim3(kNumThreads), (size_t)Cfg<BN>::SMEM_BYTES, s, kPair ? 2 : 1, g.prm));
     WD_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
 }
 
 int GemmOp::launch(cudaStream_t s) {
-#define WD_DISPATCH(BN)                                                                         \
-    if (block_n == BN) {                                                                        \
-        if (!split) return out_f32 ? launch_inst<BN, float, false>(*this, s)                    \
-                                   : launch_inst<BN, __nv_bfloat16, false>(*this, s);           \
-    }
-    WD_DISPATCH(64)
-    WD_DISPATCH(128)
-    if (block_n == 256 && !split && prm.clu == 2)
-        return out_f32 ? launch_inst<256, float, false, true>(*this, s) : launch_inst<256, __nv_bfloat16, false, true>(*this, s);
-    WD_DISPATCH(256)
-#undef WD_DISPATCH
-    if (split && block_n == 64) return out_f32 ? launch_inst<64, float, true>(*this, s) : launch_inst<64, __nv_bfloat16, true>(*this, s);
-    if (split && block_n == 128) return out_f32 ? launch_inst<128, float, true>(*this, s) : launch_inst<128, __nv_bfloat16, true>(*this, s);
-    set_last_error("gemm: unsupported block_n=%d split=%d", block_n, split);
+    if (split) return launch_gemm_split(*this, s);
+    if (block_n == 64) return out_f32 ? launch_inst<64, float>(*this, s) : launch_inst<64, __nv_bfloat16>(*this, s);
+    if (block_n == 128) return out_f32 ? launch_inst<128, float>(*this, s) : launch_inst<128, __nv_bfloat16>(*this, s);
+    if (block_n == 256 && prm.clu == 2) return out_f32 ? launch_inst<256, float, true>(*this, s) : launch_inst<256, __nv_bfloat16, true>(*this, s);
+    if (block_n == 256) return out_f32 ? launch_inst<256, float>(*this, s) : launch_inst<256, __nv_bfloat16>(*this, s);
+    set_last_error("gemm: unsupported block_n=%d", block_n);
     return -1;
 }
 
@@ -674,11 +517,15 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     P.bias = (const float*)op.p[3];
     P.gamma = (const float*)op.p[4];
     P.resid = op.p[5];
-    g->split = I[30] == 3 ? 1 : 0;
-    WD_REQUIRE(I[30] == 0 || I[30] == 1 || I[30] == 3, "gemm: planes must be 1 or 3");
+    g->split = I[30] == 2 ? 1 : 0;
+    WD_REQUIRE(I[30] == 0 || I[30] == 1 || I[30] == 2, "gemm: planes must be 1 (bf16) or 2 (fp16 hi/lo)");
     const long long a_ps = I[31], b_ps = I[32], c_ps = I[33];
     P.resid_ps = g->split ? I[34] : 0;
-    WD_REQUIRE(!g->split || (a_ps > 0 && b_ps > 0), "gemm: precise mode needs plane strides for A and B");
+    WD_REQUIRE(!g->split || (a_ps > 0 && b_ps > 0), "gemm: split mode needs plane strides for A and B");
+    P.acc_scale = op.f[1] != 0.f ? op.f[1] : 1.f;
+    P.lblk = I[40] > 0 ? I[40] : 1;
+    // a residual given as fp16 hi/lo planes is stored times kPlaneScale
+    if (g->split && P.resid_dtype == 1) P.alpha /= kPlaneScale;
 
     WD_REQUIRE(P.D0 > 0 && P.D1 > 0 && P.D2 > 0, "gemm: bad dims %d %d %d", P.D0, P.D1, P.D2);
     WD_REQUIRE(P.E0 > 0 && P.E1 > 0 && P.E2 > 0 && P.E0 * P.E1 * P.E2 <= kTileM, "gemm: bad tile %d %d %d", P.E0, P.E1, P.E2);
@@ -686,7 +533,6 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     WD_REQUIRE(P.ntaps == 1 || P.ntaps == 9, "gemm: ntaps=%d", P.ntaps);
     WD_REQUIRE(P.N > 0 && P.N % 8 == 0, "gemm: N=%d must be a positive multiple of 8", P.N);
     WD_REQUIRE(g->block_n == 64 || g->block_n == 128 || g->block_n == 256, "gemm: block_n=%d", g->block_n);
-    WD_REQUIRE(!(g->split && g->block_n == 256), "gemm: split mode supports block_n <= 128");
     WD_REQUIRE(op.p[0] && op.p[1], "gemm: null operand");
     WD_REQUIRE(P.group_cols > 0 && n_groups > 0 && P.group_cols * n_groups >= P.N, "gemm: bad groups");
     const int CH = g->out_f32 ? 32 : 64;
@@ -707,7 +553,11 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     P.rows_a = P.E0 * P.E1 * P.E2;
     // pair mode: 256-wide tiles of the fast path; halves the B bytes each SM pulls through L2 (the L2->SM fabric, not
     // HBM or the tensor pipe, is what bounds 128x256 tiles).  I[36] = 1 disables it (A/B measurements).
-    P.clu = (g->block_n == 256 && !g->split && P.epi_mode == 0 && P.num_m_tiles >= 2 && I[36] == 0) ? 2 : 1;
+    // split mode: 128- and 256-wide tiles pair up (each UMMA then reads 6 or 8 KB of operands from this SM's shared memory
+    // instead of 8 or 12); 256-wide tiles exist only as pairs (a single CTA has room for two pipeline stages of them).
+    if (g->split) P.clu = (g->block_n >= 128 && P.epi_mode == 0 && P.num_m_tiles >= 2 && I[36] == 0) ? 2 : 1;
+    else P.clu = (g->block_n == 256 && P.epi_mode == 0 && P.num_m_tiles >= 2 && I[36] == 0) ? 2 : 1;
+    WD_REQUIRE(!(g->split && g->block_n == 256 && P.clu != 2), "gemm: split mode runs 256-wide tiles only as CTA pairs (>= 2 m-tiles)");
     P.num_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
 
     // --- A: rank-4 (k, d0, d1, d2), bf16, box (64, E0, E1, E2), 128B swizzle
@@ -722,7 +572,7 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         uint64_t str[3] = {(uint64_t)sa0 * 2, (uint64_t)sa1 * 2, (uint64_t)sa2 * 2};
         uint32_t box[4] = {kBlockK, (uint32_t)(P.E0 * P.a_step), (uint32_t)(P.E1 * P.a_step), (uint32_t)P.E2};
         uint32_t est[4] = {1u, (uint32_t)P.a_step, (uint32_t)P.a_step, 1u};
-        for (int pl = 0; pl < (g->split ? 3 : 1); ++pl)
+        for (int pl = 0; pl < (g->split ? 2 : 1); ++pl)
             if (encode_tmap(&P.tmA[pl], (const __nv_bfloat16*)op.p[0] + pl * a_ps, 2, 4, dims, str, box, true, est)) return -1;
     }
     // --- B: rank-2 (k_total, n)
@@ -731,7 +581,7 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         uint64_t dims[2] = {(uint64_t)bk_valid, (uint64_t)P.N};
         uint64_t str[1] = {(uint64_t)ldb * 2};
         uint32_t box[2] = {kBlockK, (uint32_t)(P.clu == 2 ? g->block_n / 2 : g->block_n)};
-        for (int pl = 0; pl < (g->split ? 3 : 1); ++pl)
+        for (int pl = 0; pl < (g->split ? 2 : 1); ++pl)
             if (encode_tmap(&P.tmB[pl], (const __nv_bfloat16*)op.p[1] + pl * b_ps, 2, 2, dims, str, box, true)) return -1;
     }
     // --- C: rank-5 (c, d0, d1, d2, group), box (CH, E0, E1, E2, 1)
@@ -758,14 +608,17 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             uint32_t wbox[5] = {(uint32_t)CH, (uint32_t)P.w0, (uint32_t)P.w1, (uint32_t)P.w2, 1};
             if (encode_tmap(&P.tmCw[0], op.p[2], eb, 5, dims, str, wbox, true)) return -1;
             if (g->split && !g->out_f32)
-                for (int pl = 1; pl < 3; ++pl)
-                    if (encode_tmap(&P.tmCw[pl], (__nv_bfloat16*)op.p[2] + pl * c_ps, eb, 5, dims, str, wbox, true)) return -1;
+                if (encode_tmap(&P.tmCw[1], (__nv_bfloat16*)op.p[2] + c_ps, eb, 5, dims, str, wbox, true)) return -1;
         }
         if (g->split && !g->out_f32) {
-            WD_REQUIRE(c_ps > 0, "gemm: precise mode with bf16 output needs a C plane stride");
-            for (int pl = 1; pl < 3; ++pl)
-                if (encode_tmap(&P.tmC[pl], (__nv_bfloat16*)op.p[2] + pl * c_ps, eb, 5, dims, str, box, true)) return -1;
+            WD_REQUIRE(c_ps > 0, "gemm: split mode with a 16-bit output needs a C plane stride");
+            if (encode_tmap(&P.tmC[1], (__nv_bfloat16*)op.p[2] + c_ps, eb, 5, dims, str, box, true)) return -1;
         }
+        // direct-store fallback of the split kernel
+        P.out = op.p[2];
+        P.out_ps = c_ps;
+        P.sc0 = sc0; P.sc1 = sc1; P.sc2 = sc2; P.scg = n_groups == 1 ? 0 : scg;
+        P.cols_valid = cols;
         if (n_groups == 1) P.group_cols = 1 << 30;  // never wrap
     } else {
         P.tmC[0] = P.tmA[0];  // unused, keep a valid descriptor for the prefetch

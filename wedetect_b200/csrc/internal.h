@@ -15,7 +15,11 @@ namespace wd {
 extern std::atomic<uint64_t> g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 
-int device_sm_count();
+int device_sm_count();   // of the CURRENT device (cached per device ordinal)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the opt-in is per device, and one process may
+// drive several GPUs.
+cudaError_t ensure_smem_attr(const void* func, int bytes);
 
 bool pdl_enabled();   // WD_NO_PDL=1 turns programmatic dependent launch off (A/B measurements)
 

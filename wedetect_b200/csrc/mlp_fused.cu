@@ -301,11 +301,7 @@ int compile_mlp_fused(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         MlpParams prm;
         int grid;
         int launch(cudaStream_t s) override {
-            static bool attr = false;
-            if (!attr) {
-                WD_CHECK_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem));
-                attr = true;
-            }
+            WD_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(mlp_fused_kernel), kMlpSmem));
             WD_CHECK_CUDA(launch_pdl(mlp_fused_kernel, dim3(grid), dim3(kMThreads), (size_t)kMlpSmem, s, 2, prm));
             WD_CHECK_CUDA(cudaGetLastError());
             count_launch();

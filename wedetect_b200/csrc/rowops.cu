@@ -4,7 +4,8 @@
 //   kept-proposal embedding gather.
 // All activations are NHWC ("rows" = pixels, columns = channels), loads/stores are 8/16-byte vectors,
 // coalesced along channels.  `*_lo` outputs are the low bf16 plane of the bf16x3 precise mode.
-#include "internal.h"
+#include "gemm_params.h"
+#include <cuda_fp16.h>
 #include <functional>
 #include <algorithm>
 #include <math.h>
@@ -17,32 +18,38 @@ struct FnOp : CompiledOp {
     int launch(cudaStream_t s) override { return fn(s); }
 };
 
-// store 4 fp32 values as bf16; ps > 0 = precise mode: three planes p0 + p1 + p2 (plane stride ps elements)
-__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, long long ps, long long idx, float a, float b, float c, float d) {
+// Store fp32 values as a GEMM operand.  ps == 0: one bf16 plane (fast mode).  ps > 0: the parity-grade format of
+// gemm_split.cu, two fp16 planes hi + lo = value * sc (plane stride ps elements; sc = kPlaneScale for activations).
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, long long ps, long long idx, float a, float b, float c, float d, float sc = kPlaneScale) {
     uint2 w;
-    w.x = pack_bf16x2(a, b);
-    w.y = pack_bf16x2(c, d);
-    *reinterpret_cast<uint2*>(hi + idx) = w;
     if (ps) {
-#pragma unroll
-        for (int pl = 1; pl < 3; ++pl) {
-            a -= bf16_lo(w.x); b -= bf16_hi(w.x); c -= bf16_lo(w.y); d -= bf16_hi(w.y);
-            w.x = pack_bf16x2(a, b);
-            w.y = pack_bf16x2(c, d);
-            *reinterpret_cast<uint2*>(hi + pl * ps + idx) = w;
-        }
+        a = sat_f16(a * sc); b = sat_f16(b * sc); c = sat_f16(c * sc); d = sat_f16(d * sc);
+        w.x = pack_f16x2(a, b);
+        w.y = pack_f16x2(c, d);
+        *reinterpret_cast<uint2*>(hi + idx) = w;
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+        w.x = pack_f16x2(a - f0.x, b - f0.y);
+        w.y = pack_f16x2(c - f1.x, d - f1.y);
+        *reinterpret_cast<uint2*>(hi + ps + idx) = w;
+    } else {
+        w.x = pack_bf16x2(a, b);
+        w.y = pack_bf16x2(c, d);
+        *reinterpret_cast<uint2*>(hi + idx) = w;
     }
 }
-__device__ __forceinline__ void store_bf16x1(__nv_bfloat16* hi, long long ps, long long idx, float a) {
-    __nv_bfloat16 h = __float2bfloat16_rn(a);
-    hi[idx] = h;
+__device__ __forceinline__ void store_bf16x1(__nv_bfloat16* hi, long long ps, long long idx, float a, float sc = kPlaneScale) {
     if (ps) {
-#pragma unroll
-        for (int pl = 1; pl < 3; ++pl) {
-            a -= __bfloat162float(h);
-            h = __float2bfloat16_rn(a);
-            hi[pl * ps + idx] = h;
-        }
+        a = sat_f16(a * sc);
+        const __half h = __float2half_rn(a);
+        reinterpret_cast<__half*>(hi)[idx] = h;
+        reinterpret_cast<__half*>(hi)[ps + idx] = __float2half_rn(a - __half2float(h));
+    } else {
+        hi[idx] = __float2bfloat16_rn(a);
     }
 }
 
@@ -443,7 +450,7 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, long long
         const bool inb = iy >= 0 && iy < H && ix >= 0 && ix < W;
         const long long src = (((long long)bi * H + iy) * W + ix) * ld_in + cv * 8;
         const long long dst = r * (9LL * C) + (long long)tap * C + cv * 8;
-        for (int pl = 0; pl < (out_ps ? 3 : 1); ++pl) {
+        for (int pl = 0; pl < (out_ps ? 2 : 1); ++pl) {
             uint4 v = make_uint4(0, 0, 0, 0);
             if (inb) v = *reinterpret_cast<const uint4*>(in + pl * in_ps + src);
             *reinterpret_cast<uint4*>(out + pl * out_ps + dst) = v;
@@ -601,13 +608,13 @@ __global__ void gather_rows_kernel(const float* __restrict__ in, int S, int C, i
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fold_text_kernel(const float* __restrict__ text, int K, int C, int normalize, const float* __restrict__ g,
                                                         const float* __restrict__ hh, const float* __restrict__ logit_scale, const float* __restrict__ bias,
-                                                        __nv_bfloat16* W, long long W_ps, float* bprime) {
+                                                        __nv_bfloat16* W, long long W_ps, float w_scale, float* bprime) {
     __shared__ float red[8];
     __shared__ float bc;
     const int k = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= K) {  // zero padding rows
-        for (int c = threadIdx.x; c < C; c += blockDim.x) store_bf16x1(W, W_ps, (long long)k * C + c, 0.f);
+        for (int c = threadIdx.x; c < C; c += blockDim.x) store_bf16x1(W, W_ps, (long long)k * C + c, 0.f, w_scale);
         if (threadIdx.x == 0) bprime[k] = 0.f;
         return;
     }
@@ -633,7 +640,7 @@ __global__ void __launch_bounds__(256) fold_text_kernel(const float* __restrict_
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float tn = t[c] * inv;
         const float wv = tn * g[c] * es;
-        store_bf16x1(W, W_ps, (long long)k * C + c, wv);
+        store_bf16x1(W, W_ps, (long long)k * C + c, wv, w_scale);
         dot += hh[c] * tn;
     }
     dot = warp_sum(dot);
@@ -681,8 +688,13 @@ __global__ void gather_embed_kernel(GatherEmbedArgs a, const int* __restrict__ k
     const __nv_bfloat16* e = a.emb[lvl] + row * a.C;
     const long long eps_ = a.emb_ps[lvl];
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-        float v = __bfloat162float(e[c]);
-        if (eps_) v += __bfloat162float(e[eps_ + c]) + __bfloat162float(e[2 * eps_ + c]);
+        float v;
+        if (eps_) {   // fp16 hi + lo planes of value * kPlaneScale
+            const __half* eh = reinterpret_cast<const __half*>(e);
+            v = (__half2float(eh[c]) + __half2float(eh[eps_ + c])) * (1.f / kPlaneScale);
+        } else {
+            v = __bfloat162float(e[c]);
+        }
         o[c] = v * g[lvl * a.C + c] + hh[lvl * a.C + c];
     }
 }
@@ -964,11 +976,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
                     __nv_bfloat16* oh;
                     long long ol;
                     int launch(cudaStream_t s) override {
-                        static bool attr = false;
-                        if (!attr) {
-                            WD_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                            attr = true;
-                        }
+                        WD_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(dwconv7_tma_kernel), 227 * 1024));
                         launch_pdl(dwconv7_tma_kernel, dim3(grid), dim3((kDwConsumerWarps + 1) * 32), (size_t)(smem), s, 1, prm);
                         launch_ln_rows(s, prm.yscr, rows, prm.C, prm.C, lw, lb, eps, oh, ol, nullptr, ld_out, 0, 0, 0);
                         WD_CHECK_CUDA(cudaGetLastError());
@@ -1088,11 +1096,7 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             const long long ol = I[30];
             const int smem = 4 * 3 * L * 65 * (int)sizeof(float);
             f->fn = [=](cudaStream_t s) {
-                static bool attr = false;
-                if (!attr) {
-                    WD_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * 32 * 65 * 4));
-                    attr = true;
-                }
+                WD_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(attn_small_kernel), 4 * 3 * 32 * 65 * 4));
                 attn_small_kernel<<<(S * heads + 3) / 4, 128, smem, s>>>(qkv, mask, S, L, heads, ld, scale, oh, ol);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
@@ -1135,8 +1139,9 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             __nv_bfloat16* Wd = (__nv_bfloat16*)P[5];
             const long long Wl = I[30];
             float* bp = (float*)P[6];
+            const float wsc = F[0] != 0.f ? F[0] : 1.f;   // power of two the fp16 hi/lo planes of W' are stored at
             f->fn = [=](cudaStream_t s) {
-                fold_text_kernel<<<Kpad, 256, 0, s>>>(t, K, C, normalize, g, hh, ls, bi, Wd, Wl, bp);
+                fold_text_kernel<<<Kpad, 256, 0, s>>>(t, K, C, normalize, g, hh, ls, bi, Wd, Wl, wsc, bp);
                 WD_CHECK_CUDA(cudaGetLastError());
                 count_launch();
                 return 0;

@@ -57,7 +57,7 @@ def _sample_texts(s):
 class YOLOWorldDetector:
     """Text-conditioned detector facade.  `model_cfg` is the `model=` dict of config/wedetect_*.py."""
 
-    def __init__(self, model_cfg=None, *, size=None, test_cfg=None, device="cuda:0", precise=False, tokenizer=None, cuda_graph=True):
+    def __init__(self, model_cfg=None, *, size=None, test_cfg=None, device="cuda:0", precise=True, tokenizer=None, cuda_graph=True):
         L.load(require_gpu=True)
         self.cuda_graph = bool(cuda_graph) and not os.environ.get("WD_NO_GRAPH")
         self.model_cfg = model_cfg
@@ -243,7 +243,7 @@ class SimpleYOLOWorldDetector:
     `labels`, `scales` and `bias` (the logit_scale / bias of each kept proposal's pyramid level), and `score_text`
     computes the image x class retrieval scores of the last batch on the device (retrieval_metric.py:365-373)."""
 
-    def __init__(self, backbone_size, prompt_dim=768, num_prompts=512, num_proposals=300, *, device="cuda:0", precise=False, extract=False,
+    def __init__(self, backbone_size, prompt_dim=768, num_prompts=512, num_proposals=300, *, device="cuda:0", precise=True, extract=False,
                  cuda_graph=True):
         L.load(require_gpu=True)
         self.cuda_graph = bool(cuda_graph) and not os.environ.get("WD_NO_GRAPH")
@@ -356,7 +356,7 @@ class XLMRobertaLanguageBackbone:
     (an mmengine `.pth` with 'state_dict'), or a state dict / its text slice.  The tokenizer comes from `model_name` (the
     reference reads ../xlm-roberta-{base,large}/) unless one is passed in."""
 
-    def __init__(self, ckpt, *, model_name=None, tokenizer=None, device="cuda:0", precise=False):
+    def __init__(self, ckpt, *, model_name=None, tokenizer=None, device="cuda:0", precise=True):
         L.load(require_gpu=True)
         sd = torch.load(ckpt, map_location="cpu", weights_only=False) if isinstance(ckpt, (str, os.PathLike)) else ckpt
         sd = schema.text_state_dict(sd)

@@ -5,6 +5,8 @@ All activations are NHWC: a feature map is a view [B, H, W, C] whose last stride
 [rows, cols].  Channel slices of a wider buffer (concat fusion) are plain views.
 """
 import functools
+import math
+import os as _os
 
 import torch
 
@@ -12,42 +14,56 @@ from . import _lib as L
 from ._lib import WdOp
 
 
-class P3:
-    """A bf16 tensor view `t` that is plane 0 of a 3-plane precise tensor (value = p0 + p1 + p2); the other
-    planes live `ps` elements further in the same allocation.  ps == 0: an ordinary single-plane tensor."""
+ACT_SCALE = L.ACT_PLANE_SCALE     # power of two every activation written by the library is stored at (fp16 hi/lo planes)
 
-    def __init__(self, t, ps=0):
-        self.t, self.ps = t, int(ps)
+
+def weight_scale(x):
+    """Power of two s with max|x| * s in [8192, 16384): keeps the low plane of a weight matrix out of the fp16 subnormals."""
+    m = float(x.abs().max())
+    if not (m > 0.0) or not math.isfinite(m):
+        return 1.0
+    return 2.0 ** (13 - math.floor(math.log2(m)))
+
+
+class P3:
+    """A 16-bit GEMM operand view.  ps == 0: an ordinary bf16 tensor (fast mode).  ps > 0 (parity-grade mode): `t` is the
+    HIGH plane of an fp16 hi/lo pair, the low plane lives `ps` elements further in the same allocation, and
+    hi + lo = value * scale (scale a power of two: ACT_SCALE for activations, per matrix for weights).
+    torch sees both planes as 16-bit storage of dtype float16 (planes) or bfloat16 (single)."""
+
+    def __init__(self, t, ps=0, scale=1.0):
+        self.t, self.ps, self.scale = t, int(ps), float(scale)
 
     @staticmethod
-    def from_f32(x, device=None):
-        """Split an fp32 tensor into three bf16 planes (test / weight-upload helper)."""
+    def from_f32(x, device=None, scale=None):
+        """Split an fp32 tensor into fp16 hi/lo planes of x * scale (test / weight-upload helper)."""
         x = x.float()
-        base = torch.empty((3,) + tuple(x.shape), dtype=torch.bfloat16)
-        r = x.clone()
-        for i in range(3):
-            base[i] = r.to(torch.bfloat16)
-            r = r - base[i].float()
+        if scale is None:
+            scale = weight_scale(x)
+        y = (x * scale).clamp(-65504.0, 65504.0)
+        base = torch.empty((2,) + tuple(x.shape), dtype=torch.float16)
+        base[0] = y.to(torch.float16)
+        base[1] = (y - base[0].float()).to(torch.float16)
         if device is not None:
             base = base.to(device)
-        return P3(base[0], base.stride(0))
+        return P3(base[0], base.stride(0), scale)
 
     @staticmethod
-    def zeros(shape, device, planes3):
-        if planes3:
-            base = torch.zeros((3,) + tuple(shape), dtype=torch.bfloat16, device=device)
-            return P3(base[0], base.stride(0))
-        return P3(torch.zeros(shape, dtype=torch.bfloat16, device=device), 0)
+    def zeros(shape, device, planes, scale=ACT_SCALE):
+        if planes:
+            base = torch.zeros((2,) + tuple(shape), dtype=torch.float16, device=device)
+            return P3(base[0], base.stride(0), scale)
+        return P3(torch.zeros(shape, dtype=torch.bfloat16, device=device), 0, 1.0)
 
     def value(self):
-        """fp32 reconstruction (sum of planes)."""
+        """fp32 reconstruction."""
         if not self.ps:
             return self.t.float()
-        planes = [self.t.as_strided(self.t.shape, self.t.stride(), self.t.storage_offset() + i * self.ps) for i in range(3)]
-        return planes[0].float() + planes[1].float() + planes[2].float()
+        lo = self.t.as_strided(self.t.shape, self.t.stride(), self.t.storage_offset() + self.ps)
+        return (self.t.float() + lo.float()) / self.scale
 
     def view(self, fn):
-        return P3(fn(self.t), self.ps)
+        return P3(fn(self.t), self.ps, self.scale)
 
 
 def _tp(x):
@@ -56,8 +72,17 @@ def _tp(x):
     return (x.t, x.ps) if isinstance(x, P3) else (x, 0)
 
 
+def _sc(x):
+    return x.scale if isinstance(x, P3) and x.ps else 1.0
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def _chk16(t, ps, name):
+    """16-bit operand: fp16 planes (ps > 0) or a single bf16 plane."""
+    _chk(t, torch.float16 if ps else torch.bfloat16, name)
 
 
 def _chk(t, dtype, name):
@@ -81,9 +106,12 @@ def pick_tile(W, H, B):
     return best[1]
 
 
-def pick_block_n(N, out_f32=False, split=False):
-    """Tile width minimising padded columns, weighted by the relative MMA efficiency of each width."""
-    cands = ((128, 1.15), (64, 1.5)) if split else ((256, 1.0), (128, 1.15), (64, 1.5))
+def pick_block_n(N, out_f32=False, split=False, m_tiles=2):
+    """Tile width minimising padded columns, weighted by the relative MMA efficiency of each width.
+    Split (fp16 hi/lo) mode runs 256-wide tiles only as CTA pairs, which need >= 2 m-tiles."""
+    cands = ((256, 1.0), (128, 1.15), (64, 1.5))
+    if split:
+        cands = ((256, 1.0), (128, 1.1), (64, 1.6)) if m_tiles >= 2 else ((128, 1.1), (64, 1.6))
     best = None
     for bn, pen in cands:
         cost = -(-N // bn) * bn * pen
@@ -92,21 +120,26 @@ def pick_block_n(N, out_f32=False, split=False):
     return best[1]
 
 
+# fp16 hi/lo mode: 64-wide k-blocks a TMEM accumulator lives for before its partial sum moves to fp32 registers (the tensor
+# pipe truncates on every accumulate; see gemm_split.cu).  Measured on B200 against the fp32 oracle: DESIGN.md §6.
+SPLIT_LBLK = int(_os.environ.get("WD_SPLIT_LBLK", "1"))
+
 # activations for which the fast path must use the exact formula (debug / accuracy studies): subset of {ACT_SILU, ACT_GELU}
-import os as _os
 NO_WARP_STORE = 1 if _os.environ.get("WD_NO_WARP_STORE") == "1" else 0   # A/B switch: warpgroup-wide epilogue stores
 EXACT_ACT = {dict(silu=L.ACT_SILU, gelu=L.ACT_GELU)[a] for a in _os.environ.get("WD_EXACT_ACT", "").split(",") if a in ("silu", "gelu")}
 
 
 def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, block_n=None, out_f32=False,
              act=L.ACT_NONE, bias=None, gamma=None, resid=None, ld_res=0, alpha=1.0, group_cols=None, n_groups=1,
-             c_gstride=0, dfl=False, a_ps=0, w_ps=0, c_ps=0, r_ps=0, group_valid=0, k_valid=0, bk_valid=0, in_wh=None):
+             c_gstride=0, dfl=False, a_ps=0, w_ps=0, c_ps=0, r_ps=0, group_valid=0, k_valid=0, bk_valid=0, in_wh=None,
+             acc_scale=1.0, lblk=None):
     op = WdOp()
     op.kind = L.OP_GEMM
     split = bool(a_ps) and bool(w_ps)
-    assert bool(a_ps) == bool(w_ps), "precise mode needs 3-plane A and W"
+    assert bool(a_ps) == bool(w_ps), "fp16 hi/lo mode needs two-plane A and W"
     if block_n is None:
-        block_n = 64 if dfl else pick_block_n(N, out_f32, split)
+        m_tiles = -(-dims[0] // tile[0]) * -(-dims[1] // tile[1]) * -(-dims[2] // tile[2])
+        block_n = 64 if dfl else pick_block_n(N, out_f32, split, m_tiles)
     I = op.i
     I[0], I[1], I[2] = dims
     I[3], I[4], I[5] = tile
@@ -127,9 +160,11 @@ def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, 
     I[37] = NO_WARP_STORE
     if in_wh is not None:
         I[38], I[39] = in_wh
-    I[30] = 3 if split else 1
+    I[30] = 2 if split else 1
     I[31], I[32], I[33], I[34] = a_ps, w_ps, c_ps, r_ps
+    I[40] = SPLIT_LBLK if lblk is None else lblk
     op.f[0] = alpha
+    op.f[1] = acc_scale
     for k, t in enumerate((A, W, C, bias, gamma, resid)):
         op.p[k] = _ptr(t)
     return op
@@ -143,8 +178,10 @@ def _flat_strides(ld, rows):
 def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, dfl=False):
     """C[M, N] = epi(A[M, K] @ W[N, K]^T); A / C / resid may be column slices of wider row-major buffers.
     A, W (and bf16 C / resid) may be P3 three-plane tensors (precise mode)."""
+    acc_scale = 1.0 / (_sc(A) * _sc(W))
+    assert _sc(C) in (1.0, ACT_SCALE) and _sc(resid) in (1.0, ACT_SCALE), "fp16 hi/lo outputs / residuals live at ACT_SCALE"
     (A, a_ps), (W, w_ps), (C, c_ps), (resid, r_ps) = _tp(A), _tp(W), _tp(C), _tp(resid)
-    _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
+    _chk16(A, a_ps, "A"); _chk16(W, w_ps, "W")
     M, K = A.shape
     N = W.shape[0]
     assert W.shape[1] == K and K % 8 == 0, (W.shape, K)
@@ -163,14 +200,16 @@ def linear(A, W, C, *, bias=None, gamma=None, resid=None, alpha=1.0, act=L.ACT_N
     return gemm_raw(A=A, W=W, C=C, dims=(M, 1, 1), tile=(128, 1, 1), Kc=Kc, N=N, a_strides=_flat_strides(A.stride(0), M),
                     ldb=W.stride(0), c_strides=c_str, block_n=block_n, out_f32=out_f32, act=act, bias=bias, gamma=gamma,
                     resid=resid, ld_res=ld_res, alpha=alpha, dfl=dfl, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps, r_ps=r_ps,
-                    k_valid=K, bk_valid=K)
+                    k_valid=K, bk_valid=K, acc_scale=acc_scale)
 
 
 def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_n=None, stride=1):
     """3x3 pad-1 convolution (stride 1 or 2) as 9 shifted TMA brick loads.  A [B,H,W,Cin], W [N, 9*pad64(Cin)] (tap-major).
     stride 2: the A tensor map walks the input with element strides 2 (no im2col); C is [B, ceil(H/2), ceil(W/2), N]."""
+    acc_scale = 1.0 / (_sc(A) * _sc(W))
+    assert _sc(C) in (1.0, ACT_SCALE) and _sc(resid) in (1.0, ACT_SCALE), "fp16 hi/lo outputs / residuals live at ACT_SCALE"
     (A, a_ps), (W, w_ps), (C, c_ps), (resid, r_ps) = _tp(A), _tp(W), _tp(C), _tp(resid)
-    _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
+    _chk16(A, a_ps, "A"); _chk16(W, w_ps, "W")
     B, H, Wd, Cin = A.shape
     N = W.shape[0]
     Kc = (Cin + 63) // 64 * 64
@@ -187,15 +226,16 @@ def conv3x3(A, W, C, *, bias=None, resid=None, alpha=1.0, act=L.ACT_NONE, block_
                     a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
                     c_strides=(C.stride(2), C.stride(1), C.stride(0)), block_n=block_n, out_f32=C.dtype == torch.float32,
                     act=act, bias=bias, resid=resid, ld_res=ld_res, alpha=alpha, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps, r_ps=r_ps,
-                    in_wh=(Wd, H) if stride == 2 else None)
+                    in_wh=(Wd, H) if stride == 2 else None, acc_scale=acc_scale)
 
 
 def deconv2x2(A, W, C, bias2):
     """ConvTranspose2d(k=2, s=2) as two GEMMs (dy = 0, 1) whose TMA stores scatter into the 2x upsampled map.
     A [B,H,W,Cin]; W [4*Co, Cin] rows ordered (dy, dx, co); C [B,2H,2W,Co] (may be a channel slice);
     bias2 f32 [2*Cg] = bias repeated for dx = 0, 1."""
+    acc_scale = 1.0 / (_sc(A) * _sc(W))
     (A, a_ps), (W, w_ps), (C, c_ps) = _tp(A), _tp(W), _tp(C)
-    _chk(A, torch.bfloat16, "A"); _chk(W, torch.bfloat16, "W")
+    _chk16(A, a_ps, "A"); _chk16(W, w_ps, "W")
     B, H, Wd, Cin = A.shape
     Co = C.shape[3]
     Cg = W.shape[0] // 4          # rows per (dy, dx) group, = pad64(Co) with zero rows beyond Co
@@ -209,7 +249,8 @@ def deconv2x2(A, W, C, bias2):
         ops.append(gemm_raw(A=A, W=Wdy, C=Cdy, dims=(Wd, H, B), tile=pick_tile(Wd, H, B), Kc=Kc, k_valid=Cin, bk_valid=Cin,
                             N=2 * Cg, a_strides=(A.stride(2), A.stride(1), A.stride(0)), ldb=W.stride(0),
                             c_strides=(2 * C.stride(2), 2 * C.stride(1), C.stride(0)), group_cols=Cg, group_valid=Co,
-                            n_groups=2, c_gstride=C.stride(2), bias=bias2, out_f32=False, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps))
+                            n_groups=2, c_gstride=C.stride(2), bias=bias2, out_f32=False, a_ps=a_ps, w_ps=w_ps, c_ps=c_ps,
+                            acc_scale=acc_scale))
     return ops
 
 
@@ -316,7 +357,7 @@ def stem_patch(img, out, scale=1.0):
 
 def im2col_s2(x, out):
     (x, x_ps), (out, o_ps) = _tp(x), _tp(out)
-    _chk(x, torch.bfloat16, "x")
+    _chk16(x, x_ps, "x")
     B, H, W, C = x.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     assert out.shape == (B * Ho * Wo, 9 * C) and out.is_contiguous()
@@ -392,6 +433,8 @@ def gather_rows(x, out, S, row_stride):
 
 
 def fold_text(text, bn_g, bn_h, logit_scale, bias, Wout, bout, normalize):
+    """Wout (a P3 in parity-grade mode) is written at Wout.scale; the similarity GEMM undoes it through its acc_scale."""
+    w_scale = _sc(Wout)
     Wout, w_ps = _tp(Wout)
     K, C = text.shape
     assert text.dtype == torch.float32 and text.is_contiguous() and Wout.shape[1] == C and Wout.is_contiguous()
@@ -399,6 +442,7 @@ def fold_text(text, bn_g, bn_h, logit_scale, bias, Wout, bout, normalize):
     op.kind = L.OP_FOLD_TEXT
     op.i[0], op.i[1], op.i[2], op.i[3] = K, C, 1 if normalize else 0, Wout.shape[0]
     op.i[30] = w_ps
+    op.f[0] = w_scale
     for k, t in enumerate((text, bn_g, bn_h, logit_scale, bias, Wout, bout)):
         op.p[k] = _ptr(t)
     return op

@@ -21,32 +21,32 @@ from . import _lib as L
 from . import ops, schema
 from .ops import P3
 
-BF16, F32 = torch.bfloat16, torch.float32
+F32 = torch.float32
 
 
 class Act:
-    """A bf16 activation [rows, C] with NHWC geometry; `ps` > 0 = three-plane precise tensor (ops.P3)."""
+    """A 16-bit activation [rows, C] with NHWC geometry; `ps` > 0 = fp16 hi/lo planes at `scale` (ops.P3), else bf16."""
 
-    def __init__(self, t, ps, B, H, W):
-        self.t, self.ps, self.B, self.H, self.W = t, ps, B, H, W
+    def __init__(self, t, ps, B, H, W, scale=1.0):
+        self.t, self.ps, self.B, self.H, self.W, self.scale = t, ps, B, H, W, scale
 
     @property
     def C(self):
         return self.t.shape[1]
 
     def cols(self, c0, c1):
-        return Act(self.t[:, c0:c1], self.ps, self.B, self.H, self.W)
+        return Act(self.t[:, c0:c1], self.ps, self.B, self.H, self.W, self.scale)
 
     @property
     def p3(self):
-        return P3(self.t, self.ps)
+        return P3(self.t, self.ps, self.scale)
 
     @property
     def p3_4d(self):
         t = self.t
         ld = t.stride(0)
         v = t.as_strided((self.B, self.H, self.W, t.shape[1]), (self.H * self.W * ld, self.W * ld, ld, 1), t.storage_offset())
-        return P3(v, self.ps)
+        return P3(v, self.ps, self.scale)
 
     def value(self):
         return self.p3.value()
@@ -86,13 +86,13 @@ class VisionPlan:
 
     def _act(self, name, B, H, W, C):
         q = P3.zeros((B * H * W, C), self.dev, self.precise)
-        a = Act(q.t, q.ps, B, H, W)
+        a = Act(q.t, q.ps, B, H, W, q.scale)
         self.bufs[name] = a
         return a
 
     def _view_act(self, scratch, rows, C, B, H, W):
         """A [rows, C] activation carved out of a flat scratch P3 (all planes keep the scratch's plane stride)."""
-        return Act(scratch.t[: rows * C].view(rows, C), scratch.ps, B, H, W)
+        return Act(scratch.t[: rows * C].view(rows, C), scratch.ps, B, H, W, scratch.scale)
 
     def _mat(self, name):
         return self.Wt.mat(name)
@@ -235,7 +235,10 @@ class VisionPlan:
             self._conv3x3(h1, q + "1.w", h2, bias=W_[q + "1.b"], act=L.ACT_SILU)
             self._linear(h2, q + "2.w", emb, bias=W_[q + "2.b"])
             # similarity GEMM against the folded (BN * normalised text * exp(logit_scale)) matrix
-            sw = P3.zeros((self.K_pad, schema.EMBED_DIM), self.dev, self.precise)
+            # folded similarity matrix: |w| <= max|g| * exp(logit_scale) * max|text element| (<= 1 for normalised class texts)
+            tmax = float(W_["prompts"].abs().max()) if self.uni else 1.0
+            sw = P3.zeros((self.K_pad, schema.EMBED_DIM), self.dev, self.precise,
+                          scale=ops.weight_scale(torch.tensor(W_[f"head.contrast.{l}.wmax"] * max(tmax, 1e-30))))
             sb = torch.zeros(self.K_pad, dtype=F32, device=self.dev)
             lg = self._f32(f"head{l}.logits", M, self.K_pad)
             self.ops.append(ops.linear(emb.p3, sw, lg, bias=sb))

@@ -28,7 +28,7 @@ class RetrievalScorer:
     then runs right behind the detector on the same stream) or buffers owned here and filled by `load()`.
     """
 
-    def __init__(self, text_embedding, B, P, *, device="cuda:0", precise=False, emb=None, scale=None, bias=None, counts=None):
+    def __init__(self, text_embedding, B, P, *, device="cuda:0", precise=True, emb=None, scale=None, bias=None, counts=None):
         L.load(require_gpu=True)
         self.dev = torch.device(device)
         K, C = text_embedding.shape
@@ -43,11 +43,14 @@ class RetrievalScorer:
         assert self.emb.shape == (B, P, C) and self.scale.shape == (B, P) and self.bias.shape == (B, P) and self.counts.shape == (B,)
         self.text_f32 = torch.zeros(self.K_pad, C, **f32)
         self.text_f32[:K] = text_embedding.to(self.dev, torch.float32)
-        self.text = P3.zeros((self.K_pad, C), self.dev, precise)
+        if precise:   # fp16 hi/lo planes at the matrix's own power-of-two scale (split on the host, once)
+            self.text = P3.from_f32(self.text_f32.cpu(), self.dev)
+        else:
+            self.text = P3.zeros((self.K_pad, C), self.dev, False)
+            L.Program([ops.cast_bf16(self.text_f32, self.text)]).run(torch.cuda.current_stream().cuda_stream)
         self.rows = P3.zeros((B * P, C), self.dev, precise)
         self.z = torch.zeros(B * P, self.K_pad, **f32)
         self.scores = torch.zeros(B, K, **f32)
-        L.Program([ops.cast_bf16(self.text_f32, self.text)]).run(torch.cuda.current_stream().cuda_stream)
         self.program = L.Program([
             ops.scale_rows(self.emb, self.rows, scale=self.scale, counts=self.counts),
             ops.linear(self.rows, self.text, self.z),
@@ -157,7 +160,7 @@ def save_corpus(path, corpus):
     torch.save({"image_embedding": corpus["image_embedding"], "text_embedding": corpus["text_embedding"]}, path)
 
 
-def score_saved(pred, *, device="cuda:0", batch_size=64, model="wedetect", precise=False):
+def score_saved(pred, *, device="cuda:0", batch_size=64, model="wedetect", precise=True):
     """Image x class scores [N, K] for a saved corpus (the loop body of retrieval_metric.py:365-373, batched on the GPU).
     model == 'hqclip': plain sigmoid(logits) (no scale / bias), as the reference's switch at :369-370."""
     items = pred["image_embedding"]

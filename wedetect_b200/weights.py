@@ -1,4 +1,4 @@
-"""Load-time weight preparation (host, once): BN folding, layout changes, bf16 (hi/lo) conversion, upload.
+"""Load-time weight preparation (host, once): BN folding, layout changes, fp16 hi/lo (or bf16) conversion, upload.
 
 Input: a checkpoint dict in the mmengine key layout (schema.normalize_state_dict).  Output: a flat dict of
 device tensors consumed by plan.py.  Transformations (all exact algebra, done in fp64 on the CPU):
@@ -20,13 +20,13 @@ from .ops import P3
 
 
 class DeviceWeights:
-    def __init__(self, device, precise=False):
+    def __init__(self, device, precise=True):
         self.device = device
         self.precise = precise
         self.t = {}
 
     def put_mat(self, name, w64):
-        """GEMM B operand: bf16, or three bf16 planes (p0 + p1 + p2 ~ fp32) in precise mode."""
+        """GEMM B operand: fp16 hi/lo planes at the matrix's own power-of-two scale (parity-grade mode), or bf16 (fast mode)."""
         w32 = w64.float().contiguous()
         self.t[name] = P3.from_f32(w32, self.device) if self.precise else P3(w32.to(torch.bfloat16).to(self.device), 0)
 
@@ -64,7 +64,7 @@ def _taps_flat(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
 
-def prepare_vision(sd, size, device, *, input_format="f32_rgb", precise=False):
+def prepare_vision(sd, size, device, *, input_format="f32_rgb", precise=True):
     cfg = schema.SIZES[size]
     W = DeviceWeights(device, precise)
     bb = "backbone.image_model.model."
@@ -144,6 +144,9 @@ def prepare_vision(sd, size, device, *, input_format="f32_rgb", precise=False):
         W.put_f32(f"head.contrast.{l}.h", h)
         W.put_f32(f"head.contrast.{l}.logit_scale", sd[c + "logit_scale"].reshape(1))
         W.put_f32(f"head.contrast.{l}.bias", sd[c + "bias"].reshape(1))
+        # bound of |folded similarity weight| for unit-norm text rows: max|g| * exp(logit_scale); plan.py picks the power of two
+        # the fp16 hi/lo planes of the folded matrix are stored at from it
+        W.t[f"head.contrast.{l}.wmax"] = float(g.abs().max() * torch.exp(sd[c + "logit_scale"].double().reshape(-1)[0]))
         g_all.append(g)
         h_all.append(h)
     W.put_f32("head.contrast.g_all", torch.cat(g_all))
@@ -153,7 +156,7 @@ def prepare_vision(sd, size, device, *, input_format="f32_rgb", precise=False):
     return W
 
 
-def prepare_text(sd, size, device, *, precise=False):
+def prepare_text(sd, size, device, *, precise=True):
     t = schema.TEXT[schema.SIZES[size]["text"]]
     W = DeviceWeights(device, precise)
     tm = "backbone.text_model.model."
