@@ -1,0 +1,128 @@
+// epi_split.cuh — fp32-grade epilogue arithmetic of gemm_split.cu on packed fp32 pairs (FFMA2 / FMUL2 / FADD2).
+//
+// The epilogue warps of the parity-grade GEMM are bound by the FMA pipe (one 3-operand FFMA per 2 cycles per scheduler):
+// the library erff / expf / division forms cost ~40 issue slots per element, 20 000 cycles per 128 x 256 tile against
+// 12 000 cycles of UMMA.  Everything here works on two columns per instruction and keeps the results within ~1 ulp of the
+// fp32 forms the reference evaluates (torch erf-GELU / SiLU, mm_backbone.py:120, yolo_world_pafpn.py:40-68).
+#pragma once
+#include "epi_math.cuh"
+#include <cuda_fp16.h>
+
+namespace wd {
+
+__device__ __forceinline__ uint64_t splat2(float c) { return pk2(c, c); }
+// -x on both halves; ptxas folds the negations into the consuming FFMA2's operand modifiers
+__device__ __forceinline__ uint64_t neg2(uint64_t x) {
+    uint64_t y;
+    asm("{.reg .f32 lo, hi; mov.b64 {lo, hi}, %1; neg.f32 lo, lo; neg.f32 hi, hi; mov.b64 %0, {lo, hi};}" : "=l"(y) : "l"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// erf on a pair.  N. Juffa's two-interval erff (max error < 1 ulp on each interval), both intervals evaluated with packed
+// FMAs and selected per element.  |z| > 0.927734375: erf = 1 - exp(t (p(t) - 1)) with the polynomial's coefficients
+// pre-multiplied by log2(e), so the exponential is one MUFU.EX2 (its 2^-22 relative error meets exp(.) <= 0.19 there).
+__device__ __forceinline__ uint64_t erf2(uint64_t z) {
+    constexpr float kL2E = 1.4426950408889634f;
+    float z0, z1;
+    upk2(z, z0, z1);
+    const float t0 = fabsf(z0), t1 = fabsf(z1);
+    const uint64_t t = pk2(t0, t1), s = mul2(z, z);
+    // large |z|
+    uint64_t r = fma2(splat2(-1.72853470e-5f * kL2E), t, splat2(3.83197126e-4f * kL2E));
+    const uint64_t u = fma2(splat2(-3.88396438e-3f * kL2E), t, splat2(2.42546219e-2f * kL2E));
+    r = fma2(r, s, u);
+    r = fma2(r, t, splat2(-1.06777877e-1f * kL2E));
+    r = fma2(r, t, splat2(-6.34846687e-1f * kL2E));
+    r = fma2(r, t, splat2((-1.28717512e-1f - 1.0f) * kL2E));
+    r = mul2(r, t);
+    float r0, r1;
+    upk2(r, r0, r1);
+    const uint64_t big = fma2(pk2(ex2_approx(r0), ex2_approx(r1)), splat2(-1.f), splat2(1.f));   // 1 - exp(.)
+    // small |z|: z + z * q(z^2)
+    uint64_t q = fma2(splat2(-5.96761703e-4f), s, splat2(4.99119423e-3f));
+    q = fma2(q, s, splat2(-2.67681349e-2f));
+    q = fma2(q, s, splat2(1.12819925e-1f));
+    q = fma2(q, s, splat2(-3.76125336e-1f));
+    q = fma2(q, s, splat2(1.28379166e-1f));
+    q = fma2(q, z, z);
+    float b0, b1, q0, q1;
+    upk2(big, b0, b1);
+    upk2(q, q0, q1);
+    return pk2(t0 > 0.927734375f ? copysignf(b0, z0) : q0, t1 > 0.927734375f ? copysignf(b1, z1) : q1);
+}
+
+// exact-form activations on a pair
+template <int ACT>
+__device__ __forceinline__ uint64_t act2_exact(uint64_t x) {
+    if constexpr (ACT == WD_ACT_GELU) {
+        // 0.5 x (1 + erf(x / sqrt 2))
+        const uint64_t h = mul2(x, splat2(0.5f));
+        return fma2(h, erf2(mul2(x, splat2(0.70710678118654752440f))), h);
+    } else if constexpr (ACT == WD_ACT_SILU) {
+        // x / (1 + exp(-x)): MUFU.EX2, MUFU.RCP and one Newton step on the reciprocal
+        float m0, m1;
+        upk2(mul2(x, splat2(-1.4426950408889634f)), m0, m1);
+        const uint64_t d = add2(pk2(ex2_approx(fminf(m0, 126.f)), ex2_approx(fminf(m1, 126.f))), splat2(1.f));
+        float d0, d1;
+        upk2(d, d0, d1);
+        uint64_t r = pk2(rcp_approx(d0), rcp_approx(d1));
+        r = fma2(r, fma2(neg2(d), r, splat2(1.f)), r);
+        return mul2(x, r);
+    } else if constexpr (ACT == WD_ACT_RELU) {
+        float a, b;
+        upk2(x, a, b);
+        return pk2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+    } else {
+        return x;
+    }
+}
+
+// a2[j] <- gamma[n] * act(a2[j] * (1 + comp) * s + bias[n]) over NC columns starting at n_base (two columns per element of a2).
+// comp undoes the tensor pipe's truncating accumulation (a measured, data-independent shrink of each TMEM block sum); columns
+// at or beyond N get no bias / gamma (they are never stored).
+template <int NC, int ACT>
+__device__ __forceinline__ void split_epi_math(uint64_t* a2, float comp, float s, const float* __restrict__ bias, const float* __restrict__ gamma, int n_base,
+                                               int N) {
+    const uint64_t comp2 = splat2(comp), s2 = splat2(s);
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+        const int n = n_base + j;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        uint64_t x0 = fma2(a2[j / 2], comp2, a2[j / 2]), x1 = fma2(a2[j / 2 + 1], comp2, a2[j / 2 + 1]);
+        x0 = act2_exact<ACT>(fma2(x0, s2, pk2(b4.x, b4.y)));
+        x1 = act2_exact<ACT>(fma2(x1, s2, pk2(b4.z, b4.w)));
+        if (gamma && n < N) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n));
+            x0 = mul2(x0, pk2(g4.x, g4.y));
+            x1 = mul2(x1, pk2(g4.z, g4.w));
+        }
+        a2[j / 2] = x0;
+        a2[j / 2 + 1] = x1;
+    }
+}
+
+// fp16 hi / lo planes of a pair (already multiplied by the plane scale): hi saturates at +-65504, lo = fp16(v - hi)
+__device__ __forceinline__ uint32_t cvt_h2_sat(uint64_t v) {
+    float a, b;
+    upk2(v, a, b);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source operand -> upper half
+    return r;
+}
+__device__ __forceinline__ uint64_t h2_to_f2(uint32_t h) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    return pk2(f.x, f.y);
+}
+
+}  // namespace wd

@@ -21,8 +21,7 @@
 //
 // Reference arithmetic replaced: see include/wedetect_b200.h (WD_OP_GEMM).
 #include "gemm_params.h"
-#include "epi_math.cuh"
-#include <cuda_fp16.h>
+#include "epi_split.cuh"
 
 namespace wd {
 
@@ -46,32 +45,6 @@ struct SCfg {
 
 // UMMA instruction descriptor (kind::f16): fp32 accumulate, fp16 A/B (format 0), both K-major
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
-__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
-
-// v[j] = gamma[n] * act(v[j] * s + bias[n]) over CH columns starting at n_base (exact activation forms; columns >= N: no bias / gamma)
-template <int CH, int ACT>
-__device__ __forceinline__ void split_bias_act(float* v, float s, const float* __restrict__ bias, const float* __restrict__ gamma, int n_base, int N) {
-#pragma unroll
-    for (int j = 0; j < CH; j += 4) {
-        const int n = n_base + j;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
-        v[j + 0] = act_fn<ACT, false>(fmaf(v[j + 0], s, b4.x));
-        v[j + 1] = act_fn<ACT, false>(fmaf(v[j + 1], s, b4.y));
-        v[j + 2] = act_fn<ACT, false>(fmaf(v[j + 2], s, b4.z));
-        v[j + 3] = act_fn<ACT, false>(fmaf(v[j + 3], s, b4.w));
-        if (gamma && n < N) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n));
-            v[j + 0] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
-        }
-    }
-}
 
 template <int BN, typename OutT, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid_constant__ GemmParams p) {
@@ -308,10 +281,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                     aphase ^= 1;
                 }
             }
-            float acc[WCOLS];
-#pragma unroll
-            for (int j = 0; j < WCOLS / 2; ++j) upk2(acc2[j], acc[2 * j], acc[2 * j + 1]);
-
             // ---- this thread's output row ----
             const int i0 = r % p.E0, i1 = (r / p.E0) % p.E1, i2 = r / (p.E0 * p.E1);
             const int d0 = o0 + i0, d1 = o1 + i1, d2 = o2 + i2;
@@ -321,13 +290,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
             if (p.epi_mode == 1) {
                 // ---- DFL epilogue (BN == N == 64): softmax over 16 bins x 4 sides, expectation (yolo_world_head.py:283-291) ----
                 if constexpr (BN == 64) {
+                    float acc[64];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) upk2(acc2[j], acc[2 * j], acc[2 * j + 1]);
                     float out4[4];
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
                         float mx = -INFINITY;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            acc[s * 16 + j] = fmaf(acc[s * 16 + j], p.acc_scale, __ldg(p.bias + s * 16 + j));
+                            const float a = fmaf(acc[s * 16 + j], p.trunc_comp, acc[s * 16 + j]);
+                            acc[s * 16 + j] = fmaf(a, p.acc_scale, __ldg(p.bias + s * 16 + j));
                             mx = fmaxf(mx, acc[s * 16 + j]);
                         }
                         float den = 0.f, num = 0.f;
@@ -344,22 +317,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                 continue;
             }
 
-            // first row of this warp's quarter inside the tile brick (per-warp TMA stores)
-            const int qr = quarter * 32;
-            const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
-            // ---- acc = gamma * act(acc * acc_scale + bias) over the warpgroup's columns (column guards inside) ----
+            // ---- acc = gamma * act(acc * (1 + trunc_comp) * acc_scale + bias) over the warpgroup's columns, two per instruction ----
             {
                 const int nb = n_blk * BN + wg * WCOLS;
                 switch (p.act) {
-                    case WD_ACT_RELU: split_bias_act<WCOLS, WD_ACT_RELU>(acc, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
-                    case WD_ACT_SILU: split_bias_act<WCOLS, WD_ACT_SILU>(acc, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
-                    case WD_ACT_GELU: split_bias_act<WCOLS, WD_ACT_GELU>(acc, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
-                    default: split_bias_act<WCOLS, WD_ACT_NONE>(acc, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                    case WD_ACT_RELU: split_epi_math<WCOLS, WD_ACT_RELU>(acc2, p.trunc_comp, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                    case WD_ACT_SILU: split_epi_math<WCOLS, WD_ACT_SILU>(acc2, p.trunc_comp, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                    case WD_ACT_GELU: split_epi_math<WCOLS, WD_ACT_GELU>(acc2, p.trunc_comp, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                    default: split_epi_math<WCOLS, WD_ACT_NONE>(acc2, p.trunc_comp, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
                 }
             }
+            // first row of this warp's quarter inside the tile brick (per-warp TMA stores)
+            const int qr = quarter * 32;
+            const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
+            const uint64_t alpha2 = splat2(p.alpha);
 #pragma unroll
             for (int c = 0; c < WCOLS / CH; ++c) {
-                float* v = acc + c * CH;
+                uint64_t* v2 = acc2 + c * (CH / 2);
                 const int n_base = n_blk * BN + wg * WCOLS + c * CH;
                 if (n_base >= p.N) continue;   // warp-uniform: nothing of this chunk exists
                 // ---- v += resid * alpha ----
@@ -369,10 +343,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                     for (int j = 0; j < CH; j += 4) {
                         if (n_base + j < p.N) {
                             const float4 x = *reinterpret_cast<const float4*>(rp + j);
-                            v[j + 0] = fmaf(p.alpha, x.x, v[j + 0]);
-                            v[j + 1] = fmaf(p.alpha, x.y, v[j + 1]);
-                            v[j + 2] = fmaf(p.alpha, x.z, v[j + 2]);
-                            v[j + 3] = fmaf(p.alpha, x.w, v[j + 3]);
+                            v2[j / 2] = fma2(alpha2, pk2(x.x, x.y), v2[j / 2]);
+                            v2[j / 2 + 1] = fma2(alpha2, pk2(x.z, x.w), v2[j / 2 + 1]);
                         }
                     }
                 } else if (p.resid_dtype == 1 && row_ok) {
@@ -382,26 +354,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                     for (int j = 0; j < CH; j += 8) {
                         if (n_base + j < p.N) {
                             const uint4 x = *reinterpret_cast<const uint4*>(rp + j);
-                            const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
-                            float xs[8];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 f = unpack_h2(xw[q]);
-                                xs[2 * q] = f.x;
-                                xs[2 * q + 1] = f.y;
-                            }
+                            uint64_t xs[4] = {h2_to_f2(x.x), h2_to_f2(x.y), h2_to_f2(x.z), h2_to_f2(x.w)};
                             if (p.resid_ps) {
                                 const uint4 y = *reinterpret_cast<const uint4*>(rp + p.resid_ps + j);
-                                const uint32_t yw[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float2 f = unpack_h2(yw[q]);
-                                    xs[2 * q] += f.x;
-                                    xs[2 * q + 1] += f.y;
-                                }
+                                xs[0] = add2(xs[0], h2_to_f2(y.x)); xs[1] = add2(xs[1], h2_to_f2(y.y));
+                                xs[2] = add2(xs[2], h2_to_f2(y.z)); xs[3] = add2(xs[3], h2_to_f2(y.w));
                             }
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) v[j + q] = fmaf(p.alpha, xs[q], v[j + q]);
+                            for (int q = 0; q < 4; ++q) v2[j / 2 + q] = fma2(alpha2, xs[q], v2[j / 2 + q]);
                         }
                     }
                 }
@@ -418,24 +378,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                             uint32_t ww[4];
 #pragma unroll
                             for (int h = 0; h < 4; ++h) {
-                                float a = v[q * 8 + 2 * h], b = v[q * 8 + 2 * h + 1];
-                                if (pl == 0) {
-                                    a = clamp_h(a * kPlaneScale);
-                                    b = clamp_h(b * kPlaneScale);
-                                }
-                                ww[h] = pack_h2(a, b);
-                                if (pl == 0) {   // keep the remainder for the low plane
-                                    const float2 f = unpack_h2(ww[h]);
-                                    v[q * 8 + 2 * h] = a - f.x;
-                                    v[q * 8 + 2 * h + 1] = b - f.y;
-                                }
+                                uint64_t a = v2[q * 4 + h];
+                                if (pl == 0) a = mul2(a, splat2(kPlaneScale));
+                                ww[h] = cvt_h2_sat(a);
+                                if (pl == 0) v2[q * 4 + h] = add2(a, neg2(h2_to_f2(ww[h])));   // the remainder goes to the low plane
                             }
                             w[q] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            w[q] = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+                        for (int q = 0; q < 8; ++q) {
+                            float f0, f1, f2, f3;
+                            upk2(v2[q * 2], f0, f1);
+                            upk2(v2[q * 2 + 1], f2, f3);
+                            w[q] = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
+                        }
                     }
                     if (p.warp_store) {
                         if (lane == 0) tma_store_wait_read<0>();   // the staging buffer is no longer being read by the previous store

@@ -524,6 +524,10 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     WD_REQUIRE(!g->split || (a_ps > 0 && b_ps > 0), "gemm: split mode needs plane strides for A and B");
     P.acc_scale = op.f[1] != 0.f ? op.f[1] : 1.f;
     P.lblk = I[40] > 0 ? I[40] : 1;
+    // Measured on B200 (tools/trunc_probe.py, profiles/trunc_probe_r02.json): with the three products of a 64-wide k-block
+    // accumulated in TMEM the block sum comes out 8.9e-8 (~1.5 * 2^-24) too small relative to an exact sum, independent of K
+    // and of the data distribution (2.8e-7 for two blocks, 6.8e-7 for four).  I[41] = 1 turns the compensation off.
+    P.trunc_comp = I[41] ? 0.f : (P.lblk == 1 ? 8.9e-8f : P.lblk == 2 ? 2.84e-7f : P.lblk == 4 ? 6.8e-7f : 0.f);
     // a residual given as fp16 hi/lo planes is stored times kPlaneScale
     if (g->split && P.resid_dtype == 1) P.alpha /= kPlaneScale;
 
