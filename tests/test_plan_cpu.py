@@ -13,7 +13,7 @@ def test_pick_tile_and_block_n():
         tiles = -(-W // e0) * -(-H // e1) * -(-B // e2)
         assert W * H * B / (tiles * 128) > 0.6
     assert pick_block_n(2048) == 256 and pick_block_n(384) == 128 and pick_block_n(64) == 64 and pick_block_n(1208) == 256
-    assert pick_block_n(512, split=True) == 256 and pick_block_n(512, split=True, m_tiles=1) == 128 and pick_block_n(80, split=True) == 128
+    assert pick_block_n(512, split=True) == 128 and pick_block_n(512, split=True, m_tiles=1) == 128 and pick_block_n(80, split=True) == 128 and pick_block_n(64, split=True) == 64
 
 
 def test_bn_fold_and_layouts_match_conv_semantics():

@@ -11,7 +11,7 @@ for line in sys.stdin:
     j=line[line.index('{'):]; d=json.loads(j)
     print(line[:line.index('{')], {k:v[0] for k,v in d.items() if k.startswith(('p5','logit','dist'))})
 "; tail -3 gpurun_out/r2_e2e.log
-timeout 420 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-parity-mode --profile-ops gpurun_out/r2_ops.json > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
+timeout 420 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-fast-mode --no-torch-eager --profile-ops gpurun_out/r2_ops.json > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
 echo "== bench exit $?"; python -c "
 import json;d=json.load(open('gpurun_out/r2_bench.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['clocks'])
 p=json.load(open('gpurun_out/r2_ops.json'))

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwedetect_b200.so")
+LIB_PATH = os.environ.get("WD_LIB_PATH") or os.path.join(_HERE, "libwedetect_b200.so")   # WD_LIB_PATH: A/B builds of the library
 
 WD_OP_NI, WD_OP_NF, WD_OP_NP = 48, 8, 16
 ACT_PLANE_SCALE = 4.0    # WD_ACT_PLANE_SCALE of include/wedetect_b200.h

@@ -28,18 +28,20 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None, tag=""):
+    """defines / out / tag: A/B variants of the library (e.g. defines=("-DWD_SPLIT_EPI_BUFS=2",), out=".../lib_b.so", tag="_b")."""
     nvcc = _nvcc()
+    OUT = out or globals()["OUT"]
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "wedetect_b200.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + tag)
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, "-c", s, "-o", o] + ARCH + COMMON + PER_FILE.get(src, [])
+            cmd = [nvcc, "-c", s, "-o", o] + ARCH + COMMON + PER_FILE.get(src, []) + list(defines)
             if verbose:
                 cmd += ["-Xptxas", "-v"]
             jobs.append(cmd)

@@ -90,18 +90,26 @@ __device__ __forceinline__ uint64_t act2_exact(uint64_t x) {
 // a2[j] <- gamma[n] * act(a2[j] * (1 + comp) * s + bias[n]) over NC columns starting at n_base (two columns per element of a2).
 // comp undoes the tensor pipe's truncating accumulation (a measured, data-independent shrink of each TMEM block sum); columns
 // at or beyond N get no bias / gamma (they are never stored).
-template <int NC, int ACT>
-__device__ __forceinline__ void split_epi_math(uint64_t* a2, float comp, float s, const float* __restrict__ bias, const float* __restrict__ gamma, int n_base,
-                                               int N) {
+template <int NC, int ACT, bool kBiasRegs>
+__device__ __forceinline__ void split_epi_math(uint64_t* a2, float comp, float s, const float* __restrict__ bias, const uint64_t* bias2,
+                                               const float* __restrict__ gamma, int n_base, int N) {
     const uint64_t comp2 = splat2(comp), s2 = splat2(s);
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
         const int n = n_base + j;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        uint64_t b0, b1;
+        if constexpr (kBiasRegs) {   // prefetched by the caller (zeros where there is no bias)
+            b0 = bias2[j / 2];
+            b1 = bias2[j / 2 + 1];
+        } else {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+            b0 = pk2(b4.x, b4.y);
+            b1 = pk2(b4.z, b4.w);
+        }
         uint64_t x0 = fma2(a2[j / 2], comp2, a2[j / 2]), x1 = fma2(a2[j / 2 + 1], comp2, a2[j / 2 + 1]);
-        x0 = act2_exact<ACT>(fma2(x0, s2, pk2(b4.x, b4.y)));
-        x1 = act2_exact<ACT>(fma2(x1, s2, pk2(b4.z, b4.w)));
+        x0 = act2_exact<ACT>(fma2(x0, s2, b0));
+        x1 = act2_exact<ACT>(fma2(x1, s2, b1));
         if (gamma && n < N) {
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n));
             x0 = mul2(x0, pk2(g4.x, g4.y));

@@ -31,12 +31,17 @@ struct SCfg {
     static constexpr int B_ROWS = kPair ? BN / 2 : BN;
     static constexpr int B_BYTES = B_ROWS * 128;                 // one plane of this CTA's B rows
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // [A hi][A lo][B hi][B lo]
-    static constexpr int EPI_BYTES = 8 * 4096;                   // 32 rows x 128 B per epilogue warp
+#ifndef WD_SPLIT_EPI_BUFS
+#define WD_SPLIT_EPI_BUFS 1
+#endif
+    static constexpr int EPI_BUFS = ((kPair && BN == 128) || BN == 64) ? WD_SPLIT_EPI_BUFS : 1;   // staging buffers per epilogue warp (32 rows x 128 B each)
+    static constexpr int EPI_BYTES = 8 * EPI_BUFS * 4096;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int kStagesRaw = (232448 - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
     static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
     static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int NBUF = BN == 256 ? 2 : 4;               // TMEM accumulator buffers (block sums in flight)
+    static constexpr int TMEM_COLS = NBUF * BN;
     static constexpr int ACTIVE_WG = BN == 64 ? 1 : 2;           // a warpgroup owns >= 64 accumulator columns
     static constexpr int WCOLS = BN / ACTIVE_WG;
     static_assert(kStages >= 3, "pipeline too shallow");
@@ -61,8 +66,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
     uint64_t* bar_empty = bar_full + 8;
     uint64_t* bar_tfull = bar_empty + 8;
-    uint64_t* bar_tempty = bar_tfull + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    uint64_t* bar_tempty = bar_tfull + 8;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_tempty + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < C::NBUF; ++a) {
             mbar_init(&bar_tfull[a], 1);
             mbar_init(&bar_tempty[a], 4 * C::ACTIVE_WG * kClu);   // one arrival per epilogue warp (of both CTAs in pair mode)
         }
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                     }
                     if (last) {
                         inblk = 0;
-                        if (++as == 2) {
+                        if (++as == C::NBUF) {
                             as = 0;
                             aphase ^= 1;
                         }
@@ -239,8 +244,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
         const int quarter = warp & 3;   // TMEM lane quarter this warp may access
         if (wg < C::ACTIVE_WG) {
         const int r = quarter * 32 + lane;
-        uint8_t* wbuf = smem_epi + (warp - 4) * 4096;
-        const uint32_t srow_s = smem_u32(wbuf) + lane * 128;
+        uint8_t* wbuf0 = smem_epi + (warp - 4) * C::EPI_BUFS * 4096;
+        int sbuf = 0;
         const int nblk = (k_iters + lblk - 1) / lblk;
         int as = 0;
         uint32_t aphase = 0;
@@ -253,6 +258,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
             const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
             const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
 
+            // narrow warp slices: the bias of this warpgroup's columns is fetched now, behind the tile's UMMAs (in the epilogue
+            // proper every first use of a bias value would wait for its L1 / L2 round trip: ncu shows 11 % of the samples there)
+            constexpr bool kBiasRegs = WCOLS <= 64;
+            uint64_t bias2[kBiasRegs ? WCOLS / 2 : 1];
+            if constexpr (kBiasRegs) {
+                const int nb = n_blk * BN + wg * WCOLS;
+#pragma unroll
+                for (int j = 0; j < WCOLS; j += 4) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias && nb + j < p.N && p.epi_mode == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                    bias2[j / 2] = pk2(b4.x, b4.y);
+                    bias2[j / 2 + 1] = pk2(b4.z, b4.w);
+                }
+            }
             // ---- sum the block accumulators in fp32 registers (packed round-to-nearest adds) ----
             uint64_t acc2[WCOLS / 2];
 #pragma unroll
@@ -276,7 +295,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) release_acc(as);
-                if (++as == 2) {
+                if (++as == C::NBUF) {
                     as = 0;
                     aphase ^= 1;
                 }
@@ -321,10 +340,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
             {
                 const int nb = n_blk * BN + wg * WCOLS;
                 switch (p.act) {
-                    case WD_ACT_RELU: split_epi_math<WCOLS, WD_ACT_RELU>(acc2, p.trunc_comp, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
-                    case WD_ACT_SILU: split_epi_math<WCOLS, WD_ACT_SILU>(acc2, p.trunc_comp, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
-                    case WD_ACT_GELU: split_epi_math<WCOLS, WD_ACT_GELU>(acc2, p.trunc_comp, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
-                    default: split_epi_math<WCOLS, WD_ACT_NONE>(acc2, p.trunc_comp, p.acc_scale, p.bias, p.gamma, nb, p.N); break;
+                    case WD_ACT_RELU: split_epi_math<WCOLS, WD_ACT_RELU, kBiasRegs>(acc2, p.trunc_comp, p.acc_scale, p.bias, bias2, p.gamma, nb, p.N); break;
+                    case WD_ACT_SILU: split_epi_math<WCOLS, WD_ACT_SILU, kBiasRegs>(acc2, p.trunc_comp, p.acc_scale, p.bias, bias2, p.gamma, nb, p.N); break;
+                    case WD_ACT_GELU: split_epi_math<WCOLS, WD_ACT_GELU, kBiasRegs>(acc2, p.trunc_comp, p.acc_scale, p.bias, bias2, p.gamma, nb, p.N); break;
+                    default: split_epi_math<WCOLS, WD_ACT_NONE, kBiasRegs>(acc2, p.trunc_comp, p.acc_scale, p.bias, bias2, p.gamma, nb, p.N); break;
                 }
             }
             // first row of this warp's quarter inside the tile brick (per-warp TMA stores)
@@ -395,7 +414,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                         }
                     }
                     if (p.warp_store) {
-                        if (lane == 0) tma_store_wait_read<0>();   // the staging buffer is no longer being read by the previous store
+                        uint8_t* wbuf = wbuf0 + sbuf * 4096;
+                        const uint32_t srow_s = smem_u32(wbuf) + lane * 128;
+                        sbuf = (sbuf + 1) % C::EPI_BUFS;
+                        if (lane == 0) tma_store_wait_read<C::EPI_BUFS - 1>();   // this staging buffer is no longer being read by an earlier store
                         __syncwarp();
 #pragma unroll
                         for (int q = 0; q < 8; ++q)

@@ -526,8 +526,9 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     P.lblk = I[40] > 0 ? I[40] : 1;
     // Measured on B200 (tools/trunc_probe.py, profiles/trunc_probe_r02.json): with the three products of a 64-wide k-block
     // accumulated in TMEM the block sum comes out 8.9e-8 (~1.5 * 2^-24) too small relative to an exact sum, independent of K
-    // and of the data distribution (2.8e-7 for two blocks, 6.8e-7 for four).  I[41] = 1 turns the compensation off.
-    P.trunc_comp = I[41] ? 0.f : (P.lblk == 1 ? 8.9e-8f : P.lblk == 2 ? 2.84e-7f : P.lblk == 4 ? 6.8e-7f : 0.f);
+    // and of the data distribution (2.8e-7 for two blocks, 6.8e-7 for four: lblk > 1 is an experiment switch and is not
+    // compensated, its last block of a tile may be shorter).  I[41] = 1 turns the compensation off.
+    P.trunc_comp = (I[41] || P.lblk != 1) ? 0.f : 8.9e-8f;
     // a residual given as fp16 hi/lo planes is stored times kPlaneScale
     if (g->split && P.resid_dtype == 1) P.alpha /= kPlaneScale;
 
