@@ -25,34 +25,34 @@
 
 namespace wd {
 
+constexpr int kSplitEpiWarps = 16;
+constexpr int kSplitThreads = 128 + 32 * kSplitEpiWarps;   // warps 0..3: TMA / UMMA / TMEM roles; warps 4..19: epilogue
+
 template <int BN, bool kPair>
 struct SCfg {
+    static_assert(BN == 64 || BN == 128, "split tiles are 64 or 128 columns wide");
     static constexpr int A_BYTES = kTileM * 128;                 // one plane of this CTA's A rows
     static constexpr int B_ROWS = kPair ? BN / 2 : BN;
     static constexpr int B_BYTES = B_ROWS * 128;                 // one plane of this CTA's B rows
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // [A hi][A lo][B hi][B lo]
-#ifndef WD_SPLIT_EPI_BUFS
-#define WD_SPLIT_EPI_BUFS 1
-#endif
-    static constexpr int EPI_BUFS = ((kPair && BN == 128) || BN == 64) ? WD_SPLIT_EPI_BUFS : 1;   // staging buffers per epilogue warp (32 rows x 128 B each)
-    static constexpr int EPI_BYTES = 8 * EPI_BUFS * 4096;
+    static constexpr int EPI_BYTES = 8 * 4096;                   // 16-bit outputs: 32 rows x 128 B per PAIR of epilogue warps
     static constexpr int BAR_BYTES = 1024;
     static constexpr int kStagesRaw = (232448 - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
     static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
     static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
-    static constexpr int NBUF = BN == 256 ? 2 : 4;               // TMEM accumulator buffers (block sums in flight)
+    static constexpr int NBUF = 4;                               // TMEM accumulator buffers (block sums in flight)
     static constexpr int TMEM_COLS = NBUF * BN;
-    static constexpr int ACTIVE_WG = BN == 64 ? 1 : 2;           // a warpgroup owns >= 64 accumulator columns
-    static constexpr int WCOLS = BN / ACTIVE_WG;
+    static constexpr int WCOLS = 32;                             // accumulator columns per epilogue warp
+    static constexpr int NGRP = BN / WCOLS;                      // active column groups (x 4 lane quarters = active epilogue warps)
     static_assert(kStages >= 3, "pipeline too shallow");
-    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols");
 };
 
 // UMMA instruction descriptor (kind::f16): fp32 accumulate, fp16 A/B (format 0), both K-major
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
 
 template <int BN, typename OutT, bool kPair>
-__global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __grid_constant__ GemmParams p) {
     constexpr int kClu = kPair ? 2 : 1;
     pdl_launch_dependents();
     using C = SCfg<BN, kPair>;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
         }
         for (int a = 0; a < C::NBUF; ++a) {
             mbar_init(&bar_tfull[a], 1);
-            mbar_init(&bar_tempty[a], 4 * C::ACTIVE_WG * kClu);   // one arrival per epilogue warp (of both CTAs in pair mode)
+            mbar_init(&bar_tempty[a], 4 * C::NGRP * kClu);   // one arrival per epilogue warp (of both CTAs in pair mode)
         }
         fence_mbar_init();
     }
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
     pdl_wait();   // everything above overlapped the previous kernel's tail
 
     if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ================= TMA producer =================
         int stage = 0;
@@ -238,14 +238,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================= epilogue warps =================
-        const int wg = (warp - 4) >> 2;
-        const int quarter = warp & 3;   // TMEM lane quarter this warp may access
-        if (wg < C::ACTIVE_WG) {
+        // Warp (quarter, cg) owns TMEM lanes 32 quarter .. +31 (rows of the tile) and accumulator columns 32 cg .. +31.
+        const int e = warp - 4;
+        const int quarter = warp & 3, cg = e >> 2;
+        if (cg < C::NGRP) {
         const int r = quarter * 32 + lane;
-        uint8_t* wbuf0 = smem_epi + (warp - 4) * C::EPI_BUFS * 4096;
-        int sbuf = 0;
+        // 16-bit outputs leave through swizzled shared memory in 64-column (128-byte) chunks: the two warps of a chunk
+        // (same rows, column groups 2m and 2m+1) share one 32-row staging buffer and a named barrier; the even one stores
+        const int pairbuf = (cg >> 1) * 4 + quarter;
+        uint8_t* wbuf = smem_epi + pairbuf * 4096;
+        const uint32_t srow_s = smem_u32(wbuf) + lane * 128;
+        const bool store_issuer = (cg & 1) == 0 && lane == 0;
         const int nblk = (k_iters + lblk - 1) / lblk;
         int as = 0;
         uint32_t aphase = 0;
@@ -257,21 +262,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
             const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
             const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
             const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
-
-            // narrow warp slices: the bias of this warpgroup's columns is fetched now, behind the tile's UMMAs (in the epilogue
-            // proper every first use of a bias value would wait for its L1 / L2 round trip: ncu shows 11 % of the samples there)
-            constexpr bool kBiasRegs = WCOLS <= 64;
-            uint64_t bias2[kBiasRegs ? WCOLS / 2 : 1];
-            if constexpr (kBiasRegs) {
-                const int nb = n_blk * BN + wg * WCOLS;
-#pragma unroll
-                for (int j = 0; j < WCOLS; j += 4) {
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.bias && nb + j < p.N && p.epi_mode == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                    bias2[j / 2] = pk2(b4.x, b4.y);
-                    bias2[j / 2 + 1] = pk2(b4.z, b4.w);
-                }
+            const int nb = n_blk * BN + cg * WCOLS;     // first output column of this warp
+            // pull this warp's bias / LayerScale line into L1 behind the tile's UMMAs (the epilogue's loads then hit)
+            if (lane == 0) {
+                if (p.bias && nb < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + nb));
+                if (p.gamma && nb < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.gamma + nb));
             }
+
             // ---- sum the block accumulators in fp32 registers (packed round-to-nearest adds) ----
             uint64_t acc2[WCOLS / 2];
 #pragma unroll
@@ -279,22 +276,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
             for (int b = 0; b < nblk; ++b) {
                 mbar_wait(&bar_tfull[as], aphase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + wg * WCOLS);
-#pragma unroll
-                for (int j0 = 0; j0 < WCOLS; j0 += 32) {
-                    uint32_t t[32];
-                    tmem_ld_32x32(taddr + j0, t);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        uint64_t tv;
-                        asm("mov.b64 %0, {%1, %2};" : "=l"(tv) : "r"(t[2 * j]), "r"(t[2 * j + 1]));
-                        acc2[j0 / 2 + j] = add2(acc2[j0 / 2 + j], tv);
-                    }
-                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + cg * WCOLS);
+                uint32_t t[32];
+                tmem_ld_32x32(taddr, t);
+                tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) release_acc(as);
+                if (lane == 0) release_acc(as);   // the values are in registers: the tensor pipe may refill this buffer
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    uint64_t tv;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(tv) : "r"(t[2 * j]), "r"(t[2 * j + 1]));
+                    acc2[j] = add2(acc2[j], tv);
+                }
                 if (++as == C::NBUF) {
                     as = 0;
                     aphase ^= 1;
@@ -307,71 +301,65 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
             const long long pix = ((long long)d2 * p.D1 + d1) * p.D0 + d0;
 
             if (p.epi_mode == 1) {
-                // ---- DFL epilogue (BN == N == 64): softmax over 16 bins x 4 sides, expectation (yolo_world_head.py:283-291) ----
+                // ---- DFL epilogue (BN == N == 64): softmax over 16 bins x 4 sides, expectation (yolo_world_head.py:283-291);
+                //      this warp's 32 columns are sides 2 cg and 2 cg + 1 ----
                 if constexpr (BN == 64) {
-                    float acc[64];
+                    float acc[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) upk2(acc2[j], acc[2 * j], acc[2 * j + 1]);
-                    float out4[4];
+                    for (int j = 0; j < 16; ++j) upk2(acc2[j], acc[2 * j], acc[2 * j + 1]);
+                    float out2[2];
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
+                    for (int s = 0; s < 2; ++s) {
                         float mx = -INFINITY;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float a = fmaf(acc[s * 16 + j], p.trunc_comp, acc[s * 16 + j]);
-                            acc[s * 16 + j] = fmaf(a, p.acc_scale, __ldg(p.bias + s * 16 + j));
+                            acc[s * 16 + j] = fmaf(a, p.acc_scale, __ldg(p.bias + cg * 32 + s * 16 + j));
                             mx = fmaxf(mx, acc[s * 16 + j]);
                         }
                         float den = 0.f, num = 0.f;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float e = expf(acc[s * 16 + j] - mx);
-                            den += e;
-                            num += e * (float)j;
+                            const float ex = expf(acc[s * 16 + j] - mx);
+                            den += ex;
+                            num += ex * (float)j;
                         }
-                        out4[s] = num / den;
+                        out2[s] = num / den;
                     }
-                    if (row_ok) *reinterpret_cast<float4*>(p.dfl_out + pix * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+                    if (row_ok) *reinterpret_cast<float2*>(p.dfl_out + pix * 4 + cg * 2) = make_float2(out2[0], out2[1]);
                 }
                 continue;
             }
 
-            // ---- acc = gamma * act(acc * (1 + trunc_comp) * acc_scale + bias) over the warpgroup's columns, two per instruction ----
-            {
-                const int nb = n_blk * BN + wg * WCOLS;
-                switch (p.act) {
-                    case WD_ACT_RELU: split_epi_math<WCOLS, WD_ACT_RELU, kBiasRegs>(acc2, p.trunc_comp, p.acc_scale, p.bias, bias2, p.gamma, nb, p.N); break;
-                    case WD_ACT_SILU: split_epi_math<WCOLS, WD_ACT_SILU, kBiasRegs>(acc2, p.trunc_comp, p.acc_scale, p.bias, bias2, p.gamma, nb, p.N); break;
-                    case WD_ACT_GELU: split_epi_math<WCOLS, WD_ACT_GELU, kBiasRegs>(acc2, p.trunc_comp, p.acc_scale, p.bias, bias2, p.gamma, nb, p.N); break;
-                    default: split_epi_math<WCOLS, WD_ACT_NONE, kBiasRegs>(acc2, p.trunc_comp, p.acc_scale, p.bias, bias2, p.gamma, nb, p.N); break;
-                }
+            // ---- acc = osc * gamma * act(acc * (1 + trunc_comp) * acc_scale + bias), two columns per instruction; osc = the plane
+            //      scale of a 16-bit output (powers of two commute with every rounding below) ----
+            const float osc = kOut16 ? kPlaneScale : 1.f;
+            switch (p.act) {
+                case WD_ACT_RELU: split_epi_math<WCOLS, WD_ACT_RELU>(acc2, p.trunc_comp, p.acc_scale, osc, p.bias, p.gamma, nb, p.N); break;
+                case WD_ACT_SILU: split_epi_math<WCOLS, WD_ACT_SILU>(acc2, p.trunc_comp, p.acc_scale, osc, p.bias, p.gamma, nb, p.N); break;
+                case WD_ACT_GELU: split_epi_math<WCOLS, WD_ACT_GELU>(acc2, p.trunc_comp, p.acc_scale, osc, p.bias, p.gamma, nb, p.N); break;
+                default: split_epi_math<WCOLS, WD_ACT_NONE>(acc2, p.trunc_comp, p.acc_scale, osc, p.bias, p.gamma, nb, p.N); break;
             }
-            // first row of this warp's quarter inside the tile brick (per-warp TMA stores)
-            const int qr = quarter * 32;
-            const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
-            const uint64_t alpha2 = splat2(p.alpha);
+            const bool cols_ok = nb < p.N;      // warp-uniform: some of this warp's columns exist
+            // ---- acc += resid * alpha ----
+            if (cols_ok && row_ok) {
+                const uint64_t alpha2 = splat2(p.alpha * osc);   // acc already carries the output's plane scale
+                if (p.resid_dtype == 2) {
+                    const float* rp = reinterpret_cast<const float*>(p.resid) + pix * p.ld_res + nb;
 #pragma unroll
-            for (int c = 0; c < WCOLS / CH; ++c) {
-                uint64_t* v2 = acc2 + c * (CH / 2);
-                const int n_base = n_blk * BN + wg * WCOLS + c * CH;
-                if (n_base >= p.N) continue;   // warp-uniform: nothing of this chunk exists
-                // ---- v += resid * alpha ----
-                if (p.resid_dtype == 2 && row_ok) {
-                    const float* rp = reinterpret_cast<const float*>(p.resid) + pix * p.ld_res + n_base;
-#pragma unroll
-                    for (int j = 0; j < CH; j += 4) {
-                        if (n_base + j < p.N) {
+                    for (int j = 0; j < WCOLS; j += 4) {
+                        if (nb + j < p.N) {
                             const float4 x = *reinterpret_cast<const float4*>(rp + j);
-                            v2[j / 2] = fma2(alpha2, pk2(x.x, x.y), v2[j / 2]);
-                            v2[j / 2 + 1] = fma2(alpha2, pk2(x.z, x.w), v2[j / 2 + 1]);
+                            acc2[j / 2] = fma2(alpha2, pk2(x.x, x.y), acc2[j / 2]);
+                            acc2[j / 2 + 1] = fma2(alpha2, pk2(x.z, x.w), acc2[j / 2 + 1]);
                         }
                     }
-                } else if (p.resid_dtype == 1 && row_ok) {
+                } else if (p.resid_dtype == 1) {
                     // fp16 hi (+ lo) planes; alpha already carries 1 / kPlaneScale
-                    const __half* rp = reinterpret_cast<const __half*>(p.resid) + pix * p.ld_res + n_base;
+                    const __half* rp = reinterpret_cast<const __half*>(p.resid) + pix * p.ld_res + nb;
 #pragma unroll
-                    for (int j = 0; j < CH; j += 8) {
-                        if (n_base + j < p.N) {
+                    for (int j = 0; j < WCOLS; j += 8) {
+                        if (nb + j < p.N) {
                             const uint4 x = *reinterpret_cast<const uint4*>(rp + j);
                             uint64_t xs[4] = {h2_to_f2(x.x), h2_to_f2(x.y), h2_to_f2(x.z), h2_to_f2(x.w)};
                             if (p.resid_ps) {
@@ -380,61 +368,95 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_split_kernel(const __grid
                                 xs[2] = add2(xs[2], h2_to_f2(y.z)); xs[3] = add2(xs[3], h2_to_f2(y.w));
                             }
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) v2[j / 2 + q] = fma2(alpha2, xs[q], v2[j / 2 + q]);
+                            for (int q = 0; q < 4; ++q) acc2[j / 2 + q] = fma2(alpha2, xs[q], acc2[j / 2 + q]);
                         }
                     }
                 }
-                // ---- output: fp32, or fp16 hi / lo planes of v * kPlaneScale (one pass per plane) ----
-                const int g = n_base / p.group_cols, c0 = n_base - g * p.group_cols;
-                constexpr int kOutPlanes = kOut16 ? 2 : 1;
-                const long long grow = (long long)d0 * p.sc0 + (long long)d1 * p.sc1 + (long long)d2 * p.sc2 + (long long)g * p.scg + c0;
-#pragma unroll
-                for (int pl = 0; pl < kOutPlanes; ++pl) {
-                    uint4 w[8];
-                    if constexpr (kOut16) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            uint32_t ww[4];
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                uint64_t a = v2[q * 4 + h];
-                                if (pl == 0) a = mul2(a, splat2(kPlaneScale));
-                                ww[h] = cvt_h2_sat(a);
-                                if (pl == 0) v2[q * 4 + h] = add2(a, neg2(h2_to_f2(ww[h])));   // the remainder goes to the low plane
-                            }
-                            w[q] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
-                        }
-                    } else {
+            }
+            // ---- output ----
+            const int g = nb / p.group_cols, c0 = nb - g * p.group_cols;     // column inside its output group (concat / deconv layouts)
+            const long long grow = (long long)d0 * p.sc0 + (long long)d1 * p.sc1 + (long long)d2 * p.sc2 + (long long)g * p.scg + c0;
+            if constexpr (!kOut16) {
+                // fp32: this warp's 32 columns are one 128-byte chunk.  The two warps of a pair take turns on the pair's staging
+                // buffer (even warp first): the odd warp waits for the even warp's TMA store to have read the buffer.
+                if (p.warp_store) {
+                    const int qr = quarter * 32;
+                    const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
+                    const bool odd = (cg & 1) != 0;
+                    if (odd && lane == 0) tma_store_wait_read<0>();      // my store of the previous tile has released the buffer
+                    named_bar_sync(1 + pairbuf, 64);
+                    if (odd) named_bar_sync(1 + pairbuf, 64);            // ... until the even warp's store has read its rows
+                    if (cols_ok) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float f0, f1, f2, f3;
-                            upk2(v2[q * 2], f0, f1);
-                            upk2(v2[q * 2 + 1], f2, f3);
-                            w[q] = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
+                            upk2(acc2[q * 2], f0, f1);
+                            upk2(acc2[q * 2 + 1], f2, f3);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + ((q ^ (lane & 7)) << 4)), "f"(f0), "f"(f1), "f"(f2), "f"(f3) : "memory");
                         }
-                    }
-                    if (p.warp_store) {
-                        uint8_t* wbuf = wbuf0 + sbuf * 4096;
-                        const uint32_t srow_s = smem_u32(wbuf) + lane * 128;
-                        sbuf = (sbuf + 1) % C::EPI_BUFS;
-                        if (lane == 0) tma_store_wait_read<C::EPI_BUFS - 1>();   // this staging buffer is no longer being read by an earlier store
-                        __syncwarp();
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + ((q ^ (lane & 7)) << 4)), "r"(w[q].x), "r"(w[q].y), "r"(w[q].z), "r"(w[q].w) : "memory");
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_5d(&p.tmCw[pl], wbuf, c0, o0 + q0, o1 + q1, o2 + q2, g);
+                            tma_store_5d(&p.tmCw[0], wbuf, c0, o0 + q0, o1 + q1, o2 + q2, g);
+                            tma_store_commit();
+                            if (!odd) tma_store_wait_read<0>();
+                        }
+                        __syncwarp();
+                    }
+                    if (!odd) named_bar_sync(1 + pairbuf, 64);           // hand the buffer to the odd warp
+                } else if (cols_ok && row_ok) {
+                    // the 32 rows of a lane quarter are not a sub-brick of the tile: each thread writes its own row
+                    float* op = reinterpret_cast<float*>(p.out) + grow;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (c0 + q * 4 < p.cols_valid) {
+                            float f0, f1, f2, f3;
+                            upk2(acc2[q * 2], f0, f1);
+                            upk2(acc2[q * 2 + 1], f2, f3);
+                            *reinterpret_cast<float4*>(op + q * 4) = make_float4(f0, f1, f2, f3);
+                        }
+                    }
+                }
+            } else {
+                // fp16 hi / lo planes of acc * kPlaneScale (one pass per plane)
+                const int chunk_n = n_blk * BN + (cg & ~1) * WCOLS;      // first column of the 64-column chunk this warp pair writes
+                const bool chunk_ok = chunk_n < p.N;                        // uniform over the pair
+                const int gc = chunk_n / p.group_cols, cc0 = chunk_n - gc * p.group_cols;
+                const int qr = quarter * 32;
+                const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+                    uint4 w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t ww[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const uint64_t a = acc2[q * 4 + h];
+                            ww[h] = cvt_h2_sat(a);
+                            if (pl == 0) acc2[q * 4 + h] = add2(a, neg2(h2_to_f2(ww[h])));   // the remainder goes to the low plane
+                        }
+                        w[q] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+                    }
+                    if (p.warp_store) {
+                        if (!chunk_ok) continue;
+                        if (store_issuer) tma_store_wait_read<0>();   // the pair's staging buffer is no longer being read by the previous store
+                        named_bar_sync(1 + pairbuf, 64);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + ((((cg & 1) * 4 + q) ^ (lane & 7)) << 4)), "r"(w[q].x), "r"(w[q].y), "r"(w[q].z), "r"(w[q].w) : "memory");
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + pairbuf, 64);
+                        if (store_issuer) {
+                            tma_store_5d(&p.tmCw[pl], wbuf, cc0, o0 + q0, o1 + q1, o2 + q2, gc);
                             tma_store_commit();
                         }
-                    } else if (row_ok) {
-                        // this warp's 32 rows are not a sub-brick of the tile: each thread writes its own row
-                        constexpr int EPV = 16 / (int)sizeof(OutT);
-                        OutT* op = reinterpret_cast<OutT*>(p.out) + (long long)pl * p.out_ps + grow;
+                    } else if (cols_ok && row_ok) {
+                        // the 32 rows of a lane quarter are not a sub-brick of the tile: each thread writes its own row
+                        __half* op = reinterpret_cast<__half*>(p.out) + (long long)pl * p.out_ps + grow;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (c0 + q * EPV < p.cols_valid) *reinterpret_cast<uint4*>(op + q * EPV) = w[q];
+                        for (int q = 0; q < 4; ++q)
+                            if (c0 + q * 8 < p.cols_valid) *reinterpret_cast<uint4*>(op + q * 8) = w[q];
                     }
                 }
             }
@@ -463,7 +485,7 @@ static int launch_split_inst(const GemmOp& g, cudaStream_t s) {
     auto kern = gemm_split_kernel<BN, OutT, kPair>;
     using C = SCfg<BN, kPair>;
     WD_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
-    WD_CHECK_CUDA(launch_pdl(kern, dim3(g.grid), dim3(kNumThreads), (size_t)C::SMEM_BYTES, s, kPair ? 2 : 1, g.prm));
+    WD_CHECK_CUDA(launch_pdl(kern, dim3(g.grid), dim3(kSplitThreads), (size_t)C::SMEM_BYTES, s, kPair ? 2 : 1, g.prm));
     WD_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -474,7 +496,6 @@ int launch_gemm_split(const GemmOp& g, cudaStream_t s) {
     if (g.block_n == 64 && !pair) return g.out_f32 ? launch_split_inst<64, float, false>(g, s) : launch_split_inst<64, __half, false>(g, s);
     if (g.block_n == 128 && !pair) return g.out_f32 ? launch_split_inst<128, float, false>(g, s) : launch_split_inst<128, __half, false>(g, s);
     if (g.block_n == 128 && pair) return g.out_f32 ? launch_split_inst<128, float, true>(g, s) : launch_split_inst<128, __half, true>(g, s);
-    if (g.block_n == 256 && pair) return g.out_f32 ? launch_split_inst<256, float, true>(g, s) : launch_split_inst<256, __half, true>(g, s);
     set_last_error("gemm (split): unsupported block_n=%d pair=%d", g.block_n, (int)pair);
     return -1;
 }

@@ -558,11 +558,10 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     P.rows_a = P.E0 * P.E1 * P.E2;
     // pair mode: 256-wide tiles of the fast path; halves the B bytes each SM pulls through L2 (the L2->SM fabric, not
     // HBM or the tensor pipe, is what bounds 128x256 tiles).  I[36] = 1 disables it (A/B measurements).
-    // split mode: 128- and 256-wide tiles pair up (each UMMA then reads 6 or 8 KB of operands from this SM's shared memory
-    // instead of 8 or 12); 256-wide tiles exist only as pairs (a single CTA has room for two pipeline stages of them).
-    if (g->split) P.clu = (g->block_n >= 128 && P.epi_mode == 0 && P.num_m_tiles >= 2 && I[36] == 0) ? 2 : 1;
+    // split mode: 128-wide tiles pair up (a UMMA then reads 6 KB of operands from this SM's shared memory instead of 8)
+    if (g->split) P.clu = (g->block_n == 128 && P.epi_mode == 0 && P.num_m_tiles >= 2 && I[36] == 0) ? 2 : 1;
     else P.clu = (g->block_n == 256 && P.epi_mode == 0 && P.num_m_tiles >= 2 && I[36] == 0) ? 2 : 1;
-    WD_REQUIRE(!(g->split && g->block_n == 256 && P.clu != 2), "gemm: split mode runs 256-wide tiles only as CTA pairs (>= 2 m-tiles)");
+    WD_REQUIRE(!(g->split && g->block_n == 256), "gemm: split (fp16 hi/lo) mode has 64- and 128-wide tiles");
     P.num_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
 
     // --- A: rank-4 (k, d0, d1, d2), bf16, box (64, E0, E1, E2), 128B swizzle

@@ -111,9 +111,9 @@ def pick_block_n(N, out_f32=False, split=False, m_tiles=2):
     Split (fp16 hi/lo) mode runs 256-wide tiles only as CTA pairs, which need >= 2 m-tiles."""
     cands = ((256, 1.0), (128, 1.15), (64, 1.5))
     if split:
-        # measured (tools/split_sweep.py): 128-wide CTA-pair tiles with four TMEM accumulator buffers beat 256-wide ones on
-        # every ConvNeXt / neck shape (the epilogue of a tile hides behind four block sums instead of two)
-        cands = ((128, 1.0), (256, 1.02), (64, 1.6)) if m_tiles >= 2 else ((128, 1.0), (64, 1.6))
+        # 64- and 128-wide tiles only; measured (tools/split_sweep.py): 128-wide CTA-pair tiles with four TMEM accumulator
+        # buffers beat 256-wide ones on every ConvNeXt / neck shape (a tile's epilogue hides behind four block sums, not two)
+        cands = ((128, 1.0), (64, 1.6))
     best = None
     for bn, pen in cands:
         cost = -(-N // bn) * bn * pen
