@@ -109,7 +109,8 @@ def _head_stack(sd, p, x):
 
 
 def head(sd, feats, text=None, prompts=None):
-    """Returns per level: dict(embed [B,HW,768] after BN, logits [B,HW,K], dist [B,HW,4]).
+    """Returns per level: dict(embed [B,HW,768] after BN, logits [B,HW,K], dist [B,HW,4], dfl_prob [B,HW,4,16] = the bin
+    distribution whose expectation `dist` is).
     text: [K,768] (L2-normalised inside, BNContrastiveHead) ; prompts: [P,768] used raw (Uni)."""
     outs = []
     for l, f in enumerate(feats):
@@ -122,7 +123,7 @@ def head(sd, feats, text=None, prompts=None):
         r = _head_stack(sd, HM + f"reg_preds.{l}.", f)
         r = r.reshape(B, 4, schema.REG_MAX, H * W).permute(0, 3, 1, 2).softmax(3)
         dist = r.matmul(torch.arange(schema.REG_MAX, dtype=r.dtype))
-        outs.append(dict(embed=e.permute(0, 2, 3, 1).reshape(B, H * W, -1), logits=logits.permute(0, 2, 3, 1).reshape(B, H * W, -1), dist=dist))
+        outs.append(dict(embed=e.permute(0, 2, 3, 1).reshape(B, H * W, -1), logits=logits.permute(0, 2, 3, 1).reshape(B, H * W, -1), dist=dist, dfl_prob=r))
     return outs
 
 

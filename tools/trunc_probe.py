@@ -10,7 +10,7 @@ d = torch.device("cuda:0")
 L.load()
 out = []
 for kind in ("normal", "relu"):
-    for K in (64, 128, 256, 512, 2048):
+    for K in (128, 256, 512, 2048, 1152):
         M, N = 1024, 512
         g = torch.Generator().manual_seed(K)
         A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
@@ -20,7 +20,7 @@ for kind in ("normal", "relu"):
         Ap, Wp = P3.from_f32(A, d, scale=ops.ACT_SCALE), P3.from_f32(W, d)
         # what the operand representation alone costs (fp64 product of the reconstructed planes)
         rep = (Ap.value().cpu().double() @ Wp.value().cpu().double().t()) - ref
-        for lblk, nocomp in ((1, 1), (1, 0), (2, 1), (2, 0), (4, 1), (4, 0), (1000, 1)):
+        for lblk, nocomp in ((1, 1), (1, 0), (2, 1), (2, 0)):
             C = torch.zeros(M, N, dtype=torch.float32, device=d)
             op = ops.linear(Ap, Wp, C)
             op.i[40], op.i[41] = lblk, nocomp

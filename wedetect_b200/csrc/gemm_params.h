@@ -15,6 +15,7 @@ constexpr int kBlockK = 64;  // 16-bit elements = 128 bytes = one swizzle atom
 // the low plane of O(1) activations out of the fp16 subnormal range while leaving headroom below 65504 for outliers (the
 // converters clamp).  Weight matrices carry their own per-matrix power of two, folded into the op's `acc_scale`.
 constexpr float kPlaneScale = WD_ACT_PLANE_SCALE;
+constexpr float kSplitComp2 = 1.55e-7f;   // truncation shrink of a two-stage accumulator block (cross products of both stages first; tools/trunc_probe.py)
 
 struct GemmParams {
     CUtensorMap tmA[2], tmB[2], tmC[2];   // plane 0 (+ plane 1: the low fp16 plane in split mode)

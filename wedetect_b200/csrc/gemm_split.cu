@@ -175,63 +175,60 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
+            // An accumulator block = `lblk` (1 or 2) consecutive pipeline stages.  All cross products of the block are issued before
+            // its hi x hi products: the small terms meet a small accumulator, so only the 4 * lblk large adds truncate at full size.
             for (int tile = t_first; tile < t_total; tile += t_step) {
-                int inblk = 0;
-                for (int kit = 0; kit < k_iters; ++kit) {
-                    const bool fresh = inblk == 0;
-                    const bool last = inblk == lblk - 1 || kit == k_iters - 1;
-                    if (fresh) {
-                        mbar_wait(&bar_tempty[as], aphase ^ 1);   // the epilogue has moved this buffer's previous block to registers
-                        tc_fence_after();
-                    }
+                for (int kit = 0; kit < k_iters; kit += lblk) {
+                    mbar_wait(&bar_tempty[as], aphase ^ 1);   // the epilogue has moved this buffer's previous block to registers
                     mbar_wait(&bar_full[stage], phase);
+                    if (lblk == 2) mbar_wait(&bar_full[stage + 1], phase);   // (an even stage count: the pair never wraps)
                     tc_fence_after();
                     __syncwarp();
                     if (elect_one()) {
                         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                        const uint32_t sbase = smem0 + (uint32_t)(stage * C::STAGE_BYTES);
-                        const uint32_t ah = (sbase >> 4) & 0x3FFFu, al = ((sbase + C::A_BYTES) >> 4) & 0x3FFFu;
-                        const uint32_t bh = ((sbase + 2 * C::A_BYTES) >> 4) & 0x3FFFu, bl = ((sbase + 2 * C::A_BYTES + C::B_BYTES) >> 4) & 0x3FFFu;
-                        // cross terms first (small: they meet a small accumulator), then the hi x hi products
+                        for (int h = 0; h < lblk; ++h) {
+                            const uint32_t sbase = smem0 + (uint32_t)((stage + h) * C::STAGE_BYTES);
+                            const uint32_t ah = (sbase >> 4) & 0x3FFFu, al = ((sbase + C::A_BYTES) >> 4) & 0x3FFFu;
+                            const uint32_t bh = ((sbase + 2 * C::A_BYTES) >> 4) & 0x3FFFu, bl = ((sbase + 2 * C::A_BYTES + C::B_BYTES) >> 4) & 0x3FFFu;
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            const uint64_t dal = umma_desc_from_lo(al + 2 * k), dbh = umma_desc_from_lo(bh + 2 * k);
-                            const uint64_t dah = umma_desc_from_lo(ah + 2 * k), dbl = umma_desc_from_lo(bl + 2 * k);
-                            if constexpr (kPair) {
-                                umma_bf16_2sm(tmem_d, dal, dbh, idesc, (fresh && k == 0) ? 0u : 1u);
-                                umma_bf16_2sm(tmem_d, dah, dbl, idesc, 1u);
-                            } else {
-                                umma_bf16(tmem_d, dal, dbh, idesc, (fresh && k == 0) ? 0u : 1u);
-                                umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t dal = umma_desc_from_lo(al + 2 * k), dbh = umma_desc_from_lo(bh + 2 * k);
+                                const uint64_t dah = umma_desc_from_lo(ah + 2 * k), dbl = umma_desc_from_lo(bl + 2 * k);
+                                if constexpr (kPair) {
+                                    umma_bf16_2sm(tmem_d, dal, dbh, idesc, (h == 0 && k == 0) ? 0u : 1u);
+                                    umma_bf16_2sm(tmem_d, dah, dbl, idesc, 1u);
+                                } else {
+                                    umma_bf16(tmem_d, dal, dbh, idesc, (h == 0 && k == 0) ? 0u : 1u);
+                                    umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                                }
                             }
                         }
+                        for (int h = 0; h < lblk; ++h) {
+                            const uint32_t sbase = smem0 + (uint32_t)((stage + h) * C::STAGE_BYTES);
+                            const uint32_t ah = (sbase >> 4) & 0x3FFFu, bh = ((sbase + 2 * C::A_BYTES) >> 4) & 0x3FFFu;
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            const uint64_t dah = umma_desc_from_lo(ah + 2 * k), dbh = umma_desc_from_lo(bh + 2 * k);
-                            if constexpr (kPair) umma_bf16_2sm(tmem_d, dah, dbh, idesc, 1u);
-                            else umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t dah = umma_desc_from_lo(ah + 2 * k), dbh = umma_desc_from_lo(bh + 2 * k);
+                                if constexpr (kPair) umma_bf16_2sm(tmem_d, dah, dbh, idesc, 1u);
+                                else umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                            }
                         }
-                        if constexpr (kPair) {
-                            umma_commit_2sm_mc(&bar_empty[stage], (uint16_t)3);
-                            if (last) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
-                        } else {
-                            umma_commit(&bar_empty[stage]);
-                            if (last) umma_commit(&bar_tfull[as]);
+                        for (int h = 0; h < lblk; ++h) {
+                            if constexpr (kPair) umma_commit_2sm_mc(&bar_empty[stage + h], (uint16_t)3);
+                            else umma_commit(&bar_empty[stage + h]);
                         }
+                        if constexpr (kPair) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
+                        else umma_commit(&bar_tfull[as]);
                     }
                     __syncwarp();
-                    if (++stage == C::kStages) {
+                    stage += lblk;
+                    if (stage >= C::kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
-                    if (last) {
-                        inblk = 0;
-                        if (++as == C::NBUF) {
-                            as = 0;
-                            aphase ^= 1;
-                        }
-                    } else {
-                        ++inblk;
+                    if (++as == C::NBUF) {
+                        as = 0;
+                        aphase ^= 1;
                     }
                 }
             }
@@ -251,7 +248,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
         uint8_t* wbuf = smem_epi + pairbuf * 4096;
         const uint32_t srow_s = smem_u32(wbuf) + lane * 128;
         const bool store_issuer = (cg & 1) == 0 && lane == 0;
-        const int nblk = (k_iters + lblk - 1) / lblk;
+        const int nblk = k_iters / lblk;   // (the host only allows lblk = 2 for an even number of k-blocks)
         int as = 0;
         uint32_t aphase = 0;
         auto release_acc = [&](int a) {

@@ -122,9 +122,11 @@ def pick_block_n(N, out_f32=False, split=False, m_tiles=2):
     return best[1]
 
 
-# fp16 hi/lo mode: 64-wide k-blocks a TMEM accumulator lives for before its partial sum moves to fp32 registers (the tensor
-# pipe truncates on every accumulate; see gemm_split.cu).  Measured on B200 against the fp32 oracle: DESIGN.md §6.
-SPLIT_LBLK = int(_os.environ.get("WD_SPLIT_LBLK", "1"))
+# fp16 hi/lo mode: 64-wide k-blocks (1 or 2) a TMEM accumulator lives for before its partial sum moves to fp32 registers: the
+# tensor pipe truncates on every accumulate (gemm_split.cu).  Two-block accumulators halve the TMEM -> register traffic that
+# bounds the kernel (+8 % images/s) at the same distance from a float64 run of the reference (tools/trunc_probe.py,
+# profiles/e2e_*_r02*.json); the library falls back to 1 where a tile has an odd number of k-blocks.
+SPLIT_LBLK = int(_os.environ.get("WD_SPLIT_LBLK", "2"))
 
 # activations for which the fast path must use the exact formula (debug / accuracy studies): subset of {ACT_SILU, ACT_GELU}
 NO_WARP_STORE = 1 if _os.environ.get("WD_NO_WARP_STORE") == "1" else 0   # A/B switch: warpgroup-wide epilogue stores
