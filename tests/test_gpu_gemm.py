@@ -205,7 +205,7 @@ SPLIT_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("lblk", [1, 2, 1000])
+@pytest.mark.parametrize("lblk", [1, 2])
 @pytest.mark.parametrize("M,K,N,block_n", SPLIT_SHAPES)
 def test_linear_split_shapes(M, K, N, block_n, lblk):
     """fp16 hi/lo mode against an fp64 GEMM: fp32-grade results for every tile configuration / accumulator block length."""
@@ -223,7 +223,7 @@ def test_linear_split_shapes(M, K, N, block_n, lblk):
     err = (C.cpu().double() - ref)
     rel = float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
     print(f"split linear {M}x{K}x{N} lblk={lblk}: rel-rms {rel:.3e} max-abs {float(err.abs().max()):.3e} mean (bias) {float(err.mean()):.3e}")
-    tol = 3e-6 if lblk <= 2 else 3e-5   # lblk = 1000: the whole K accumulates in the tensor pipe (truncating adds)
+    tol = 3e-6
     report_close(f"split linear {M}x{K}x{N}", C, ref.float(), rtol=tol, atol=tol * float(ref.abs().mean()) * 4)
 
 

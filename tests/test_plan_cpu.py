@@ -82,7 +82,7 @@ def test_standalone_text_tower_facade_wires_on_cpu(monkeypatch):
             pass
 
     monkeypatch.setattr(L, "Program", FakeProg)
-    monkeypatch.setattr(L, "load", lambda require_gpu=True: None)
+    monkeypatch.setattr(L, "load", lambda require_gpu=True, device=0: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda: types.SimpleNamespace(cuda_stream=0))
     from wedetect_b200.detector import XLMRobertaLanguageBackbone
     sd = synth.synth_state_dict("tiny", seed=0, with_text=True, text_vocab=64, calibrate=False)

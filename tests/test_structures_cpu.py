@@ -63,8 +63,10 @@ def test_resolve_texts_branches():
     assert resolve_texts([DetDataSample(dict(texts=infer_style))] * 2) == ["person", "dog", " "]
     assert resolve_texts(dict(texts=[["a", "b"], ["a", "b"]])) == ["a", "b"]                   # dict form, one list per image
     assert resolve_texts(dict(texts=["a", "b"])) == ["a", "b"]                                 # dict form, one shared list
-    with pytest.raises(NotImplementedError):
-        resolve_texts([DetDataSample(dict(texts=["a"])), DetDataSample(dict(texts=["b"]))])
+    # per-image lists that differ (equal counts): one list per image comes back, predict() then runs one group per distinct list
+    assert resolve_texts([DetDataSample(dict(texts=["a"])), DetDataSample(dict(texts=["b"]))]) == [["a"], ["b"]]
+    with pytest.raises(AssertionError):                                                         # mm_backbone.py:378-380
+        resolve_texts([DetDataSample(dict(texts=["a"])), DetDataSample(dict(texts=["b", "c"]))])
 
 
 def test_predict_host_logic_with_a_stub_plan(monkeypatch):
@@ -73,7 +75,7 @@ def test_predict_host_logic_with_a_stub_plan(monkeypatch):
     import wedetect_b200._lib as L
     from wedetect_b200 import detector as det
     from wedetect_b200.structures import DetDataSample
-    monkeypatch.setattr(L, "load", lambda require_gpu=True: None)
+    monkeypatch.setattr(L, "load", lambda require_gpu=True, device=0: None)
     B, H, W = 2, 64, 96
 
     class StubPlan:
@@ -124,7 +126,7 @@ def test_uni_forward_tensor_host_logic_with_a_stub_plan(monkeypatch):
     original size - expressed as the post-NMS metadata row; extract variant adds labels / scales / bias; result slicing."""
     import wedetect_b200._lib as L
     from wedetect_b200 import detector as det
-    monkeypatch.setattr(L, "load", lambda require_gpu=True: None)
+    monkeypatch.setattr(L, "load", lambda require_gpu=True, device=0: None)
     B, H, W, P = 2, 64, 64, 6
 
     class StubPlan:

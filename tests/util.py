@@ -26,3 +26,23 @@ def report_close(name, got, ref, rtol, atol):
         msg.append(f"  ref[{r0},{c0}:{c0+8}] = {r2[r0, c0:c0+8].tolist()}")
         raise AssertionError("\n".join(msg))
     return float(err.max())
+
+
+class FixtureTokenizer:
+    """Replays tests/golden/tokens_*.json: what the reference's tokenizer (xlm-roberta-base/, absent on the GPU box) returned for
+    the reference's own class-prompt lists under `tokenizer(text=..., return_tensors="pt", padding=True)` (mm_backbone.py:382-383)."""
+
+    def __init__(self, name):
+        import json
+        import os
+        d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"tokens_{name}.json"), encoding="utf-8"))
+        self.texts, self.ids, self.mask = d["texts"], torch.tensor(d["input_ids"]), torch.tensor(d["attention_mask"])
+        self.rows = {t: [i for i, m in zip(r, k) if m] for t, r, k in zip(d["texts"], d["input_ids"], d["attention_mask"])}
+
+    def __call__(self, text, return_tensors="pt", padding=True):
+        """Any sub-list of the fixture's prompts, padded to its longest member with <pad> = 1 like the real tokenizer does."""
+        assert return_tensors == "pt" and padding is True and all(t in self.rows for t in text), "FixtureTokenizer only knows its own prompts"
+        rows = [self.rows[t] for t in text]
+        n = max(len(r) for r in rows)
+        ids = torch.tensor([r + [1] * (n - len(r)) for r in rows])
+        return dict(input_ids=ids, attention_mask=(torch.tensor([[1] * len(r) + [0] * (n - len(r)) for r in rows])))

@@ -58,8 +58,8 @@ class WdError(RuntimeError):
 _lib = None
 
 
-def load(require_gpu=True):
-    """Load the shared library (building it is `__graft_entry__.build()`'s job, not ours)."""
+def load(require_gpu=True, device=0):
+    """Load the shared library (building it is `__graft_entry__.build()`'s job, not ours).  `device`: the ordinal to validate."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
@@ -88,7 +88,7 @@ def load(require_gpu=True):
         _lib = lib
     if require_gpu:
         sm, major, minor = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
-        rc = _lib.wd_device_info(0, ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor))
+        rc = _lib.wd_device_info(int(device), ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor))
         if rc != 0:
             raise WdError("no CUDA device for libwedetect_b200: " + last_error())
         if major.value != 10:

@@ -26,7 +26,8 @@ def init_detector(config, checkpoint=None, palette="none", device="cuda:0", cfg_
         raise NotImplementedError(model_cfg["type"])
     model = YOLOWorldDetector(model_cfg, device=device, precise=precise)
     if checkpoint is not None:
-        sd = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, str) else checkpoint
+        # mmengine checkpoints carry meta / message_hub objects besides tensors: a trusted local file, so weights_only=False
+        sd = torch.load(checkpoint, map_location="cpu", weights_only=False) if isinstance(checkpoint, str) else checkpoint
         model.load_state_dict(sd)
     model.cfg = cfg
     return model.eval()

@@ -9,6 +9,8 @@ Same names, argument meaning and error behaviour; the arithmetic runs in libwede
 `plan.VisionPlan` / `plan.TextPlan`.  There is no PyTorch / CPU fallback: constructing a detector without
 the CUDA library or an sm_100 device raises.
 """
+import collections
+import contextlib
 import itertools
 import os
 
@@ -21,6 +23,38 @@ from .preprocess import Letterbox, decode_images, letterbox_params  # noqa: F401
 from .structures import DetDataSample, InstanceData, instances_for  # noqa: F401
 
 _DEF_TEST_CFG = dict(multi_label=True, nms_pre=30000, score_thr=0.001, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300)
+
+
+class _LRU(collections.OrderedDict):
+    """Bounded cache of per-shape state (plans own every activation buffer of a shape: a serving loop with varying batch
+    sizes / prompt counts / resolutions must not grow without bound).  Evicted entries are dropped; their device buffers and
+    compiled programs go with the last reference."""
+
+    def __init__(self, cap):
+        super().__init__()
+        self.cap = cap
+
+    def get_or_make(self, key, make):
+        if key in self:
+            self.move_to_end(key)
+            return self[key]
+        v = make()
+        self[key] = v
+        while len(self) > self.cap:
+            self.popitem(last=False)
+        return v
+
+
+def _on(device):
+    """Make `device` the current CUDA device for the enclosed library calls (kernel launches, stream lookups, TMA descriptor
+    encoding all act on the current device); a no-op for the CPU wiring tests."""
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
+
+
+def _own(r):
+    """The plan's result buffers are static (the CUDA graph rewrites them every step): hand the caller its own copy, as the
+    reference does (one small device-to-device copy of the packed [B, max, ...] block per step)."""
+    return {k: v.clone() for k, v in r.items()}
 
 
 def _size_from_cfg(model_cfg):
@@ -44,9 +78,12 @@ def resolve_texts(batch_data_samples):
         return None
     if texts and isinstance(texts[0], str):
         texts = [texts]                        # a single prompt list for the whole batch
-    if any(t != texts[0] for t in texts):
-        raise NotImplementedError("per-image text sets that differ inside one batch are not supported")
-    return [t[0] if isinstance(t, (list, tuple)) else t for t in texts[0]]
+    flat = [[t[0] if isinstance(t, (list, tuple)) else t for t in per_img] for per_img in texts]
+    if any(len(f) != len(flat[0]) for f in flat):
+        raise AssertionError("number of sequences not equal in batch")       # mm_backbone.py:378-380
+    if any(f != flat[0] for f in flat):
+        return flat                            # per-image prompt lists (equal counts): predict() runs one group per distinct list
+    return flat[0]
 
 
 def _sample_texts(s):
@@ -57,8 +94,14 @@ def _sample_texts(s):
 class YOLOWorldDetector:
     """Text-conditioned detector facade.  `model_cfg` is the `model=` dict of config/wedetect_*.py."""
 
-    def __init__(self, model_cfg=None, *, size=None, test_cfg=None, device="cuda:0", precise=True, tokenizer=None, cuda_graph=True):
-        L.load(require_gpu=True)
+    def __init__(self, model_cfg=None, *, size=None, test_cfg=None, device="cuda:0", precise=True, tokenizer=None, cuda_graph=True,
+                 zero_copy=False):
+        """precise=True (default): fp16 hi/lo operands, logits within 1e-3 of the fp32 reference; precise=False: the opt-in
+        bf16 mode (faster, does not meet that gate).  zero_copy=True returns views of the plan's static result buffers (valid
+        until the next step on the same shape) instead of copies."""
+        self.device = torch.device(device)
+        L.load(require_gpu=True, device=self.device.index or 0)
+        self.zero_copy = bool(zero_copy)
         self.cuda_graph = bool(cuda_graph) and not os.environ.get("WD_NO_GRAPH")
         self.model_cfg = model_cfg
         self.size = size or _size_from_cfg(model_cfg)
@@ -69,12 +112,14 @@ class YOLOWorldDetector:
             self.test_cfg = dict(model_cfg["test_cfg"])
         if model_cfg is not None and model_cfg.get("mm_neck", False):
             raise NotImplementedError("mm_neck=True (text-guided neck) is not used by any shipped config")
-        self.device = torch.device(device)
+        if not self.test_cfg.get("multi_label", True):
+            # mmdet's single-label branch (argmax class per anchor) is not lowered; no shipped config uses it
+            raise NotImplementedError("test_cfg.multi_label=False is not supported (every shipped config sets multi_label=True)")
         self.precise = precise
         self._tokenizer = tokenizer
-        self._plans = {}
-        self._text_plans = {}
-        self._text_cache = {}
+        self._plans = _LRU(4)
+        self._text_plans = _LRU(8)
+        self._text_cache = _LRU(32)
         self._vw = {}
         self._tw = None
         self._sd = None
@@ -115,14 +160,12 @@ class YOLOWorldDetector:
         """ids / mask: int [S, L] (CPU or device).  Returns L2-normalised embeddings [S, 768] on the device."""
         if self._sd is None:
             raise RuntimeError("load_state_dict first")
-        if self._tw is None:
-            self._tw = weights.prepare_text(self._sd, self.size, self.device, precise=self.precise)
-        S, Lt = ids.shape
-        key = (S, Lt)
-        if key not in self._text_plans:
-            self._text_plans[key] = plan.TextPlan(self._tw, self.size, S, Lt, device=self.device)
-        tp = self._text_plans[key]
-        return tp.run(ids.to(self.device, torch.int32), mask.to(self.device, torch.int32)).clone()
+        with _on(self.device):
+            if self._tw is None:
+                self._tw = weights.prepare_text(self._sd, self.size, self.device, precise=self.precise)
+            S, Lt = ids.shape
+            tp = self._text_plans.get_or_make((S, Lt), lambda: plan.TextPlan(self._tw, self.size, S, Lt, device=self.device))
+            return tp.run(ids.to(self.device, torch.int32), mask.to(self.device, torch.int32)).clone()
 
     def forward_text(self, texts):
         """texts: List[List[str]] (one list of class prompts per image); mm_backbone.py:376-390."""
@@ -131,11 +174,11 @@ class YOLOWorldDetector:
         flat = list(itertools.chain(*texts))
         key = tuple(flat)
         key = (key, num[0])
-        if key not in self._text_cache:       # cached per text set: same tensor object on every call (predict relies on it)
+        def make():                           # cached per text set: same tensor object on every call (predict relies on it)
             tok = self._get_tokenizer()(text=flat, return_tensors="pt", padding=True)
             f = self.encode_tokens(tok["input_ids"], tok["attention_mask"])
-            self._text_cache[key] = f.reshape(-1, num[0], f.shape[-1])
-        return self._text_cache[key]
+            return f.reshape(-1, num[0], f.shape[-1])
+        return self._text_cache.get_or_make(key, make)
 
     def reparameterize(self, texts):
         self.texts = texts
@@ -149,20 +192,25 @@ class YOLOWorldDetector:
 
     # --- vision ---
     def _plan(self, B, H, W, K, dtype):
-        key = (B, H, W, K, dtype)
-        if key not in self._plans:
+        def make():
             fmt = "u8_bgr" if dtype == torch.uint8 else "f32_rgb"
             if fmt not in self._vw:
                 self._vw[fmt] = weights.prepare_vision(self._sd, self.size, self.device, input_format=fmt, precise=self.precise)
             tc = self.test_cfg
             if tc.get("nms", {}).get("type", "nms") != "nms":
                 raise NotImplementedError(f"nms type {tc['nms']['type']}")
+            # mmdet's default nms_pre is 100000 (= "all candidates" for these heads); the device top-k ranks in 16 bits
+            cand = sum(h * w for h, w in schema.level_hw(H, W)) * K
+            nms_pre = min(int(tc.get("nms_pre", 100000)), cand)
+            if nms_pre > 65535:
+                raise NotImplementedError(f"nms_pre={nms_pre} exceeds the 65535 candidates per image the post-process ranks (shipped configs: 30000)")
             p = plan.VisionPlan(self._vw[fmt], self.size, B, H, W, K=K, uni=False, input_dtype=dtype, score_thr=float(tc.get("score_thr", -1)),
-                                nms_pre=int(tc.get("nms_pre", 100000)), iou_thr=float(tc["nms"]["iou_threshold"]),
+                                nms_pre=nms_pre, iou_thr=float(tc["nms"]["iou_threshold"]),
                                 max_per_img=int(tc["max_per_img"]), nms_mode=0, device=self.device)
             p._text_key = None
-            self._plans[key] = p
-        return self._plans[key]
+            return p
+        with _on(self.device):
+            return self._plans.get_or_make((B, H, W, K, dtype), make)
 
     def predict(self, batch_inputs, batch_data_samples, rescale=True):
         if self._sd is None:
@@ -174,6 +222,25 @@ class YOLOWorldDetector:
         flat = resolve_texts(batch_data_samples)
         if isinstance(batch_data_samples, dict):
             batch_data_samples = None          # the dict form carries texts only: no per-image metainfo
+        if flat is not None and flat and isinstance(flat[0], list):
+            # per-image prompt lists that differ inside the batch (mm_backbone.py:376-390 encodes B x K prompts): the similarity
+            # matrix is folded once per distinct list, so run the images group by group and put the results back in order
+            groups = {}
+            for b, f in enumerate(flat):
+                groups.setdefault(tuple(f), []).append(b)
+            out = [None] * B
+            for f, idx in groups.items():
+                sub = [DetDataSample(dict(batch_data_samples[b].metainfo, texts=list(f))) for b in idx] if batch_data_samples else dict(texts=list(f))
+                if batch_data_samples:
+                    res = self.predict(batch_inputs[idx], sub, rescale)
+                    for b, r in zip(idx, res):
+                        s = batch_data_samples[b]
+                        s.pred_instances = r.pred_instances
+                        out[b] = s
+                else:
+                    for b, r in zip(idx, self.predict(batch_inputs[idx], sub, rescale)):
+                        out[b] = r
+            return out
         if flat is not None:
             feats = self.forward_text([flat])
         elif self.text_feats is not None:
@@ -184,6 +251,10 @@ class YOLOWorldDetector:
         feats = feats.reshape(-1, schema.EMBED_DIM)
         K = feats.shape[0]
         p = self._plan(B, H, W, K, batch_inputs.dtype)
+        with _on(self.device):
+            return self._predict_on(p, src, feats, batch_inputs, batch_data_samples, rescale, B, H, W)
+
+    def _predict_on(self, p, src, feats, batch_inputs, batch_data_samples, rescale, B, H, W):
         if p._text_key is not src:            # fold BN * text * exp(scale) only when the text set changes
             p.set_text(feats.contiguous())
             p._text_key = src
@@ -209,7 +280,7 @@ class YOLOWorldDetector:
             p._meta_key = key
         p.image.copy_(batch_inputs, non_blocking=True)
         _run_plan(p, self.cuda_graph)
-        r = p.results()
+        r = p.results() if self.zero_copy else _own(p.results())
         self.last_batch_result = r            # packed device tensors [B,max,...] + counts: bulk readers copy these once
         labels64 = r["labels"].long()         # one conversion for the batch (the reference's labels are int64)
         counts = r["counts"].cpu().tolist()   # the one host sync of the step (the reference has >= 3 per image)
@@ -244,16 +315,18 @@ class SimpleYOLOWorldDetector:
     computes the image x class retrieval scores of the last batch on the device (retrieval_metric.py:365-373)."""
 
     def __init__(self, backbone_size, prompt_dim=768, num_prompts=512, num_proposals=300, *, device="cuda:0", precise=True, extract=False,
-                 cuda_graph=True):
-        L.load(require_gpu=True)
+                 cuda_graph=True, zero_copy=False):
+        self.device = torch.device(device)
+        L.load(require_gpu=True, device=self.device.index or 0)
+        self.zero_copy = bool(zero_copy)
         self.cuda_graph = bool(cuda_graph) and not os.environ.get("WD_NO_GRAPH")
         if backbone_size not in ("base", "large", "tiny"):
             raise ValueError(backbone_size)
         assert prompt_dim == schema.EMBED_DIM
         self.size, self.num_prompts, self.num_proposals = backbone_size, num_prompts, num_proposals
         self.img_size = (1280, 1280) if backbone_size == "large" else (640, 640)
-        self.device, self.precise, self.extract = torch.device(device), precise, bool(extract)
-        self._sd, self._vw, self._plans = None, {}, {}
+        self.precise, self.extract = precise, bool(extract)
+        self._sd, self._vw, self._plans = None, {}, _LRU(4)
         self._scorers, self._cur, self._letterbox = {}, None, {}
         self.last_batch_result = None
 
@@ -272,19 +345,25 @@ class SimpleYOLOWorldDetector:
         if missing:
             raise RuntimeError(f"checkpoint lacks {len(missing)} tensors needed for inference, e.g. {missing[:3]}")
         self._sd = {k: v.detach().float().cpu() for k, v in sd.items()}
-        self._vw, self._plans, self._scorers, self._cur, self._letterbox = {}, {}, {}, None, {}
+        self._vw, self._plans, self._scorers, self._cur, self._letterbox = {}, _LRU(4), {}, None, {}
         return "<All keys matched successfully>"
 
     def _plan(self, B, H, W, dtype=torch.float32):
-        key = (B, H, W, dtype)
-        if key not in self._plans:
+        def make():
             fmt = "u8_rgb" if dtype == torch.uint8 else "f32_rgb"
             if fmt not in self._vw:
                 self._vw[fmt] = weights.prepare_vision(self._sd, self.size, self.device, input_format=fmt, precise=self.precise)
-            self._plans[key] = plan.VisionPlan(self._vw[fmt], self.size, B, H, W, K=self.num_prompts, uni=True, input_dtype=dtype, score_thr=0.0,
-                                               nms_pre=30000, iou_thr=0.7, max_per_img=self.num_proposals, nms_mode=1, extract=self.extract,
-                                               device=self.device)
-        return self._plans[key]
+            return plan.VisionPlan(self._vw[fmt], self.size, B, H, W, K=self.num_prompts, uni=True, input_dtype=dtype, score_thr=0.0,
+                                   nms_pre=30000, iou_thr=0.7, max_per_img=self.num_proposals, nms_mode=1, extract=self.extract,
+                                   device=self.device)
+        key = (B, H, W, dtype)
+        evicted = key not in self._plans and len(self._plans) >= self._plans.cap
+        with _on(self.device):
+            p = self._plans.get_or_make(key, make)
+        if evicted:     # state tied to an evicted plan's buffers
+            self._letterbox = {k: v for k, v in self._letterbox.items() if k in self._plans}
+            self._scorers = {}
+        return p
 
     def _run(self, p, key, B, H, W, ratios, offsets, ori_shapes, rescale):
         meta = torch.zeros(B, 8)
@@ -298,9 +377,11 @@ class SimpleYOLOWorldDetector:
                 meta[b, 6] = float(ratios[b])
             if ori_shapes is not None:
                 clamp[b, 0], clamp[b, 1] = float(ori_shapes[b][1]), float(ori_shapes[b][0])
-        p.set_meta(meta.to(self.device), clamp.to(self.device))
-        _run_plan(p, self.cuda_graph)
-        r = p.results()
+        with _on(self.device):
+            p.set_meta(meta.to(self.device), clamp.to(self.device))
+            _run_plan(p, self.cuda_graph)
+        self._live = p.results()              # the plan's own buffers (score_text reads them in place)
+        r = self._live if self.zero_copy else _own(self._live)
         self.last_batch_result, self._cur = r, key
         counts = r["counts"].cpu().tolist()
         out = [dict(bboxes=r["boxes"][b, :counts[b]], embeddings=r["embeddings"][b, :counts[b]], scores=r["scores"][b, :counts[b]])
@@ -328,7 +409,8 @@ class SimpleYOLOWorldDetector:
         p = self._plan(*key)
         if key not in self._letterbox:
             self._letterbox[key] = Letterbox(p.image)
-        ratios, offsets, ori_shapes = self._letterbox[key].run(arrays)
+        with _on(self.device):
+            ratios, offsets, ori_shapes = self._letterbox[key].run(arrays)
         return self._run(p, key, B, H, W, ratios, offsets, ori_shapes, rescale)
 
     __call__ = forward
@@ -344,10 +426,13 @@ class SimpleYOLOWorldDetector:
         if key not in self._scorers:
             p = self._plans[self._cur]
             r = p.results()
-            sc = RetrievalScorer(text_embedding, p.B, p.max_per_img, device=self.device, precise=self.precise, emb=r["embeddings"],
-                                 scale=r["scales"], bias=r["bias"], counts=r["counts"])
+            with _on(self.device):
+                sc = RetrievalScorer(text_embedding, p.B, p.max_per_img, device=self.device, precise=self.precise, emb=r["embeddings"],
+                                     scale=r["scales"], bias=r["bias"], counts=r["counts"])
             self._scorers = {key: (sc, text_embedding)}      # one live text set at a time (keeps the id() key valid)
-        return self._scorers[key][0].run()
+        with _on(self.device):
+            s = self._scorers[key][0].run()
+        return s if self.zero_copy else s.clone()
 
 
 class XLMRobertaLanguageBackbone:
@@ -357,7 +442,7 @@ class XLMRobertaLanguageBackbone:
     reference reads ../xlm-roberta-{base,large}/) unless one is passed in."""
 
     def __init__(self, ckpt, *, model_name=None, tokenizer=None, device="cuda:0", precise=True):
-        L.load(require_gpu=True)
+        L.load(require_gpu=True, device=torch.device(device).index or 0)
         sd = torch.load(ckpt, map_location="cpu", weights_only=False) if isinstance(ckpt, (str, os.PathLike)) else ckpt
         sd = schema.text_state_dict(sd)
         self.text = schema.text_size_of(sd)                         # 'base' | 'large'
@@ -370,7 +455,7 @@ class XLMRobertaLanguageBackbone:
             raise RuntimeError(f"text tower checkpoint: missing {missing[:3]} ({len(missing)}), size mismatch {bad[:3]}")
         self.device, self.precise = torch.device(device), precise
         self._sd = {k: v.detach().float().cpu() for k, v in sd.items()}
-        self._tw, self._plans = None, {}
+        self._tw, self._plans = None, _LRU(8)
         self._tokenizer, self._model_name = tokenizer, model_name or f"./xlm-roberta-{self.text}/"
         self.language_dim = schema.TEXT[self.text]["hidden"]
 
@@ -388,14 +473,13 @@ class XLMRobertaLanguageBackbone:
         return self._tokenizer
 
     def encode_tokens(self, ids, mask, normalize=False):
-        if self._tw is None:
-            self._tw = weights.prepare_text(self._sd, self.size, self.device, precise=self.precise)
-        key = tuple(ids.shape)
-        if key not in self._plans:
-            self._plans[key] = plan.TextPlan(self._tw, self.size, key[0], key[1], device=self.device)
-        tp = self._plans[key]
-        feats = tp.run(ids.to(self.device, torch.int32), mask.to(self.device, torch.int32))
-        return (feats if normalize else tp.head_out).clone()
+        with _on(self.device):
+            if self._tw is None:
+                self._tw = weights.prepare_text(self._sd, self.size, self.device, precise=self.precise)
+            key = tuple(ids.shape)
+            tp = self._plans.get_or_make(key, lambda: plan.TextPlan(self._tw, self.size, key[0], key[1], device=self.device))
+            feats = tp.run(ids.to(self.device, torch.int32), mask.to(self.device, torch.int32))
+            return (feats if normalize else tp.head_out).clone()
 
     def forward(self, text):
         tok = self.tokenizer(text=list(text), return_tensors="pt", padding=True)
