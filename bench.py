@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the side measurement of the opt-in bf16 mode")
     ap.add_argument("--no-parity-mode", action="store_true", help=argparse.SUPPRESS)   # accepted for old command lines
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the PyTorch-CUDA eager timing of the reference algorithm")
+    ap.add_argument("--workload", default="detect", choices=["detect", "uni_proposals", "corpus"],
+                    help="detect: BASELINE configs[1] (the default bench line); uni_proposals: configs[3] (Base-Uni, 1000 proposals, 8 images per GPU); "
+                         "corpus: configs[4] (Base-Uni extract + image x class scores, 32 images per GPU per step, one all-gather of score rows)")
+    ap.add_argument("--corpus-classes", type=int, default=1203)
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -351,6 +355,114 @@ def other_mode_arm(args, sd, model, plan, data, imgs_u8, dev, e0, e1):
                 note="deviation measured against this run's mode on the same batch; the fp32-reference gates are asserted in tests/test_gpu_e2e.py")
 
 
+def run_side_workload(args):
+    """BASELINE configs[3] / configs[4] on N GPUs: image-sharded replicas of the Uni detector, weak scaling, one NCCL all-gather
+    of fixed-shape rows per step (proposals) or at the end (corpus scores).  Same JSON contract as the default line."""
+    import torch
+    import torch.distributed as dist
+    from oracle import synth
+    from wedetect_b200 import _lib as L, schema
+    from wedetect_b200.detector import SimpleYOLOWorldDetector
+    from wedetect_b200.retrieval import gather_rows
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.set_num_threads(max(1, host_threads() // world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load(require_gpu=True, device=local)
+    precise = args.mode == "parity"
+    prop = args.workload == "uni_proposals"
+    B, H, W, P = (8, 640, 640, 1000) if prop else (32, 640, 640, 300)
+    sd = synth.synth_state_dict("base", seed=0, uni=True, regime="sparse")
+    model = SimpleYOLOWorldDetector("base", 768, 256, P, device=dev, precise=precise, extract=not prop)
+    model.load_state_dict(sd)
+    x = synth.synth_images(B, H, W, seed=2 + rank).to(dev)
+    u8 = [(synth.synth_images(1, H, W, seed=100 + rank * B + i)[0] * 255).to(torch.uint8).permute(1, 2, 0).contiguous().numpy() for i in range(B)]
+    K = args.corpus_classes
+    text = torch.nn.functional.normalize(torch.randn(K, schema.EMBED_DIM, generator=torch.Generator().manual_seed(5)), dim=-1).to(dev)
+    gin = torch.zeros(B, P, 6, device=dev)
+    gout = torch.zeros(world * B, P, 6, device=dev)
+
+    def step_dev():
+        model.forward_tensor(x)
+        if prop:
+            if world > 1:
+                r = model.last_batch_result
+                gin[..., :4], gin[..., 4], gin[..., 5] = r["boxes"], r["scores"], r["counts"].float()[:, None]
+                dist.all_gather_into_tensor(gout, gin)
+            return None
+        return model.score_text(text)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 1.0:
+        step_dev()
+        torch.cuda.synchronize()
+    barrier()
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local, None) as clk:
+        barrier()
+        e0.record()
+        rows = []
+        for _ in range(args.steps):
+            s_ = step_dev()
+            if s_ is not None:
+                rows.append(s_)
+        if not prop:     # the corpus exchange: ONE all-gather of the [N_local, K] score rows (retrieval.gather_rows)
+            allrows = gather_rows(torch.cat(rows, 0), world * B * args.steps)
+        e1.record()
+        clk.poll_until(e1)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count() - l0
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1000.0)
+    # end to end through the facade: decoded uint8 arrays on the host -> pack + H2D + device letterbox + detector -> D2H of the results
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        res = model.forward(u8)
+        if prop:
+            host = [(r["bboxes"].cpu(), r["scores"].cpu()) for r in res]
+            d2h += sum(a.numel() * 4 + b.numel() * 4 for a, b in host)
+        else:
+            sc = model.score_text(text).cpu()
+            d2h += sc.numel() * 4
+    torch.cuda.synchronize()
+    t = torch.tensor([1000 * (time.perf_counter() - t0)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) / 1000.0)
+    if rank == 0:
+        name = "configs[3]: Base-Uni proposals, 256 prompts, 1000 proposals, 8 images per GPU" if prop else \
+               f"configs[4]: Base-Uni corpus extraction (300 proposals + embeddings) + image x class scores vs {K} classes, 32 images per GPU per step"
+        line = dict(metric=f"images/sec, WeDetect-Base-Uni 640x640, {'proposal mode' if prop else 'retrieval corpus extraction'}", value=value, unit="images/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="fp16x2 (hi/lo operand planes, fp32 accumulate)" if precise else "bf16", data="synthetic",
+                    config=dict(workload=f"BASELINE {name}", parallelism=f"dp{world}", mode=args.mode,
+                                exchange=("one NCCL all_gather of [B,1000,6] proposals per step" if prop else f"one NCCL all_gather of [N_local,{K}] score rows at the end") if world > 1 else None,
+                                extrapolation=None if prop else f"100 000 images at this rate: {100000.0 / value:.1f} s on {world} GPU(s)",
+                                l2="activations (GBs per step) far exceed the 126 MB L2"),
+                    e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=world * B * H * W * 3, d2h_bytes_per_step=world * (d2h // args.steps),
+                             api="SimpleYOLOWorldDetector.forward(list of decoded uint8 arrays)" + ("" if prop else " + score_text")),
+                    gpu_launches=int(launches), clocks=clk.summary())
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -587,5 +699,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload != "detect":
+        run_side_workload(a)
     else:
         run_ours(a)

@@ -32,6 +32,28 @@ def _letterboxed_batch(seed=11):
     return x, metas
 
 
+def _assert_same_detections(bx, sc, lb, rbx, rsc, rlb, what, cut=False):
+    """Same detections as the reference: a one-to-one match on (label, box within 0.1 px) with scores within 1e-3, both lists in
+    descending score order; positions may differ only between detections whose reference scores are closer than 1e-3 (the score
+    sort of near-ties).  cut=True: the lists were truncated by score (threshold / top-k), so near-ties at the cut may differ."""
+    assert bool((sc[:-1] >= sc[1:]).all()), f"{what}: not in descending score order"
+    n, m = len(sc), len(rsc)
+    assert n == m or cut, f"{what}: {n} detections, reference {m}"
+    assert n > 0 and m > 0, f"{what}: empty"
+    cost = (bx[:, None, :] - rbx[None, :, :]).abs().amax(-1) + 1e3 * (lb[:, None] != rlb[None, :]).float()
+    j = cost.argmin(1)
+    ok = cost[torch.arange(n), j] <= 0.1
+    if cut:      # unmatched entries must sit at the cut: their score is within 1e-3 of the lowest kept reference score
+        assert bool((ok | ((sc - rsc.min()).abs() <= 1e-3)).all()), f"{what}: detections without a reference counterpart"
+    else:
+        assert bool(ok.all()) and j.unique().numel() == n, f"{what}: detections without a reference counterpart"
+    assert float((sc[ok] - rsc[j[ok]]).abs().max()) <= 1e-3, f"{what}: scores differ"
+    moved = (j != torch.arange(n)) & ok
+    for i in moved.nonzero().flatten().tolist():
+        if i < m:
+            assert abs(float(rsc[i] - rsc[j[i]])) <= 1e-3, f"{what}: position {i} holds the reference's {int(j[i])} and their scores are not a near-tie"
+
+
 def test_infer_wedetect_chain_matches_oracle():
     from oracle import functional as Fn, synth
     from oracle.postprocess import postprocess_ref
@@ -67,17 +89,14 @@ def test_infer_wedetect_chain_matches_oracle():
         n = int(det["counts"][b])
         p = out[b].pred_instances
         assert len(p.scores) == n and p.labels.dtype == torch.int64 and p.bboxes.dtype == torch.float32
-        key = lambda bx, lb: sorted(zip(lb.tolist(), [tuple(round(v, 0) for v in r) for r in bx.tolist()]))  # noqa: E731
-        # identical (label, score-order) assignment; boxes in ORIGINAL-image coordinates within 0.1 px, inside the image
-        assert torch.equal(p.labels.cpu(), det["labels"][b, :n].long()), f"image {b}: labels / order differ"
-        assert float((p.scores.cpu() - det["scores"][b, :n]).abs().max()) <= 1e-3
-        assert float((p.bboxes.cpu() - det["boxes"][b, :n]).abs().max()) <= 0.1
+        _assert_same_detections(p.bboxes.cpu(), p.scores.cpu(), p.labels.cpu(), det["boxes"][b, :n], det["scores"][b, :n], det["labels"][b, :n].long(), f"image {b}")
         oh, ow = metas[b]["ori_shape"]
         assert float(p.bboxes.min()) >= 0 and float(p.bboxes[:, 0::2].max()) <= ow and float(p.bboxes[:, 1::2].max()) <= oh
         q = plain[b].pred_instances
         assert torch.equal(q.labels, p.labels) and torch.equal(q.bboxes, p.bboxes) and torch.equal(q.scores, p.scores)
         # ---- infer_wedetect.py:117-126 on the device results ----
-        thr, max_dets = 0.01, 20
+        assert n > 45
+        thr, max_dets = float(det["scores"][b, 40]) - 1e-6, 20     # ~40 detections survive the threshold, top-k keeps 20 of them
         sel = p[p.scores.float() > thr]
         if len(sel.scores) > max_dets:
             sel = sel[sel.scores.float().topk(max_dets)[1]]
@@ -88,8 +107,9 @@ def test_infer_wedetect_chain_matches_oracle():
         if len(rs) > max_dets:
             idx = rs.topk(max_dets)[1]
             rs, rb, rl = rs[idx], rb[idx], rl[idx]
-        assert arr["bboxes"].shape == (len(rs), 4) and arr["labels"].tolist() == rl.tolist()
-        assert abs(arr["scores"] - rs.numpy()).max() <= 1e-3 and abs(arr["bboxes"] - rb.numpy()).max() <= 0.1
+        assert arr["bboxes"].shape == (len(rs), 4) and arr["labels"].dtype.kind == "i"
+        _assert_same_detections(torch.from_numpy(arr["bboxes"]), torch.from_numpy(arr["scores"]), torch.from_numpy(arr["labels"]), rb, rs, rl.long(),
+                                f"image {b} after the infer tail", cut=True)
     # results handed to the caller are the caller's: a later step must not rewrite them
     keep = out[0].pred_instances.bboxes.clone()
     model.test_step(dict(inputs=x.flip(0).to(D), data_samples=[DetDataSample(dict(m)) for m in metas]))
