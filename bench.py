@@ -414,6 +414,7 @@ def run_side_workload(args):
         rows = []
         for _ in range(args.steps):
             s_ = step_dev()
+            clk.sample()
             if s_ is not None:
                 rows.append(s_)
         if not prop:     # the corpus exchange: ONE all-gather of the [N_local, K] score rows (retrieval.gather_rows)

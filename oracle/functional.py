@@ -122,7 +122,7 @@ def head(sd, feats, text=None, prompts=None):
         logits = torch.einsum("bchw,kc->bkhw", e, w) * sd[c + "logit_scale"].exp() + sd[c + "bias"]
         r = _head_stack(sd, HM + f"reg_preds.{l}.", f)
         r = r.reshape(B, 4, schema.REG_MAX, H * W).permute(0, 3, 1, 2).softmax(3)
-        dist = r.matmul(torch.arange(schema.REG_MAX, dtype=r.dtype))
+        dist = r.matmul(torch.arange(schema.REG_MAX, dtype=r.dtype, device=r.device))
         outs.append(dict(embed=e.permute(0, 2, 3, 1).reshape(B, H * W, -1), logits=logits.permute(0, 2, 3, 1).reshape(B, H * W, -1), dist=dist, dfl_prob=r))
     return outs
 
