@@ -36,6 +36,8 @@ def main():
         ("s2 pw1 none f32", 51200, 512, 2048, "f", L.ACT_NONE, False, False),
         ("s2 pw2 res f32", 51200, 2048, 512, "f", L.ACT_NONE, True, True),
         ("s2 pw2 none f16x2", 51200, 2048, 512, "h", L.ACT_NONE, False, False),
+        ("s2 pw2 none f32", 51200, 2048, 512, "f", L.ACT_NONE, False, False),
+        ("s2 pw2 bias f32", 51200, 2048, 512, "f", L.ACT_NONE, False, True),
         ("s0 pw1 gelu f16x2", 819200, 128, 512, "h", L.ACT_GELU, False, True),
         ("s0 pw2 res f32", 819200, 512, 128, "f", L.ACT_NONE, True, True),
         ("s1 pw1 gelu f16x2", 204800, 256, 1024, "h", L.ACT_GELU, False, True),
@@ -52,7 +54,7 @@ def main():
         bias = torch.randn(N, device=dev) if use_bias else None
         gamma = torch.randn(N, device=dev) if use_res else None
         resid = torch.randn(M, N, device=dev) if use_res else None
-        for bn, lblk in ((None, 1), (None, 2), (128, 1)):
+        for bn, lblk in ((None, 2),):
             try:
                 op = ops.linear(A, W, C, bias=bias, gamma=gamma, resid=resid, act=act, block_n=bn)
                 op.i[40] = lblk
