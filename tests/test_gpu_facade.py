@@ -141,6 +141,49 @@ def test_per_image_prompt_lists_inside_one_batch():
         model.test_step(dict(inputs=x.to(D), data_samples=[mk(0), bad]))
 
 
+def test_eval_loop_groups_bs1_batches_on_the_device():
+    """test.py's loop (bs-1 loader, config/wedetect_base.py:197-204) through wedetect_b200.loop.TestLoop: the device runs grouped
+    batches, the evaluator receives every image's own detections in loader order, identical to one test_step per image; then the
+    WeDetect-Ref hand-off keeps Uni proposals on the device."""
+    from oracle import synth
+    from wedetect_b200.api import DetDataSample, SimpleYOLOWorldDetector, TestLoop, init_detector, proposals_for_ref
+    tok = FixtureTokenizer("coco_zh")
+    sd = synth.synth_state_dict("base", seed=0, with_text=True, regime="sparse")
+    model = init_detector(CFG, checkpoint=dict(state_dict=sd), device=D)
+    model._tokenizer = tok
+    texts = [[t] for t in tok.texts[:12]]
+    g = torch.Generator().manual_seed(21)
+    imgs = (torch.rand(5, 3, 320, 320, generator=g) * 255).to(torch.uint8)
+    mk = lambda i: DetDataSample(dict(img_id=i, ori_shape=(320, 320), img_shape=(320, 320), scale_factor=(1.0, 1.0), pad_param=(0.0, 0.0, 0.0, 0.0), texts=texts))  # noqa: E731
+
+    class Loader(list):
+        dataset = list(range(5))
+
+    class Collect:
+        def __init__(self):
+            self.res = []
+
+        def process(self, data_samples, data_batch):
+            self.res += data_samples
+
+        def evaluate(self, size):
+            return dict(size=size, n=len(self.res))
+
+    ev = Collect()
+    assert TestLoop(model, Loader(dict(inputs=[imgs[i]], data_samples=[mk(i)]) for i in range(5)), ev, group=4).run() == dict(size=5, n=5)
+    for i, d in enumerate(ev.res):
+        alone = model.test_step(dict(inputs=imgs[i:i + 1].to(D), data_samples=[mk(i)]))[0].pred_instances
+        assert d["img_id"] == i and len(alone.scores) > 0
+        assert torch.equal(d["pred_instances"]["labels"], alone.labels) and torch.equal(d["pred_instances"]["bboxes"], alone.bboxes)
+        assert torch.equal(d["pred_instances"]["scores"], alone.scores)
+    # WeDetect-Ref hand-off (infer_wedetect_ref.py:27,67-74,91)
+    uni = SimpleYOLOWorldDetector("base", 768, 256, 100, device=D)
+    uni.load_state_dict(synth.synth_state_dict("base", seed=0, uni=True, regime="sparse"))
+    arr = [imgs[i].flip(0).permute(1, 2, 0).contiguous().numpy() for i in range(2)]
+    boxes, counts = proposals_for_ref(uni(arr), torch.bfloat16)
+    assert counts == [100, 100] and all(b.is_cuda and b.dtype == torch.bfloat16 and b.shape == (100, 4) for b in boxes)
+
+
 @pytest.mark.parametrize("name,size", [("coco_zh", "base"), ("lvis_v1_zh", "large")])
 def test_text_tower_reference_token_shapes(name, size):
     """The text tower at the token shapes of BASELINE configs 2 and 3: 81 x 8 (COCO prompts, XLM-R base) and 1204 x 9 (LVIS

@@ -5,6 +5,8 @@
     generate_proposal.py:   SimpleYOLOWorldDetector(...)                ->  from wedetect_b200.api import SimpleYOLOWorldDetector
     eval_retrieval/extract_embedding.py:  SimpleYOLOWorldDetector(...)  ->  SimpleYOLOWorldDetector(..., extract=True) + extract_corpus
     eval_retrieval/retrieval_metric.py:   the per-image scoring loop    ->  score_saved / predictions_from_scores / evaluate_retrieval_per_class
+    test.py / dist_test.sh:               runner.test() (mmengine TestLoop)  ->  TestLoop(model, dataloader, evaluator).run()
+    infer_wedetect_ref.py:                proposals -> numpy -> list -> cuda  ->  proposals_for_ref(outputs, model.dtype)
 See INTEGRATION.md for the exact diffs.
 """
 import torch
@@ -13,6 +15,7 @@ from .config import Config, parse_cfg_options  # noqa: F401
 from .detector import SimpleYOLOWorldDetector, XLMRobertaLanguageBackbone, YOLOWorldDetector  # noqa: F401
 from .retrieval import (RetrievalScorer, evaluate_retrieval_per_class, extract_corpus, predictions_from_scores,  # noqa: F401
                         save_corpus, score_saved)
+from .loop import TestLoop, proposals_for_ref, sample_to_dict  # noqa: F401
 from .structures import DetDataSample, InstanceData  # noqa: F401
 
 
