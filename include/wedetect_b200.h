@@ -101,7 +101,7 @@ enum wd_op_kind {
      * p: 0 ids i32[S,L] 1 mask i32[S,L] 2 word f32[V,Hd] 3 pos f32[P,Hd] 4 type f32[Hd] 5 ln_w 6 ln_b
      *    7 out f32 [S*L,Hd]  8 out bf16 */
     WD_OP_TEXT_EMBED = 7,
-    /* Short-sequence multi-head self-attention (L <= 32), one warp per (sequence, head).
+    /* Short-sequence multi-head self-attention: L <= 32 one warp per (sequence, head); 32 < L <= 128 one block per (sequence, head).
      * i: 0 S 1 L 2 heads 3 head_dim 4 ld_qkv (= 3*Hd) 30 out plane stride   f: 0 scale
      * p: 0 qkv f32 [S*L, 3*Hd]  1 mask i32[S,L]  2 out bf16 [S*L,Hd] */
     WD_OP_ATTN_SMALL = 8,

@@ -133,6 +133,23 @@ def test_text_embed_and_attention():
     report_close("attn", out.value(), R.attn_ref(qkv, mask, heads, 0.125), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("L", [33, 64, 100, 128])
+def test_attention_longer_prompts(L):
+    """Prompts of more than 32 tokens (the reference pads to the longest prompt, no truncation: mm_backbone.py:382-383)."""
+    from wedetect_b200 import ops
+    from wedetect_b200.ops import P3
+    S, Hd, heads = 3, 768, 12
+    g = _g(17)
+    qkv = torch.randn(S * L, 3 * Hd, generator=g)
+    mask = torch.ones(S, L, dtype=torch.int32)
+    mask[1, L // 2:] = 0
+    mask[2, 5:] = 0
+    out = P3.zeros((S * L, Hd), D, True)
+    _run(ops.attn_small(qkv.to(D), mask.to(D), out, heads, 0.125))
+    ref = R.attn_ref(qkv, mask, heads, 0.125)
+    report_close(f"attn L={L}", out.value(), ref, rtol=1e-5, atol=1e-5)
+
+
 def test_l2norm_gather_fold():
     from wedetect_b200 import ops
     g = _g(8)

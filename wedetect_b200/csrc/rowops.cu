@@ -579,6 +579,75 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const float* __restrict
     }
 }
 
+// Longer prompts (32 < L <= 128): one block of 4 warps per (sequence, head); K and V of the head stay in shared memory, a warp
+// owns queries warp, warp + 4, ...; a lane scores keys lane, lane + 32, ... (same arithmetic as above, key by key).
+__global__ void __launch_bounds__(128) attn_mid_kernel(const float* __restrict__ qkv, const int* __restrict__ mask, int S, int L, int heads, int ld,
+                                                       float scale, __nv_bfloat16* out_hi, long long out_ps) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int Hd = heads * 64;
+    float* K = sm;
+    float* V = K + L * 65;
+    float* Q = V + L * 65;      // 4 x 64: the query row each warp is working on
+    for (int t = threadIdx.x; t < L * 64; t += blockDim.x) {
+        const int j = t >> 6, d = t & 63;
+        const float* row = qkv + (long long)(s * L + j) * ld + h * 64 + d;
+        K[j * 65 + d] = row[Hd];
+        V[j * 65 + d] = row[2 * Hd];
+    }
+    __syncthreads();
+    constexpr int kMaxK = 4;    // keys per lane: L <= 128
+    bool ok[kMaxK];
+#pragma unroll
+    for (int u = 0; u < kMaxK; ++u) {
+        const int j = lane + 32 * u;
+        ok[u] = j < L && mask[s * L + (j < L ? j : 0)] != 0;
+    }
+    for (int i = warp; i < L; i += 4) {
+        const float* qrow = qkv + (long long)(s * L + i) * ld + h * 64;
+        Q[warp * 64 + lane] = qrow[lane];
+        Q[warp * 64 + lane + 32] = qrow[lane + 32];
+        __syncwarp();
+        float sc[kMaxK], mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < kMaxK; ++u) {
+            const int j = lane + 32 * u;
+            sc[u] = -INFINITY;
+            if (ok[u]) {
+                float a = 0.f;
+#pragma unroll 16
+                for (int d = 0; d < 64; ++d) a = fmaf(Q[warp * 64 + d], K[j * 65 + d], a);
+                sc[u] = a * scale;
+            }
+            mx = fmaxf(mx, sc[u]);
+        }
+        mx = warp_max(mx);
+        float e[kMaxK], den = 0.f;
+#pragma unroll
+        for (int u = 0; u < kMaxK; ++u) {
+            e[u] = ok[u] ? expf(sc[u] - mx) : 0.f;
+            den += e[u];
+        }
+        den = warp_sum(den);
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int u = 0; u < kMaxK; ++u) {
+            const float pj = e[u] / den;
+            const int n = min(32, L - 32 * u);
+            for (int j = 0; j < n; ++j) {
+                const float pp = __shfl_sync(0xffffffffu, pj, j);
+                o0 = fmaf(pp, V[(32 * u + j) * 65 + lane], o0);
+                o1 = fmaf(pp, V[(32 * u + j) * 65 + lane + 32], o1);
+            }
+        }
+        const long long idx = (long long)(s * L + i) * Hd + h * 64;
+        store_bf16x1(out_hi, out_ps, idx + lane, o0);
+        store_bf16x1(out_hi, out_ps, idx + lane + 32, o1);
+        __syncwarp();
+    }
+}
+
 __global__ void l2norm_rows_kernel(const float* __restrict__ in, int S, int C, int ld_in, float* out) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= S) return;
@@ -1089,13 +1158,21 @@ int compile_rowops(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
         case WD_OP_ATTN_SMALL: {
             const int S = I[0], L = I[1], heads = I[2], hd = I[3], ld = I[4];
             const float scale = F[0];
-            WD_REQUIRE(S > 0 && L > 0 && L <= 32 && hd == 64 && heads > 0 && P[0] && P[1] && P[2], "attn_small: needs L <= 32 and head_dim == 64");
+            WD_REQUIRE(S > 0 && L > 0 && L <= 128 && hd == 64 && heads > 0 && P[0] && P[1] && P[2], "attn_small: needs L <= 128 tokens and head_dim == 64");
             const float* qkv = (const float*)P[0];
             const int* mask = (const int*)P[1];
             __nv_bfloat16* oh = (__nv_bfloat16*)P[2];
             const long long ol = I[30];
             const int smem = 4 * 3 * L * 65 * (int)sizeof(float);
+            const int smem_mid = (2 * L * 65 + 4 * 64) * (int)sizeof(float);
             f->fn = [=](cudaStream_t s) {
+                if (L > 32) {   // longer prompts: one block per (sequence, head)
+                    WD_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(attn_mid_kernel), (2 * 128 * 65 + 4 * 64) * 4));
+                    attn_mid_kernel<<<S * heads, 128, smem_mid, s>>>(qkv, mask, S, L, heads, ld, scale, oh, ol);
+                    WD_CHECK_CUDA(cudaGetLastError());
+                    count_launch();
+                    return 0;
+                }
                 WD_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(attn_small_kernel), 4 * 3 * 32 * 65 * 4));
                 attn_small_kernel<<<(S * heads + 3) / 4, 128, smem, s>>>(qkv, mask, S, L, heads, ld, scale, oh, ol);
                 WD_CHECK_CUDA(cudaGetLastError());

@@ -340,8 +340,8 @@ class TextPlan:
     def __init__(self, weights, size, S, Lt, device="cuda:0"):
         t = schema.TEXT[schema.SIZES[size]["text"]]
         H, I, nh = t["hidden"], t["inter"], t["heads"]
-        if Lt > 32:
-            raise ValueError(f"text sequences of {Lt} tokens exceed the 32-token attention kernel")
+        if Lt > 128:
+            raise ValueError(f"text sequences of {Lt} tokens exceed the 128-token attention kernels")
         self.S, self.Lt, self.dev = S, Lt, torch.device(device)
         W_, dev, T = weights, self.dev, S * Lt
         pr = weights.precise
