@@ -46,7 +46,8 @@ def _assert_same_detections(bx, sc, lb, rbx, rsc, rlb, what, cut=False):
     if cut:      # unmatched entries must sit at the cut: their score is within 1e-3 of the lowest kept reference score
         assert bool((ok | ((sc - rsc.min()).abs() <= 1e-3)).all()), f"{what}: detections without a reference counterpart"
     else:
-        assert bool(ok.all()) and j.unique().numel() == n, f"{what}: detections without a reference counterpart"
+        # (boxes are clamped to the image AFTER the NMS, so distinct anchors can end as identical boxes: match both ways, not one-to-one)
+        assert bool(ok.all()) and bool((cost.amin(0) <= 0.1).all()), f"{what}: detections without a counterpart"
     assert float((sc[ok] - rsc[j[ok]]).abs().max()) <= 1e-3, f"{what}: scores differ"
     moved = (j != torch.arange(n)) & ok
     for i in moved.nonzero().flatten().tolist():
