@@ -430,6 +430,10 @@ def run_side_workload(args):
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max / 1000.0)
     # end to end through the facade: decoded uint8 arrays on the host -> pack + H2D + device letterbox + detector -> D2H of the results
+    for _ in range(3):          # the uint8 entry point has its own plan (+ CUDA graph): build it outside the timed region
+        model.forward(u8)
+        if not prop:
+            model.score_text(text)
     barrier()
     t0 = time.perf_counter()
     d2h = 0
