@@ -51,8 +51,8 @@ enum wd_op_kind {
      *   transformers XLMRobertaModel Linear layers (mm_backbone.py:382-386)
      * i: 0..2 D0,D1,D2 (row space, row m = (d2*D1+d1)*D0+d0)   3..5 E0,E1,E2 (tile extents, E0*E1*E2<=128)
      *    6 Kc (K per tap, %64==0)  7 ntaps (1|9)  8 N  9..11 A strides of d0,d1,d2 (elements)
-     *    12 ldb  13 block_n (64|128|256)  14 out_dtype (0 bf16, 1 f32)  15 act (wd_act)
-     *    16 resid_dtype (0 none, 1 bf16, 2 f32)  17 ld_res  18 group_cols  19 n_groups
+     *    12 ldb  13 block_n (64|128|256; fp16 hi/lo mode: 64|128)  14 out_dtype (0 16-bit: bf16, or fp16 hi/lo planes when planes = 2; 1 f32)  15 act (wd_act)
+     *    16 resid_dtype (0 none, 1 16-bit (format as A), 2 f32)  17 ld_res  18 group_cols  19 n_groups
      *    20..22 C strides of d0,d1,d2 (elements)  23 C stride of group  24 epi_mode (0 store, 1 DFL)
      *    25 tap_w (3 for 3x3)  26 pad (1 for 3x3)  27 group_valid (columns of a group present in memory, 0 = group_cols)
      *    28 K_valid (channels of A present in memory, 0 = Kc; TMA zero-fills up to Kc)
@@ -63,7 +63,8 @@ enum wd_op_kind {
      *    37 no_warp_store (1: one 128-row TMA store per epilogue warpgroup instead of one 32-row store per warp; A/B switch)
      *    35 exact_act (1: erf-GELU / exp-SiLU instead of the MUFU.TANH forms used for bf16 outputs of the fast path)
      *    30 planes (0|1 bf16 fast mode, 2 fp16 hi/lo)  31 A plane stride  32 B plane stride  33 C plane stride  34 resid plane stride
-     *    40 lblk (fp16 hi/lo mode: 64-wide k-blocks accumulated in TMEM before the partial sum moves to fp32 registers, 0 = 1)
+     *    40 lblk (fp16 hi/lo mode: 64-wide k-blocks (1|2) accumulated in TMEM before the partial sum moves to fp32 registers)
+     *    41 no_trunc_comp (1: do not compensate the tensor pipe's truncating accumulation; measurement switch)
      * f: 0 resid_alpha  1 acc_scale (fp16 hi/lo mode: 1 / (A scale * B scale), 0 = 1)
      * p: 0 A  1 B [N, ntaps*Kc]  2 C  3 bias f32[N]  4 gamma f32[N]  5 resid
      * out = resid*alpha + gamma * act(acc * acc_scale + bias)        (each term optional) */

@@ -96,3 +96,28 @@ def test_standalone_text_tower_facade_wires_on_cpu(monkeypatch):
     kinds = [op.kind for op in tp.program.ops]
     assert kinds[0] == L.OP_TEXT_EMBED and kinds[-1] == L.OP_L2NORM_ROWS and kinds.count(L.OP_ATTN_SMALL) == 12
     assert m.encode_tokens(torch.zeros(2, 4, dtype=torch.long), torch.ones(2, 4, dtype=torch.long), normalize=True).shape == (2, 768)
+
+
+def test_hi_lo_planes_and_scales_cpu():
+    """Host side of the default operand format: fp16 hi/lo planes at a power-of-two scale reconstruct fp32 to ~2^-24; the GEMM
+    record carries 1 / (A scale * W scale) and the accumulator block length."""
+    import torch
+    from wedetect_b200 import _lib as L, ops
+    from wedetect_b200.ops import P3
+    g = torch.Generator().manual_seed(0)
+    for mag in (1e-3, 0.02, 1.0, 300.0):
+        w = torch.randn(64, 128, generator=g) * mag
+        p = P3.from_f32(w)
+        s = p.scale
+        assert s == 2.0 ** round(__import__("math").log2(s)) and 8192 <= float(w.abs().max()) * s < 16384
+        assert p.t.dtype == torch.float16 and p.ps == w.numel()
+        assert float((p.value() - w).abs().max()) <= float(w.abs().max()) * 2.0 ** -22
+    a = P3.from_f32(torch.randn(256, 128, generator=g), scale=ops.ACT_SCALE)
+    w = P3.from_f32(torch.randn(64, 128, generator=g) * 0.05)
+    c = torch.zeros(256, 64)
+    op = ops.linear(a, w, c)
+    assert op.i[30] == 2 and op.i[31] == a.ps and op.i[32] == w.ps and op.i[13] == 64 and op.i[40] == ops.SPLIT_LBLK
+    assert abs(op.f[1] - 1.0 / (ops.ACT_SCALE * w.scale)) < 1e-12
+    big = P3.from_f32(torch.tensor([[1e9, -1e9, 1.0, 0.0]]), scale=4.0)       # out-of-range values saturate, no inf
+    assert torch.isfinite(big.value()).all() and float(big.value()[0, 2]) == 1.0
+    assert ops.ACT_SCALE == L.ACT_PLANE_SCALE == 4.0

@@ -5,19 +5,23 @@
 // products whose weight is >= 2^-12, (a_lo b_hi), (a_hi b_lo), (a_hi b_hi), on the fp16 tensor pipe with fp32 accumulation
 // in TMEM: three UMMAs where an fp32 FMA pipe would need 2 x 16 x more issue slots (the dropped a_lo b_lo is 2^-24 relative).
 //
-// What makes the result match an fp32 reference to ~1e-7 instead of ~1e-5:
-//   * the tensor pipe TRUNCATES when it adds a k-step's products to the running fp32 accumulator, a bias of ~2^-24 per step
-//     relative to the accumulator.  So an accumulator only lives for `lblk` 64-wide k-blocks; it then moves to fp32 REGISTERS of
-//     the epilogue warps, which sum the blocks with round-to-nearest adds while the tensor pipe fills the other TMEM buffer.
-//   * inside a block the two small cross products are issued BEFORE the large one: they are added while the accumulator is still
-//     ~2^-11 of its final size, so their truncation is 2^-11 smaller too; one TMEM accumulator serves all three products,
-//     which is what lets a 256-column tile double-buffer in the 512 TMEM columns.
+// What makes the result match an fp32 reference to ~1e-7 instead of ~1e-5 (measurements: tools/trunc_probe.py):
+//   * the tensor pipe TRUNCATES when it adds a k-step's products to the running fp32 accumulator.  So a TMEM accumulator only
+//     lives for a BLOCK of `lblk` (1 or 2) 64-wide k-blocks; the epilogue warps then move the block sum to fp32 REGISTERS and add
+//     it there with round-to-nearest adds, while the tensor pipe fills another of the four TMEM buffers.
+//   * inside a block the small cross products (of all its stages) are issued BEFORE the hi x hi products: they are added while
+//     the accumulator is still ~2^-11 of its final size, so only the 4 * lblk large adds truncate at full size; one TMEM
+//     accumulator serves all three products.
+//   * what remains is a data- and K-independent relative shrink of every block sum (8.9e-8 for one k-block, 1.55e-7 for two);
+//     the epilogue multiplies it back (GemmParams::trunc_comp), leaving an unbiased error of ~1e-7 rel-rms per GEMM.
 //
-// Structure (same skeleton as gemm_tc.cu): warp 0 TMA producer (A hi/lo bricks, B hi/lo tiles, 128-byte swizzle), warp 1 UMMA
-// issuer, warp 2 TMEM allocator, warps 4..11 epilogue (per warp: 32 accumulator rows x BN/2 columns in registers; bias /
-// activation / LayerScale / residual in fp32 with the exact erf / exp forms; fp16 hi/lo or fp32 output staged in swizzled shared
-// memory and written by per-warp TMA stores).  128- and 256-wide tiles run as CTA pairs (cta_group::2, M = 256): each SM stages
-// its own A rows and half of the B rows, so a UMMA reads 6-8 KB of shared memory per 64-128 tensor-pipe cycles instead of 8-12.
+// Structure (same skeleton as gemm_tc.cu): 640 threads; warp 0 TMA producer (A hi/lo bricks, B hi/lo tiles, 128-byte swizzle,
+// four stages), warp 1 UMMA issuer, warp 2 TMEM allocator, warps 4..19 epilogue: warp (quarter, cg) owns TMEM lanes 32 quarter..
+// and accumulator columns 32 cg..; per block one tcgen05.ld + 16 packed adds; per tile bias / exact erf-GELU / SiLU / ReLU /
+// LayerScale / residual on packed fp32 pairs (epi_split.cuh), then fp16 hi / lo planes (64-column chunks staged in swizzled
+// shared memory by the two warps of a chunk, one TMA store per plane) or fp32 (the pair's buffer used in turn).  128-wide tiles
+// run as CTA pairs (cta_group::2, M = 256): each SM stages its own A rows and half of the B rows, so a UMMA reads 6 KB of shared
+// memory per 64 tensor-pipe cycles instead of 8.  64-wide single-CTA tiles serve N <= 64 and the DFL epilogue.
 //
 // Reference arithmetic replaced: see include/wedetect_b200.h (WD_OP_GEMM).
 #include "gemm_params.h"
