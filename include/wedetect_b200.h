@@ -65,6 +65,8 @@ enum wd_op_kind {
      *    30 planes (0|1 bf16 fast mode, 2 fp16 hi/lo)  31 A plane stride  32 B plane stride  33 C plane stride  34 resid plane stride
      *    40 lblk (fp16 hi/lo mode: 64-wide k-blocks (1|2) accumulated in TMEM before the partial sum moves to fp32 registers)
      *    41 no_trunc_comp (1: do not compensate the tensor pipe's truncating accumulation; measurement switch)
+     *    42 no_red_store (1: an in-place fp32 residual with alpha == 1 is loaded and added in registers instead of being added by the
+     *       TMA store in the L2; same bits either way; measurement switch)
      * f: 0 resid_alpha  1 acc_scale (fp16 hi/lo mode: 1 / (A scale * B scale), 0 = 1)
      * p: 0 A  1 B [N, ntaps*Kc]  2 C  3 bias f32[N]  4 gamma f32[N]  5 resid
      * out = resid*alpha + gamma * act(acc * acc_scale + bias)        (each term optional) */

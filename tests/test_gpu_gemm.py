@@ -255,6 +255,28 @@ def test_linear_split_precise():
     report_close("linear precise f32 residual", X, ref3, rtol=2e-6, atol=2e-6)
 
 
+@pytest.mark.parametrize("M,K,N", [(515, 256, 192), (4096, 512, 128), (1024, 2048, 512)])
+def test_inplace_residual_tma_add_equals_fused_add(M, K, N, monkeypatch):
+    """x += gamma * (A W^T + b) in place: the store that adds the tile in the L2 (cp.reduce.async.bulk.tensor .add) and the epilogue
+    that loads the residual rows and adds in registers round once per element either way - bit-identical results."""
+    from wedetect_b200 import ops
+    from wedetect_b200.ops import P3
+    g = torch.Generator().manual_seed(29)
+    A, Wt = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    bias, gamma, x = torch.randn(N, generator=g), torch.rand(N, generator=g) + 0.5, torch.randn(M, N, generator=g) * 3
+    d = _dev()
+    Ap, Wp = P3.from_f32(A, d, scale=ops.ACT_SCALE), P3.from_f32(Wt, d)
+    got = []
+    for no_red in (0, 1):
+        monkeypatch.setattr(ops, "NO_RED_STORE", no_red)
+        X = x.clone().to(d)
+        _run(ops.linear(Ap, Wp, X, bias=bias.to(d), gamma=gamma.to(d), resid=X, alpha=1.0))
+        got.append(X.cpu())
+    assert torch.equal(got[0], got[1])
+    ref = (x.double() + gamma.double() * (A.double() @ Wt.double().t() + bias.double())).float()
+    report_close("in-place residual", got[0], ref, rtol=2e-6, atol=4e-6)
+
+
 def test_conv3x3_split_precise():
     from wedetect_b200 import ops
     from wedetect_b200.ops import P3

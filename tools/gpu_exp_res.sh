@@ -1,0 +1,12 @@
+#!/bin/bash
+# residual-path experiment: pw2 sweep lines + GEMM parity + e2e parity + one bench line
+mkdir -p gpurun_out
+python tools/split_sweep.py gpurun_out/split_sweep_res.json 2>&1 | grep -E "pw2" | tail -30
+timeout 900 python -m pytest tests/test_gpu_gemm.py -m gpu -x -q 2>&1 | tail -3
+bash tools/gpu_e2e.sh "north_star or benched" 2>&1 | grep -v "^\s*$" | cut -c1-330 | tail -12
+timeout 420 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-fast-mode --no-torch-eager --profile-ops gpurun_out/r2_ops_res.json > gpurun_out/r2_bench_res.json 2> gpurun_out/r2_bench_res.err
+python -c "
+import json;d=json.load(open('gpurun_out/r2_bench_res.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['clocks'])
+p=json.load(open('gpurun_out/r2_ops_res.json'))
+for k,v in p['families'].items(): print(k, round(v['ms'],3), v['launches'], v['tflops'] and round(v['tflops'],1))
+"; tail -3 gpurun_out/r2_bench_res.err

@@ -38,6 +38,9 @@ def main():
         ("s2 pw2 none f16x2", 51200, 2048, 512, "h", L.ACT_NONE, False, False),
         ("s2 pw2 none f32", 51200, 2048, 512, "f", L.ACT_NONE, False, False),
         ("s2 pw2 bias f32", 51200, 2048, 512, "f", L.ACT_NONE, False, True),
+        ("s2 pw2 gamma-only f32", 51200, 2048, 512, "f", L.ACT_NONE, "gamma", True),
+        ("s2 pw2 resid-only f32", 51200, 2048, 512, "f", L.ACT_NONE, "resid", True),
+        ("s2 pw2 resid-inplace f32", 51200, 2048, 512, "f", L.ACT_NONE, "inplace", True),
         ("s0 pw1 gelu f16x2", 819200, 128, 512, "h", L.ACT_GELU, False, True),
         ("s0 pw2 res f32", 819200, 512, 128, "f", L.ACT_NONE, True, True),
         ("s1 pw1 gelu f16x2", 204800, 256, 1024, "h", L.ACT_GELU, False, True),
@@ -52,8 +55,10 @@ def main():
         W = P3.from_f32(torch.randn(N, K) * 0.02, dev)
         C = torch.empty(M, N, device=dev, dtype=torch.float32) if out == "f" else P3.zeros((M, N), dev, True)
         bias = torch.randn(N, device=dev) if use_bias else None
-        gamma = torch.randn(N, device=dev) if use_res else None
-        resid = torch.randn(M, N, device=dev) if use_res else None
+        gamma = torch.randn(N, device=dev) if use_res in (True, "gamma") else None
+        resid = torch.randn(M, N, device=dev) if use_res in (True, "resid", "inplace") else None
+        if use_res == "inplace":
+            resid = C
         for bn, lblk in ((None, 2),):
             try:
                 op = ops.linear(A, W, C, bias=bias, gamma=gamma, resid=resid, act=act, block_n=bn)

@@ -138,6 +138,15 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
         "r"(c4)
         : "memory");
 }
+// same box, added to global memory by the L2 (fp32 tensor maps: IEEE round-to-nearest add per element)
+__device__ __forceinline__ void tma_reduce_add_5d(const CUtensorMap* m, const void* src, int c0, int c1,
+                                                  int c2, int c3, int c4) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

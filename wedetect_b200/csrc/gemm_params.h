@@ -40,6 +40,9 @@ struct GemmParams {
     void* out;
     long long out_ps, sc0, sc1, sc2, scg;
     int cols_valid;
+    // fp32 warp stores of an in-place residual with alpha == 1 (C aliases resid): the TMA store adds the staged tile to memory
+    // (cp.reduce.async.bulk.tensor .add, one rounding per element like the fused add), no residual loads in the epilogue
+    int red_store;
 };
 
 struct GemmOp : CompiledOp {

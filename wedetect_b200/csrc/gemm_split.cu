@@ -347,12 +347,23 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                 const uint64_t alpha2 = splat2(p.alpha * osc);   // acc already carries the output's plane scale
                 if (p.resid_dtype == 2) {
                     const float* rp = reinterpret_cast<const float*>(p.resid) + pix * p.ld_res + nb;
+                    if (nb + WCOLS <= p.N && (p.ld_res & 7) == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 31) == 0) {
+                        // whole 32-byte sectors per lane: one request per sector instead of two (rows are 128 bytes apart per lane)
 #pragma unroll
-                    for (int j = 0; j < WCOLS; j += 4) {
-                        if (nb + j < p.N) {
-                            const float4 x = *reinterpret_cast<const float4*>(rp + j);
-                            acc2[j / 2] = fma2(alpha2, pk2(x.x, x.y), acc2[j / 2]);
-                            acc2[j / 2 + 1] = fma2(alpha2, pk2(x.z, x.w), acc2[j / 2 + 1]);
+                        for (int j = 0; j < WCOLS; j += 8) {
+                            uint64_t x[4];
+                            asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(x[0]), "=l"(x[1]), "=l"(x[2]), "=l"(x[3]) : "l"(rp + j));
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc2[j / 2 + q] = fma2(alpha2, x[q], acc2[j / 2 + q]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < WCOLS; j += 4) {
+                            if (nb + j < p.N) {
+                                const float4 x = *reinterpret_cast<const float4*>(rp + j);
+                                acc2[j / 2] = fma2(alpha2, pk2(x.x, x.y), acc2[j / 2]);
+                                acc2[j / 2 + 1] = fma2(alpha2, pk2(x.z, x.w), acc2[j / 2 + 1]);
+                            }
                         }
                     }
                 } else if (p.resid_dtype == 1) {
@@ -398,7 +409,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_5d(&p.tmCw[0], wbuf, c0, o0 + q0, o1 + q1, o2 + q2, g);
+                            if (p.red_store) tma_reduce_add_5d(&p.tmCw[0], wbuf, c0, o0 + q0, o1 + q1, o2 + q2, g);
+                            else tma_store_5d(&p.tmCw[0], wbuf, c0, o0 + q0, o1 + q1, o2 + q2, g);
                             tma_store_commit();
                             if (!odd) tma_store_wait_read<0>();
                         }

@@ -624,6 +624,15 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
             WD_REQUIRE(c_ps > 0, "gemm: split mode with a 16-bit output needs a C plane stride");
             if (encode_tmap(&P.tmC[1], (__nv_bfloat16*)op.p[2] + c_ps, eb, 5, dims, str, box, true)) return -1;
         }
+        // In-place fp32 residual with alpha == 1 (the ConvNeXt block's x += gamma * pw2(...), mm_backbone.py:122-124): the per-lane
+        // residual rows are 32 uncoalesced 128-byte requests per load instruction and cost 12-19 % of the launch; the TMA store
+        // adds the tile in the L2 instead.  I[42] = 1 keeps the loads (A/B measurements).
+        P.red_store = 0;
+        if (g->split && g->out_f32 && P.warp_store && P.resid_dtype == 2 && P.resid == op.p[2] && P.alpha == 1.f && n_groups == 1 && I[42] == 0 &&
+            P.ld_res == sc0 && (P.D1 == 1 || sc1 == (long long)P.D0 * sc0) && (P.D2 == 1 || sc2 == (long long)P.D1 * P.D0 * sc0)) {
+            P.red_store = 1;
+            P.resid_dtype = 0;
+        }
         // direct-store fallback of the split kernel
         P.out = op.p[2];
         P.out_ps = c_ps;

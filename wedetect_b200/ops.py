@@ -130,6 +130,7 @@ SPLIT_LBLK = int(_os.environ.get("WD_SPLIT_LBLK", "2"))
 
 # activations for which the fast path must use the exact formula (debug / accuracy studies): subset of {ACT_SILU, ACT_GELU}
 NO_WARP_STORE = 1 if _os.environ.get("WD_NO_WARP_STORE") == "1" else 0   # A/B switch: warpgroup-wide epilogue stores
+NO_RED_STORE = 1 if _os.environ.get("WD_NO_RED_STORE") == "1" else 0     # A/B switch: in-place fp32 residual through loads instead of the TMA add
 EXACT_ACT = {dict(silu=L.ACT_SILU, gelu=L.ACT_GELU)[a] for a in _os.environ.get("WD_EXACT_ACT", "").split(",") if a in ("silu", "gelu")}
 
 
@@ -162,6 +163,7 @@ def gemm_raw(*, A, W, C, dims, tile, Kc, N, a_strides, ldb, c_strides, ntaps=1, 
     I[27], I[28], I[29] = group_valid, k_valid, bk_valid
     I[35] = 1 if act in EXACT_ACT else 0
     I[37] = NO_WARP_STORE
+    I[42] = NO_RED_STORE
     if in_wh is not None:
         I[38], I[39] = in_wh
     I[30] = 2 if split else 1
