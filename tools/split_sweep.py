@@ -42,7 +42,12 @@ def main():
         ("s2 pw2 resid-only f32", 51200, 2048, 512, "f", L.ACT_NONE, "resid", True),
         ("s2 pw2 resid-inplace f32", 51200, 2048, 512, "f", L.ACT_NONE, "inplace", True),
         ("s0 pw1 gelu f16x2", 819200, 128, 512, "h", L.ACT_GELU, False, True),
+        ("s0 pw1 none f16x2", 819200, 128, 512, "h", L.ACT_NONE, False, True),
+        ("s0 pw1 gelu f32", 819200, 128, 512, "f", L.ACT_GELU, False, True),
+        ("s0 pw1 none f32", 819200, 128, 512, "f", L.ACT_NONE, False, True),
         ("s0 pw2 res f32", 819200, 512, 128, "f", L.ACT_NONE, True, True),
+        ("s0 pw2 inplace f32", 819200, 512, 128, "f", L.ACT_NONE, "inplace", True),
+        ("s0 pw2 none f32", 819200, 512, 128, "f", L.ACT_NONE, False, True),
         ("s1 pw1 gelu f16x2", 204800, 256, 1024, "h", L.ACT_GELU, False, True),
         ("neck silu f16x2 N128", 51200, 1152, 128, "h", L.ACT_SILU, False, True),
         ("neck silu f16x2 N64", 204800, 576, 64, "h", L.ACT_SILU, False, True),
@@ -55,7 +60,7 @@ def main():
         W = P3.from_f32(torch.randn(N, K) * 0.02, dev)
         C = torch.empty(M, N, device=dev, dtype=torch.float32) if out == "f" else P3.zeros((M, N), dev, True)
         bias = torch.randn(N, device=dev) if use_bias else None
-        gamma = torch.randn(N, device=dev) if use_res in (True, "gamma") else None
+        gamma = torch.randn(N, device=dev) if use_res in (True, "gamma", "inplace") else None
         resid = torch.randn(M, N, device=dev) if use_res in (True, "resid", "inplace") else None
         if use_res == "inplace":
             resid = C

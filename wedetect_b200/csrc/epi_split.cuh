@@ -28,19 +28,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-// erf(x / sqrt 2) on a pair.  N. Juffa's two-interval erff (max error < 1 ulp on each interval) with the 1 / sqrt 2 of the
-// GELU argument and, on the large interval, the log2(e) of its exponential folded into the coefficients; both intervals are
-// evaluated with packed FMAs and selected per element.
+// erf(|x| / sqrt 2) on a pair, and |x| in `t`.  N. Juffa's two-interval erff (max error < 1 ulp on each interval) with the
+// 1 / sqrt 2 of the GELU argument and, on the large interval, the log2(e) of its exponential folded into the coefficients; both
+// intervals are evaluated with packed FMAs and selected per element.  Working on |x| keeps the sign out of it: the caller's
+// 0.5 x (1 + erf(x / sqrt 2)) = h + |h| erf(|x| / sqrt 2) with h = 0.5 x, the same bits as the signed form.
 //   |x| >  1.3120145 (|z| > 0.927734375): erf = 1 - 2^(T P(T)), T = |x|   (one MUFU.EX2; 2^(.) <= 0.19 there, so its 2^-22
 //                                          relative error stays below half an ulp of the result)
-//   |x| <= 1.3120145:                      erf = x Q(x^2)
+//   |x| <= 1.3120145:                      erf = |x| Q(x^2)
 // Checked against a float64 erf over [-6, 6] (1.2 M points): GELU error <= 1.3e-7 absolute below |x| = 2 and <= 0.6 ulp
 // beyond, at or below the error of torch's own fp32 GELU on the same points.
-__device__ __forceinline__ uint64_t erf_gelu_arg2(uint64_t x) {
+__device__ __forceinline__ uint64_t erf_gelu_abs2(uint64_t x, uint64_t& t) {
     float x0, x1;
     upk2(x, x0, x1);
     const float t0 = fabsf(x0), t1 = fabsf(x1);
-    const uint64_t t = pk2(t0, t1), s = mul2(x, x);
+    t = pk2(t0, t1);
+    const uint64_t s = mul2(x, x);
     uint64_t r = fma2(splat2(-2.204183147114236e-06f), t, splat2(6.910457159392536e-05f));
     const uint64_t u = fma2(splat2(-0.0009905463084578514f), t, splat2(0.008748006075620651f));
     r = fma2(r, s, u);
@@ -56,11 +58,11 @@ __device__ __forceinline__ uint64_t erf_gelu_arg2(uint64_t x) {
     q = fma2(q, s, splat2(0.019943933933973312f));
     q = fma2(q, s, splat2(-0.13298039138317108f));
     q = fma2(q, s, splat2(0.7978845834732056f));
-    q = mul2(q, x);
+    q = mul2(q, t);
     float b0, b1, q0, q1;
     upk2(big, b0, b1);
     upk2(q, q0, q1);
-    return pk2(t0 > 1.3120145f ? copysignf(b0, x0) : q0, t1 > 1.3120145f ? copysignf(b1, x1) : q1);
+    return pk2(t0 > 1.3120145f ? b0 : q0, t1 > 1.3120145f ? b1 : q1);
 }
 
 // exact-form activations on a pair, times `osc` (the power-of-two plane scale of a 16-bit output, or 1)
@@ -68,8 +70,10 @@ template <int ACT>
 __device__ __forceinline__ uint64_t act2_exact(uint64_t x, float osc) {
     if constexpr (ACT == WD_ACT_GELU) {
         // 0.5 x (1 + erf(x / sqrt 2))
-        const uint64_t h = mul2(x, splat2(0.5f * osc));
-        return fma2(h, erf_gelu_arg2(x), h);
+        const uint64_t hs = splat2(0.5f * osc);
+        uint64_t t;
+        const uint64_t e = erf_gelu_abs2(x, t);
+        return fma2(mul2(t, hs), e, mul2(x, hs));
     } else if constexpr (ACT == WD_ACT_SILU) {
         // x / (1 + exp(-x)): MUFU.EX2, MUFU.RCP and one Newton step on the reciprocal
         float m0, m1;
@@ -92,19 +96,20 @@ __device__ __forceinline__ uint64_t act2_exact(uint64_t x, float osc) {
 // a2[j] <- osc * gamma[n] * act(a2[j] * (1 + comp) * s + bias[n]) over NC columns starting at n_base (two columns per element of a2).
 // comp undoes the tensor pipe's truncating accumulation (a measured, data-independent shrink of each TMEM block sum); columns
 // at or beyond N get no bias / gamma (they are never stored).
-template <int NC, int ACT>
-__device__ __forceinline__ void split_epi_math(uint64_t* a2, float comp, float s, float osc, const float* __restrict__ bias, const float* __restrict__ gamma,
-                                               int n_base, int N) {
+template <int NC, int ACT, bool kFull>
+__device__ __forceinline__ void split_epi_math_cols(uint64_t* a2, float comp, float s, float osc, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                    int n_base, int N) {
     const uint64_t comp2 = splat2(comp), s2 = splat2(s);
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
         const int n = n_base + j;
+        const bool in = kFull || n < N;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && n < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        if (bias && in) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
         uint64_t x0 = fma2(a2[j / 2], comp2, a2[j / 2]), x1 = fma2(a2[j / 2 + 1], comp2, a2[j / 2 + 1]);
         x0 = act2_exact<ACT>(fma2(x0, s2, pk2(b4.x, b4.y)), osc);
         x1 = act2_exact<ACT>(fma2(x1, s2, pk2(b4.z, b4.w)), osc);
-        if (gamma && n < N) {
+        if (gamma && in) {
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n));
             x0 = mul2(x0, pk2(g4.x, g4.y));
             x1 = mul2(x1, pk2(g4.z, g4.w));
@@ -112,6 +117,12 @@ __device__ __forceinline__ void split_epi_math(uint64_t* a2, float comp, float s
         a2[j / 2] = x0;
         a2[j / 2 + 1] = x1;
     }
+}
+template <int NC, int ACT>
+__device__ __forceinline__ void split_epi_math(uint64_t* a2, float comp, float s, float osc, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                               int n_base, int N) {
+    if (n_base + NC <= N) split_epi_math_cols<NC, ACT, true>(a2, comp, s, osc, bias, gamma, n_base, N);   // (warp-uniform)
+    else split_epi_math_cols<NC, ACT, false>(a2, comp, s, osc, bias, gamma, n_base, N);
 }
 
 // fp16 hi / lo planes of a pair (already multiplied by the plane scale): hi saturates at +-65504, lo = fp16(v - hi)

@@ -259,11 +259,42 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
             if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[a]), 0));
             else mbar_arrive(&bar_tempty[a]);
         };
+        // Everything a division would give is computed once: the thread's row inside the tile brick, the quarter's sub-brick, and
+        // the tile coordinates, which then advance by the decomposed grid step (a runtime integer division is ~20 instructions;
+        // ten of them per tile were a fifth of this loop's issue slots on the short-K layers).
+        const int i0 = r % p.E0, i1 = (r / p.E0) % p.E1, i2 = r / (p.E0 * p.E1);
+        const int qr = quarter * 32;
+        const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
+        const int step_n = t_step % p.num_n_tiles, step_m = (t_step / p.num_n_tiles) * kClu;
+        const int a0 = step_m % p.nt0, a1 = (step_m / p.nt0) % p.nt1, a2 = step_m / (p.nt0 * p.nt1);
+        int n_blk = t_first % p.num_n_tiles;
+        int t0, t1, t2;
+        {
+            const int m_blk = (t_first / p.num_n_tiles) * kClu + crank;
+            t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
+        }
         for (int tile = t_first; tile < t_total; tile += t_step) {
-            const int m_blk = (tile / p.num_n_tiles) * kClu + crank, n_blk = tile % p.num_n_tiles;
-            const int t0 = m_blk % p.nt0, t1 = (m_blk / p.nt0) % p.nt1, t2 = m_blk / (p.nt0 * p.nt1);
             const int o0 = t0 * p.E0, o1 = t1 * p.E1, o2 = t2 * p.E2;
             const int nb = n_blk * BN + cg * WCOLS;     // first output column of this warp
+            const int n_blk_cur = n_blk;
+            {   // coordinates of the next tile of this CTA
+                n_blk += step_n;
+                t0 += a0;
+                if (n_blk >= p.num_n_tiles) {
+                    n_blk -= p.num_n_tiles;
+                    t0 += kClu;
+                }
+                while (t0 >= p.nt0) {
+                    t0 -= p.nt0;
+                    ++t1;
+                }
+                t1 += a1;
+                while (t1 >= p.nt1) {
+                    t1 -= p.nt1;
+                    ++t2;
+                }
+                t2 += a2;
+            }
             // pull this warp's bias / LayerScale line into L1 behind the tile's UMMAs (the epilogue's loads then hit)
             if (lane == 0) {
                 if (p.bias && nb < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + nb));
@@ -272,8 +303,6 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
 
             // ---- sum the block accumulators in fp32 registers (packed round-to-nearest adds) ----
             uint64_t acc2[WCOLS / 2];
-#pragma unroll
-            for (int j = 0; j < WCOLS / 2; ++j) acc2[j] = 0ull;
             for (int b = 0; b < nblk; ++b) {
                 mbar_wait(&bar_tfull[as], aphase);
                 tc_fence_after();
@@ -288,7 +317,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                 for (int j = 0; j < 16; ++j) {
                     uint64_t tv;
                     asm("mov.b64 %0, {%1, %2};" : "=l"(tv) : "r"(t[2 * j]), "r"(t[2 * j + 1]));
-                    acc2[j] = add2(acc2[j], tv);
+                    acc2[j] = b == 0 ? tv : add2(acc2[j], tv);
                 }
                 if (++as == C::NBUF) {
                     as = 0;
@@ -296,7 +325,6 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                 }
             }
             // ---- this thread's output row ----
-            const int i0 = r % p.E0, i1 = (r / p.E0) % p.E1, i2 = r / (p.E0 * p.E1);
             const int d0 = o0 + i0, d1 = o1 + i1, d2 = o2 + i2;
             const bool row_ok = (i2 < p.E2) && d0 < p.D0 && d1 < p.D1 && d2 < p.D2;
             const long long pix = ((long long)d2 * p.D1 + d1) * p.D0 + d0;
@@ -386,14 +414,12 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                 }
             }
             // ---- output ----
-            const int g = nb / p.group_cols, c0 = nb - g * p.group_cols;     // column inside its output group (concat / deconv layouts)
+            const int g = p.group_cols > nb ? 0 : nb / p.group_cols, c0 = nb - g * p.group_cols;     // column inside its output group (concat / deconv layouts)
             const long long grow = (long long)d0 * p.sc0 + (long long)d1 * p.sc1 + (long long)d2 * p.sc2 + (long long)g * p.scg + c0;
             if constexpr (!kOut16) {
                 // fp32: this warp's 32 columns are one 128-byte chunk.  The two warps of a pair take turns on the pair's staging
                 // buffer (even warp first): the odd warp waits for the even warp's TMA store to have read the buffer.
                 if (p.warp_store) {
-                    const int qr = quarter * 32;
-                    const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
                     const bool odd = (cg & 1) != 0;
                     if (odd && lane == 0) tma_store_wait_read<0>();      // my store of the previous tile has released the buffer
                     named_bar_sync(1 + pairbuf, 64);
@@ -432,11 +458,9 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                 }
             } else {
                 // fp16 hi / lo planes of acc * kPlaneScale (one pass per plane)
-                const int chunk_n = n_blk * BN + (cg & ~1) * WCOLS;      // first column of the 64-column chunk this warp pair writes
+                const int chunk_n = n_blk_cur * BN + (cg & ~1) * WCOLS;      // first column of the 64-column chunk this warp pair writes
                 const bool chunk_ok = chunk_n < p.N;                        // uniform over the pair
-                const int gc = chunk_n / p.group_cols, cc0 = chunk_n - gc * p.group_cols;
-                const int qr = quarter * 32;
-                const int q0 = qr % p.E0, q1 = (qr / p.E0) % p.E1, q2 = qr / (p.E0 * p.E1);
+                const int gc = p.group_cols > chunk_n ? 0 : chunk_n / p.group_cols, cc0 = chunk_n - gc * p.group_cols;
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl) {
                     uint4 w[4];
