@@ -168,6 +168,22 @@ enum wd_op_kind {
      * i: 0 M 1 C 2 H 3 ld of t (0 = C)
      * p: 0 t bf16 [M, C]  1 W1 bf16 [H, C]  2 W2 bf16 [C, H]  3 b1 f32[H]  4 b2 f32[C]  5 gamma f32[C]  6 x f32 [M, C] (in place) */
     WD_OP_MLP_FUSED = 17,
+    /* The mmcv test pipeline of infer_wedetect.py / test.py on the device: cv2.resize (OpenCV 4.x arithmetic, bit-exact) of a batch
+     * of decoded uint8 BGR images + paste at (left, top) on a `pad`-grey canvas, into the detector's planar uint8 input.
+     * WeDetectKeepRatioResize (transforms.py:94-123: INTER_AREA when the ratio is < 1, else INTER_LINEAR) followed by
+     * WeDetectLetterResize (transforms.py:180-272: pad 114, top/left = round(pad // 2 - 0.1)); mmcv.imresize / impad = cv2.resize /
+     * cv2.copyMakeBorder (mmcv 2.1.0, un-vendored).
+     * i: 0 B 1 H 2 W (canvas) 3 pad value
+     * p: 0 src u8: the images back to back, each [h, w, 3] interleaved (channel order is passed through)
+     *    1 desc i32 [B, 16] per image: 0,1 byte offset in src (lo, hi)  2 src_w  3 src_h  4 new_w  5 new_h  6 left  7 top
+     *      8 mode (0 copy, 1 INTER_AREA with tables, 2 INTER_AREA integer boxes, 3 INTER_LINEAR)  9 offset (int32 words) of the image's
+     *      tables in coef  10 kx 11 ky 12 bits of the float 1.f / (kx ky) (mode 2)  13 xmax (mode 3: first column that replicates the
+     *      last source column).  new_w == 0: the whole canvas is padding
+     *    2 coef i32: mode 1: xidx [new_w + 1], yidx [new_h + 1] (entry ranges), x entries si [nx], alpha f32 [nx], y entries si [ny],
+     *      beta f32 [ny] (OpenCV's computeResizeAreaTab);  mode 3: xofs [new_w], (alpha0 | alpha1 << 16) [new_w], yofs [new_h],
+     *      (beta0 | beta1 << 16) [new_h] (11-bit fixed point, OpenCV's resizeGeneric_ tables)
+     *    3 unused (nullable)  4 out u8 [B, 3, H, W] */
+    WD_OP_CV_RESIZE_PAD = 18,
 };
 
 enum wd_act { WD_ACT_NONE = 0, WD_ACT_RELU = 1, WD_ACT_SILU = 2, WD_ACT_GELU = 3 };

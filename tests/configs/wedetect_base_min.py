@@ -18,3 +18,12 @@ model = dict(
                    prior_generator=dict(type='MlvlPointGenerator', offset=0.5, strides=[8, 16, 32]),
                    bbox_coder=dict(type='WeDetectDistancePointBBoxCoder')),
     test_cfg=dict(multi_label=True, nms_pre=30000, score_thr=0.001, nms=dict(type='nms', iou_threshold=0.7), max_per_img=300))
+img_scale = (640, 640)
+test_pipeline = [
+    dict(type='LoadImageFromFile', backend_args=None),
+    dict(type='WeDetectKeepRatioResize', scale=img_scale),
+    dict(type='WeDetectLetterResize', scale=img_scale, allow_scale_up=False, pad_val=dict(img=114)),
+    dict(type='LoadAnnotations', with_bbox=True, _scope_='mmdet'),
+    dict(type='LoadText'),
+    dict(type='PackDetInputs', meta_keys=('img_id', 'img_path', 'ori_shape', 'img_shape', 'scale_factor', 'pad_param', 'texts')),
+]

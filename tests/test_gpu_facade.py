@@ -41,7 +41,9 @@ def _assert_same_detections(bx, sc, lb, rbx, rsc, rlb, what, cut=False):
     assert n == m or cut, f"{what}: {n} detections, reference {m}"
     assert n > 0 and m > 0, f"{what}: empty"
     cost = (bx[:, None, :] - rbx[None, :, :]).abs().amax(-1) + 1e3 * (lb[:, None] != rlb[None, :]).float()
-    j = cost.argmin(1)
+    # several reference detections can share a box and a label (see below): among the candidates within 0.1 px take the closest score
+    near = torch.where(cost <= 0.1, (sc[:, None] - rsc[None, :]).abs(), torch.full_like(cost, float("inf")))
+    j = near.argmin(1)
     ok = cost[torch.arange(n), j] <= 0.1
     if cut:      # unmatched entries must sit at the cut: their score is within 1e-3 of the lowest kept reference score
         assert bool((ok | ((sc - rsc.min()).abs() <= 1e-3)).all()), f"{what}: detections without a reference counterpart"

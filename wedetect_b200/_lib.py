@@ -15,7 +15,7 @@ ACT_PLANE_SCALE = 4.0    # WD_ACT_PLANE_SCALE of include/wedetect_b200.h
 # enum wd_op_kind
 OP_GEMM, OP_LN_ROWS, OP_DWCONV_LN, OP_STEM_PATCH, OP_IM2COL_S2, OP_CAST_BF16 = 1, 2, 3, 4, 5, 6
 OP_TEXT_EMBED, OP_ATTN_SMALL, OP_L2NORM_ROWS, OP_GATHER_ROWS, OP_FOLD_TEXT, OP_POSTPROCESS, OP_GATHER_EMBED = 7, 8, 9, 10, 11, 12, 13
-OP_SCALE_ROWS, OP_RETR_REDUCE, OP_LETTERBOX, OP_MLP_FUSED = 14, 15, 16, 17
+OP_SCALE_ROWS, OP_RETR_REDUCE, OP_LETTERBOX, OP_MLP_FUSED, OP_CV_RESIZE_PAD = 14, 15, 16, 17, 18
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
 
 EXPORTS = [

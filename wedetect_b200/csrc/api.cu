@@ -114,7 +114,8 @@ static int compile_op(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     switch (op.kind) {
         case WD_OP_GEMM: return compile_gemm(op, out);
         case WD_OP_POSTPROCESS: return compile_postprocess(op, out);
-        case WD_OP_LETTERBOX: return compile_preprocess(op, out);
+        case WD_OP_LETTERBOX:
+        case WD_OP_CV_RESIZE_PAD: return compile_preprocess(op, out);
         case WD_OP_MLP_FUSED: return compile_mlp_fused(op, out);
         case WD_OP_LN_ROWS:
         case WD_OP_DWCONV_LN:

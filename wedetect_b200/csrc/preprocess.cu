@@ -116,27 +116,145 @@ __global__ void __launch_bounds__(256) lb_pass2_paste_kernel(const uint8_t* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// mmcv / cv2 test pipeline (WeDetectKeepRatioResize + WeDetectLetterResize, transforms.py:94-123,180-272): cv2.resize of a
+// decoded uint8 BGR image (INTER_AREA when shrinking, INTER_LINEAR when growing) pasted at (left, top) on a grey canvas.
+// Bit-exact with OpenCV 4.x (modules/imgproc/src/resize.cpp); the host builds the tables exactly as OpenCV does
+// (wedetect_b200/preprocess.py), this kernel does the per-pixel arithmetic in OpenCV's operation order:
+//   mode 1  INTER_AREA, fractional scale (ResizeArea_<uchar, float>): per source row a float sum of S * alpha over the x-table
+//           entries in order (separate multiply and add, no FMA), rows combined as beta * rowsum, first row assigns;
+//           saturate_cast<uchar> = round-half-even + clamp.
+//   mode 2  INTER_AREA, integer scale (ResizeAreaFast_): integer box sum; 2x2 boxes (sum + 2) >> 2, else round(sum * (1.f / area)).
+//   mode 3  INTER_LINEAR (8u): 11-bit fixed-point horizontal taps (int), vertical ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2
+//           on rows clipped to the image; columns >= xmax replicate the last source column.
+//   mode 0  no resize (copy).
+// One thread per canvas pixel, three channels; output planes are written fully coalesced.
+__device__ __forceinline__ uint8_t cv_sat8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+__global__ void __launch_bounds__(256) cv_resize_pad_kernel(const uint8_t* __restrict__ src, const int* __restrict__ desc, const int* __restrict__ coef,
+                                                            uint8_t* __restrict__ out, int H, int W, int pad) {
+    const int b = blockIdx.y;
+    const int* d = desc + b * kLbDesc;
+    const long long src_off = lb_off64(d, 0);
+    const int sw = d[2], sh = d[3], nw = d[4], nh = d[5], left = d[6], top = d[7], mode = d[8];
+    const int* tab = coef + d[9];
+    const uint8_t* sb = src + src_off;
+    const long long rs = (long long)sw * 3;
+    const long long plane = (long long)H * W;
+    uint8_t* ob = out + (long long)b * 3 * plane;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < plane; t += (long long)gridDim.x * blockDim.x) {
+        const int Y = (int)(t / W), X = (int)(t - (long long)Y * W);
+        const int dy = Y - top, dx = X - left;
+        uint8_t v[3] = {(uint8_t)pad, (uint8_t)pad, (uint8_t)pad};
+        if (dy >= 0 && dy < nh && dx >= 0 && dx < nw) {
+            if (mode == 0) {
+                const uint8_t* q = sb + dy * rs + (long long)dx * 3;
+                v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+            } else if (mode == 1) {
+                const int* xidx = tab;
+                const int* yidx = tab + nw + 1;
+                const int nx = xidx[nw], ny = yidx[nh];
+                const int* xs = yidx + nh + 1;
+                const float* xa = reinterpret_cast<const float*>(xs + nx);
+                const int* ys = xs + 2 * nx;
+                const float* yb = reinterpret_cast<const float*>(ys + ny);
+                const int k0 = xidx[dx], k1 = xidx[dx + 1];
+                float sum[3] = {0.f, 0.f, 0.f};
+                for (int j = yidx[dy]; j < yidx[dy + 1]; ++j) {
+                    const uint8_t* row = sb + ys[j] * rs;
+                    const float beta = yb[j];
+                    float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+                    for (int k = k0; k < k1; ++k) {
+                        const uint8_t* q = row + (long long)xs[k] * 3;
+                        const float a = xa[k];
+                        h0 = __fadd_rn(h0, __fmul_rn((float)q[0], a));
+                        h1 = __fadd_rn(h1, __fmul_rn((float)q[1], a));
+                        h2 = __fadd_rn(h2, __fmul_rn((float)q[2], a));
+                    }
+                    if (j == yidx[dy]) {
+                        sum[0] = __fmul_rn(beta, h0); sum[1] = __fmul_rn(beta, h1); sum[2] = __fmul_rn(beta, h2);
+                    } else {
+                        sum[0] = __fadd_rn(sum[0], __fmul_rn(beta, h0));
+                        sum[1] = __fadd_rn(sum[1], __fmul_rn(beta, h1));
+                        sum[2] = __fadd_rn(sum[2], __fmul_rn(beta, h2));
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = cv_sat8(__float2int_rn(sum[c]));
+            } else if (mode == 2) {
+                const int kx = d[10], ky = d[11];
+                const float scale = __int_as_float(d[12]);
+                int s0 = 0, s1 = 0, s2 = 0;
+                for (int yy = 0; yy < ky; ++yy) {
+                    const uint8_t* q = sb + (long long)(dy * ky + yy) * rs + (long long)dx * kx * 3;
+                    for (int xx = 0; xx < kx; ++xx, q += 3) {
+                        s0 += q[0]; s1 += q[1]; s2 += q[2];
+                    }
+                }
+                if (kx == 2 && ky == 2) {
+                    v[0] = (uint8_t)((s0 + 2) >> 2); v[1] = (uint8_t)((s1 + 2) >> 2); v[2] = (uint8_t)((s2 + 2) >> 2);
+                } else {
+                    v[0] = cv_sat8(__float2int_rn(__fmul_rn((float)s0, scale)));
+                    v[1] = cv_sat8(__float2int_rn(__fmul_rn((float)s1, scale)));
+                    v[2] = cv_sat8(__float2int_rn(__fmul_rn((float)s2, scale)));
+                }
+            } else {
+                const int* xofs = tab;
+                const int* xab = tab + nw;
+                const int* yofs = xab + nw;
+                const int* yab = yofs + nh;
+                const int xmax = d[13];
+                const int sx = xofs[dx], a0 = (int)(short)(xab[dx] & 0xffff), a1 = xab[dx] >> 16;
+                const int sy = yofs[dy], b0 = (int)(short)(yab[dy] & 0xffff), b1 = yab[dy] >> 16;
+                const int r0 = min(max(sy, 0), sh - 1), r1 = min(max(sy + 1, 0), sh - 1);
+                const uint8_t* q0 = sb + r0 * rs + (long long)sx * 3;
+                const uint8_t* q1 = sb + r1 * rs + (long long)sx * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    int h0, h1;
+                    if (dx < xmax) {
+                        h0 = (int)q0[c] * a0 + (int)q0[c + 3] * a1;
+                        h1 = (int)q1[c] * a0 + (int)q1[c + 3] * a1;
+                    } else {
+                        h0 = (int)q0[c] * 2048;
+                        h1 = (int)q1[c] * 2048;
+                    }
+                    v[c] = cv_sat8((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+                }
+            }
+        }
+        ob[t] = v[0];
+        ob[plane + t] = v[1];
+        ob[2 * plane + t] = v[2];
+    }
+}
+
 int compile_preprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     const int32_t* I = op.i;
     void* const* P = op.p;
     if (device_sm_count() <= 0) return -2;
-    WD_REQUIRE(op.kind == WD_OP_LETTERBOX, "preprocess: unknown kind %d", op.kind);
+    WD_REQUIRE(op.kind == WD_OP_LETTERBOX || op.kind == WD_OP_CV_RESIZE_PAD, "preprocess: unknown kind %d", op.kind);
     const int B = I[0], H = I[1], W = I[2], pad = I[3];
     WD_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && pad >= 0 && pad <= 255, "letterbox: bad shape B=%d H=%d W=%d pad=%d", B, H, W, pad);
-    for (int k = 0; k <= 4; ++k) WD_REQUIRE(P[k], "letterbox: null pointer %d", k);
+    const bool cv = op.kind == WD_OP_CV_RESIZE_PAD;
+    for (int k = 0; k <= 4; ++k) WD_REQUIRE(P[k] || (cv && k == 3), "letterbox: null pointer %d", k);
     struct LbOp : CompiledOp {
         const uint8_t* src;
         const int *desc, *coef;
         uint8_t *tmp, *o;
-        int B, H, W, pad, gx;
+        int B, H, W, pad, gx, cv;
         int launch(cudaStream_t s) override {
-            lb_pass1_kernel<<<dim3(gx, B), 256, 0, s>>>(src, desc, coef, tmp);
-            lb_pass2_paste_kernel<<<dim3(gx, B), 256, 0, s>>>(tmp, desc, coef, o, H, W, pad);
+            if (cv) {
+                cv_resize_pad_kernel<<<dim3(gx, B), 256, 0, s>>>(src, desc, coef, o, H, W, pad);
+            } else {
+                lb_pass1_kernel<<<dim3(gx, B), 256, 0, s>>>(src, desc, coef, tmp);
+                lb_pass2_paste_kernel<<<dim3(gx, B), 256, 0, s>>>(tmp, desc, coef, o, H, W, pad);
+            }
             WD_CHECK_CUDA(cudaGetLastError());
-            count_launch(2);
+            count_launch(cv ? 1 : 2);
             return 0;
         }
-        int num_kernels() const override { return 2; }
+        int num_kernels() const override { return cv ? 1 : 2; }
     };
     auto d = std::make_unique<LbOp>();
     d->src = (const uint8_t*)P[0];
@@ -144,7 +262,7 @@ int compile_preprocess(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     d->coef = (const int*)P[2];
     d->tmp = (uint8_t*)P[3];
     d->o = (uint8_t*)P[4];
-    d->B = B; d->H = H; d->W = W; d->pad = pad;
+    d->B = B; d->H = H; d->W = W; d->pad = pad; d->cv = cv ? 1 : 0;
     d->gx = std::max(8, (device_sm_count() * 16 + B - 1) / B);   // ~16 resident blocks per SM over the whole batch
     out = std::move(d);
     return 0;

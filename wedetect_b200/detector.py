@@ -19,7 +19,7 @@ import torch
 
 from . import _lib as L
 from . import plan, schema, weights
-from .preprocess import Letterbox, decode_images, letterbox_params  # noqa: F401
+from .preprocess import Letterbox, MMTestPipeline, decode_images, decode_images_bgr, letterbox_params  # noqa: F401
 from .structures import DetDataSample, InstanceData, instances_for  # noqa: F401
 
 _DEF_TEST_CFG = dict(multi_label=True, nms_pre=30000, score_thr=0.001, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300)
@@ -278,7 +278,8 @@ class YOLOWorldDetector:
             p.set_meta(torch.tensor(meta_rows, dtype=torch.float32).to(self.device, non_blocking=True),
                        torch.tensor(clamp_rows, dtype=torch.float32).to(self.device, non_blocking=True))
             p._meta_key = key
-        p.image.copy_(batch_inputs, non_blocking=True)
+        if batch_inputs is not None:          # (predict_images: the device pipeline has already written the plan's input)
+            p.image.copy_(batch_inputs, non_blocking=True)
         _run_plan(p, self.cuda_graph)
         r = p.results() if self.zero_copy else _own(p.results())
         self.last_batch_result = r            # packed device tensors [B,max,...] + counts: bulk readers copy these once
@@ -294,6 +295,53 @@ class YOLOWorldDetector:
 
     def test_step(self, data):
         return self.predict(data["inputs"], data.get("data_samples"), rescale=True)
+
+    def pipeline_cfg(self):
+        """(scale (w, h), allow_scale_up, pad value, ...) of the config's test_pipeline (config/wedetect_base.py:111-118); the
+        shipped values when the detector was built without a config."""
+        out = dict(scale=(640, 640), allow_scale_up=False, pad=114)
+        steps = (getattr(self, "cfg", None) or {}).get("test_pipeline") or []
+        types = [t.get("type") for t in steps]
+        for t in steps:
+            if t.get("type") == "WeDetectLetterResize":
+                pv = t.get("pad_val", dict(img=0))
+                out.update(scale=tuple(t["scale"]), allow_scale_up=bool(t.get("allow_scale_up", True)), pad=int(pv.get("img", 0) if isinstance(pv, dict) else pv),
+                           use_mini_pad=bool(t.get("use_mini_pad", False)), stretch_only=bool(t.get("stretch_only", False)),
+                           half_pad_param=bool(t.get("half_pad_param", False)))
+            elif t.get("type") == "WeDetectKeepRatioResize" and tuple(t["scale"]) != tuple(out["scale"]) and "WeDetectLetterResize" in types:
+                ls = next(tuple(u["scale"]) for u in steps if u.get("type") == "WeDetectLetterResize")
+                if tuple(t["scale"]) != ls:
+                    raise NotImplementedError("WeDetectKeepRatioResize and WeDetectLetterResize with different scales")
+        if steps:
+            out["keep_ratio_first"] = "WeDetectKeepRatioResize" in types
+        return out
+
+    def predict_images(self, images, texts=None, rescale=True):
+        """infer_wedetect.py:102-117 for a batch of images: LoadImageFromFile (host decode; arrays are taken as decoded BGR),
+        WeDetectKeepRatioResize + WeDetectLetterResize on the device (cv2-exact, transforms.py:94-123,180-272) straight into the
+        detector's input, then test_step.  texts: list of prompts (one shared set), or None for the reparameterized features.
+        Returns one DetDataSample per image with the metainfo PackDetInputs would carry."""
+        if self._sd is None:
+            raise RuntimeError("load_state_dict first")
+        arrays = decode_images_bgr(images)
+        pc = self.pipeline_cfg()
+        (W, H), B = pc["scale"], len(arrays)
+        if texts is not None:
+            flat = [t[0] if isinstance(t, (list, tuple)) else t for t in texts]
+            src = self.forward_text([flat])
+        elif self.text_feats is not None:
+            src = self.text_feats
+        else:
+            raise TypeError("texts or reparameterize() first")
+        feats = src.reshape(-1, schema.EMBED_DIM)
+        p = self._plan(B, H, W, feats.shape[0], torch.uint8)
+        with _on(self.device):
+            pipe = getattr(p, "_mm_pipe", None)
+            if pipe is None:
+                pipe = p._mm_pipe = MMTestPipeline(p.image, **pc)
+            metas = pipe.run(arrays)
+            samples = [DetDataSample(dict(m, img_id=i, img_path=(im if isinstance(im, str) else None))) for i, (m, im) in enumerate(zip(metas, images))]
+            return self._predict_on(p, src, feats, None, samples, rescale, B, H, W)
 
     __call__ = test_step
 

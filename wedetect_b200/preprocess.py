@@ -86,6 +86,32 @@ def load_rgb(item):
     return item
 
 
+def load_bgr(item):
+    """One input of the mmdet test pipeline -> uint8 [h, w, 3] BGR: a file name is decoded as LoadImageFromFile does (mmcv.imfrombytes,
+    cv2 backend, flag 'color' = cv2.IMREAD_COLOR: infer_wedetect.py:111, config/wedetect_base.py:112); an array is taken as decoded."""
+    if isinstance(item, (str, bytes)) or hasattr(item, "__fspath__"):
+        try:
+            import cv2
+        except ImportError as e:          # decoding is the one host step left; without cv2 pass decoded arrays
+            raise RuntimeError("decoding image files for the mmdet pipeline needs cv2 (pass decoded uint8 BGR arrays instead)") from e
+        name = os.fsdecode(item)
+        arr = cv2.imread(name, cv2.IMREAD_COLOR)
+        if arr is None:
+            raise FileNotFoundError(name)
+        return arr
+    item = np.asarray(item)
+    if item.dtype != np.uint8 or item.ndim != 3 or item.shape[2] != 3:
+        raise TypeError(f"expected a file name or a uint8 [h, w, 3] BGR array, got {item.dtype} {item.shape}")
+    return item
+
+
+def decode_images_bgr(items):
+    items = list(items)
+    if len(items) <= 1:
+        return [load_bgr(it) for it in items]
+    return list(_pool().map(load_bgr, items))
+
+
 def decode_images(items):
     """Decode a batch on the host thread pool (PIL releases the GIL while decoding): at >1000 images/s per GPU a serial
     decode loop would be the bottleneck of the Uni entry points."""
@@ -146,6 +172,13 @@ def pack_batch(images, H, W, with_src=True):
 
 class Letterbox:
     """Letterboxes up to B decoded RGB images into `out` (uint8 [B, 3, H, W], device) on the current stream."""
+    _KIND = L.OP_LETTERBOX
+
+    def _pack(self, images):
+        return pack_batch(images, self.H, self.W, with_src=False)
+
+    def _result(self, pk):
+        return pk["ratios"], pk["offsets"], pk["shapes"]
 
     def __init__(self, out, pad=114):
         L.load(require_gpu=True)
@@ -161,7 +194,7 @@ class Letterbox:
         self._copied = None
 
     def _ensure(self, name, need, dtype, host=True):
-        if need <= self._cap[name]:
+        if need <= self._cap[name] and name in self._devb:
             return False
         cap = max(need, int(self._cap[name] * 1.5), 1 << 16)
         if host:
@@ -177,14 +210,14 @@ class Letterbox:
             raise ValueError(f"{len(images)} images for a batch of {self.B}")
         if self._copied is not None:
             self._copied.synchronize()           # the previous batch's H2D must have left the pinned buffers
-        pk = pack_batch(images, self.H, self.W, with_src=False)
+        pk = self._pack(images)
         n_src, n_coef = pk["src_bytes"], pk["coef"].size
         grew = self._ensure("src", n_src, torch.uint8)
         grew |= self._ensure("coef", n_coef, torch.int32)
         grew |= self._ensure("tmp", pk["tmp_bytes"], torch.uint8, host=False)
         if grew or self._program is None:
             op = WdOp()
-            op.kind = L.OP_LETTERBOX
+            op.kind = self._KIND
             op.i[0], op.i[1], op.i[2], op.i[3] = self.B, self.H, self.W, self.pad
             for k, t in enumerate((self._devb["src"], self._desc_dev, self._devb["coef"], self._devb["tmp"], self.out)):
                 op.p[k] = t.data_ptr()
@@ -195,7 +228,7 @@ class Letterbox:
         src_np = self._host["src"].numpy()
         # pageable -> pinned: one memcpy per image, spread over a few threads (numpy releases the GIL for the copy)
         list(_pool().map(lambda part: np.copyto(src_np[part[0]: part[0] + part[1].size], part[1]), pk["src_parts"]))
-        self._host["coef"].numpy()[:n_coef] = pk["coef"]
+        self._host["coef"].numpy()[:n_coef] = pk["coef"].view(np.int32)
         self._devb["src"][:n_src].copy_(self._host["src"][:n_src], non_blocking=True)
         self._devb["coef"][:n_coef].copy_(self._host["coef"][:n_coef], non_blocking=True)
         self._desc_dev.copy_(self._desc_host, non_blocking=True)
@@ -203,4 +236,204 @@ class Letterbox:
         self._copied.record()
         self._program.run(torch.cuda.current_stream().cuda_stream)
         self.h2d_bytes = n_src + 4 * n_coef + 4 * self.B * DESC_WORDS
-        return pk["ratios"], pk["offsets"], pk["shapes"]
+        return self._result(pk)
+
+
+# ------------------------------------------------------------------------------------------------
+# The mmcv test pipeline of infer_wedetect.py / test.py (config/wedetect_base.py:111-133) on the device:
+#   WeDetectKeepRatioResize   transforms.py:62-123   ratio = min(long / max(h, w), short / min(h, w)); mmcv.imresize to
+#                             (int(w ratio), int(h ratio)) with 'area' when ratio < 1, else 'bilinear'; scale_factor = new / old
+#   WeDetectLetterResize      transforms.py:180-272, 318-328   ratio (<= 1 unless allow_scale_up), no_pad_shape = round(shape ratio),
+#                             optional second mmcv.imresize ('bilinear'), pad to `scale` with top / left = int(round(pad // 2 - 0.1)),
+#                             scale_factor multiplied with the first transform's, pad_param float32 [top, bottom, left, right]
+# mmcv.imresize(backend='cv2') is cv2.resize and mmcv.impad is cv2.copyMakeBorder (mmcv 2.1.0, un-vendored): the pixel
+# arithmetic below is OpenCV 4.x's (modules/imgproc/src/resize.cpp), executed by WD_OP_CV_RESIZE_PAD.  Host work per image is
+# the geometry and OpenCV's coefficient tables (double precision, same operation order, cached per (source, target) size).
+# ------------------------------------------------------------------------------------------------
+_DBL_EPS = 2.220446049250313e-16
+CV_COPY, CV_AREA, CV_AREA_INT, CV_LINEAR = 0, 1, 2, 3
+
+
+def keep_ratio_resize_geometry(h, w, scale):
+    """WeDetectKeepRatioResize._resize_img (transforms.py:62-123) without pixels: ((new_h, new_w), interpolation or None,
+    scale_factor (w, h))."""
+    if isinstance(scale, (int, float)):
+        if scale <= 0:
+            raise ValueError(f"Invalid scale {scale}, must be positive.")
+        ratio = scale
+    else:
+        ratio = min(max(scale) / max(h, w), min(scale) / min(h, w))
+    nh, nw, interp = h, w, None
+    if ratio != 1:
+        nw, nh = int(w * ratio), int(h * ratio)
+        interp = "area" if ratio < 1 else "bilinear"
+    return (nh, nw), interp, (nw / w, nh / h)
+
+
+def letter_resize_geometry(h, w, scale_hw, allow_scale_up=True, use_mini_pad=False, stretch_only=False, half_pad_param=False):
+    """WeDetectLetterResize._resize_img (transforms.py:180-272) without pixels: ((no_pad_h, no_pad_w), resize needed,
+    scale_factor (w, h), (top, bottom, left, right), pad_param float32[4])."""
+    ratio = min(scale_hw[0] / h, scale_hw[1] / w)
+    if not allow_scale_up:
+        ratio = min(ratio, 1.0)
+    no_pad = (int(round(h * ratio)), int(round(w * ratio)))
+    padding_h, padding_w = scale_hw[0] - no_pad[0], scale_hw[1] - no_pad[1]
+    if use_mini_pad:
+        padding_w, padding_h = int(np.mod(padding_w, 32)), int(np.mod(padding_h, 32))
+    elif stretch_only:
+        padding_h, padding_w = 0.0, 0.0
+        no_pad = (scale_hw[0], scale_hw[1])
+    top, left = int(round(padding_h // 2 - 0.1)), int(round(padding_w // 2 - 0.1))
+    pads = (top, padding_h - top, left, padding_w - left)
+    if half_pad_param:
+        pad_param = np.array([padding_h / 2, padding_h / 2, padding_w / 2, padding_w / 2], dtype=np.float32)
+    else:
+        pad_param = np.array(pads, dtype=np.float32)
+    return no_pad, (h, w) != no_pad, (no_pad[1] / w, no_pad[0] / h), pads, pad_param
+
+
+def _cv_scale(ssize, dsize):
+    return 1.0 / (dsize / ssize)          # cv::resize: inv_scale = (double)dsize / ssize; scale = 1. / inv_scale
+
+
+@functools.lru_cache(maxsize=512)
+def cv_area_table(ssize, dsize):
+    """OpenCV computeResizeAreaTab for one axis (cn = 1): (idx int32 [dsize + 1], si int32 [n], alpha float32 [n]); the entries of
+    output d are idx[d] .. idx[d + 1] - 1, in OpenCV's order."""
+    scale = _cv_scale(ssize, dsize)
+    d = np.arange(dsize, dtype=np.float64)
+    f1 = d * scale
+    f2 = f1 + scale
+    cell = np.minimum(scale, ssize - f1)
+    s1 = np.ceil(f1).astype(np.int64)
+    s2 = np.minimum(np.floor(f2).astype(np.int64), ssize - 1)
+    s1 = np.minimum(s1, s2)
+    hl = (s1 - f1) > 1e-3
+    nm = s2 - s1
+    hr = (f2 - s2) > 1e-3
+    cnt = hl.astype(np.int64) + nm + hr.astype(np.int64)
+    idx = np.concatenate([[0], np.cumsum(cnt)])
+    n = int(idx[-1])
+    si = np.empty(n, dtype=np.int64)
+    al = np.empty(n, dtype=np.float32)
+    pl = idx[:-1][hl]
+    si[pl] = s1[hl] - 1
+    al[pl] = ((s1 - f1) / cell).astype(np.float32)[hl]
+    rep = np.repeat(np.arange(dsize), nm)
+    within = np.arange(int(nm.sum())) - np.repeat(np.cumsum(nm) - nm, nm)
+    pm = idx[:-1][rep] + hl[rep] + within
+    si[pm] = s1[rep] + within
+    al[pm] = (1.0 / cell).astype(np.float32)[rep]
+    pr = idx[1:][hr] - 1
+    si[pr] = s2[hr]
+    al[pr] = (np.minimum(np.minimum(f2 - s2, 1.0), cell) / cell).astype(np.float32)[hr]
+    return idx.astype(np.int32), si.astype(np.int32), al
+
+
+@functools.lru_cache(maxsize=512)
+def cv_linear_table(ssize, dsize, clamp):
+    """OpenCV's INTER_LINEAR tables for one axis of an 8-bit image (resize.cpp, cv::resize -> resizeGeneric_): (ofs int32 [dsize],
+    packed int32 [dsize] = alpha0 | alpha1 << 16 in 11-bit fixed point, xmax).  clamp=True is the x axis (taps clamped into the row,
+    columns >= xmax replicate the last source pixel); the y axis keeps its fractions and clips the ROWS when they are read."""
+    scale = _cv_scale(ssize, dsize)
+    d = np.arange(dsize, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    xmax = dsize
+    if clamp:
+        neg = s < 0
+        f[neg], s[neg] = 0.0, 0
+        hi = s + 1 >= ssize
+        if hi.any():
+            xmax = int(np.argmax(hi))
+        last = s >= ssize - 1
+        f[last], s[last] = 0.0, ssize - 1
+    a0 = np.clip(np.rint((np.float32(1.0) - f) * np.float32(2048.0)), -32768, 32767).astype(np.int64)
+    a1 = np.clip(np.rint(f * np.float32(2048.0)), -32768, 32767).astype(np.int64)
+    packed = ((a0 & 0xffff) | ((a1 & 0xffff) << 16)).astype(np.uint32).view(np.int32)
+    return s.astype(np.int32), packed, xmax
+
+
+def cv_resize_plan(h, w, nh, nw, interp):
+    """(mode, tables int32, kx, ky, float bits of 1 / (kx ky), xmax) of cv2.resize((h, w) -> (nh, nw), interp): OpenCV picks the
+    integer-box INTER_AREA when both scales are whole numbers (to DBL_EPSILON), the table INTER_AREA when both are >= 1, and treats
+    INTER_AREA as INTER_LINEAR otherwise (its bilinear weights then differ from INTER_LINEAR's and are not built here)."""
+    if (h, w) == (nh, nw):
+        return CV_COPY, np.zeros(0, np.int32), 0, 0, 0, 0
+    if interp == "area":
+        sx, sy = _cv_scale(w, nw), _cv_scale(h, nh)
+        if sx < 1 or sy < 1:
+            raise NotImplementedError("INTER_AREA with an up-scaled axis")
+        kx, ky = int(np.rint(sx)), int(np.rint(sy))
+        if abs(sx - kx) < _DBL_EPS and abs(sy - ky) < _DBL_EPS:
+            return CV_AREA_INT, np.zeros(0, np.int32), kx, ky, int(np.array(np.float32(1.0) / np.float32(kx * ky), np.float32).view(np.int32)), 0
+        xi, xs, xa = cv_area_table(w, nw)
+        yi, ys, ya = cv_area_table(h, nh)
+        return CV_AREA, np.concatenate([xi, yi, xs, xa.view(np.int32), ys, ya.view(np.int32)]), 0, 0, 0, 0
+    if interp == "bilinear":
+        xo, xp, xmax = cv_linear_table(w, nw, True)
+        yo, yp, _ = cv_linear_table(h, nh, False)
+        return CV_LINEAR, np.concatenate([xo, xp, yo, yp]), 0, 0, 0, xmax
+    raise NotImplementedError(f"interpolation {interp!r}")
+
+
+def mm_test_geometry(h, w, scale=(640, 640), allow_scale_up=False, keep_ratio_first=True, use_mini_pad=False, stretch_only=False,
+                     half_pad_param=False):
+    """Both transforms for one image of (h, w): dict(resize=(nh, nw), interp, pads=(top, bottom, left, right), scale_factor (w, h),
+    pad_param float32[4], img_shape (H, W, 3), ori_shape (h, w)).  `scale` is (w, h) as in the config."""
+    (h1, w1), interp, sf = (keep_ratio_resize_geometry(h, w, tuple(scale)) if keep_ratio_first else ((h, w), None, None))
+    no_pad, again, sf2, pads, pad_param = letter_resize_geometry(h1, w1, tuple(scale)[::-1], allow_scale_up, use_mini_pad, stretch_only, half_pad_param)
+    if again:
+        if interp is not None:
+            raise NotImplementedError("two chained resizes (WeDetectLetterResize resizing the output of WeDetectKeepRatioResize)")
+        interp = "bilinear"                                # MMDET_Resize's default interpolation
+    scale_factor = sf2 if sf is None else (sf2[0] * sf[0], sf2[1] * sf[1])        # transforms.py:318-325
+    H, W = no_pad[0] + pads[0] + pads[1], no_pad[1] + pads[2] + pads[3]
+    return dict(resize=no_pad, interp=interp, pads=pads, scale_factor=scale_factor, pad_param=pad_param, img_shape=(int(H), int(W), 3), ori_shape=(h, w))
+
+
+def pack_mm_batch(images, H, W, **pipe):
+    """Host side of WD_OP_CV_RESIZE_PAD for one batch (same contract as pack_batch)."""
+    desc = np.zeros((len(images), DESC_WORDS), dtype=np.int32)
+    coef_parts, src_parts, metas = [], [], []
+    src_bytes = coef_words = 0
+    for b, im in enumerate(images):
+        im = np.ascontiguousarray(im)
+        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+            raise TypeError(f"expected uint8 [h, w, 3] BGR, got {im.dtype} {im.shape}")
+        h, w = im.shape[:2]
+        g = mm_test_geometry(h, w, **pipe)
+        if g["img_shape"][:2] != (H, W):
+            raise ValueError(f"image of {w}x{h} pads to {g['img_shape'][:2]}, the batch canvas is {(H, W)}")
+        nh, nw = g["resize"]
+        if nw < 1 or nh < 1:
+            raise ValueError(f"image of {w}x{h} resizes to an empty {nw}x{nh} area")
+        mode, tab, kx, ky, sbits, xmax = cv_resize_plan(h, w, nh, nw, g["interp"])
+        desc[b] = (src_bytes, 0, w, h, nw, nh, g["pads"][2], g["pads"][0], mode, coef_words, kx, ky, sbits, xmax, 0, 0)
+        src_parts.append((src_bytes, im.reshape(-1)))
+        coef_parts.append(tab)
+        src_bytes += (im.size + 15) // 16 * 16
+        coef_words += tab.size
+        if src_bytes >= 2 ** 31:
+            raise ValueError("batch of source images exceeds 2 GiB")
+        metas.append(g)
+    coef = np.concatenate(coef_parts) if coef_words else np.zeros(1, np.int32)
+    return dict(desc=desc, coef=coef, src_parts=src_parts, src_bytes=src_bytes, tmp_bytes=0, metas=metas)
+
+
+class MMTestPipeline(Letterbox):
+    """The resize / pad half of the reference's test pipeline for up to B decoded uint8 BGR images, on the device, into `out`
+    (uint8 [B, 3, H, W], channel order passed through).  run(images) returns one metainfo dict per image with the keys
+    PackDetInputs forwards (ori_shape, img_shape, scale_factor, pad_param): config/wedetect_base.py:111-133."""
+    _KIND = L.OP_CV_RESIZE_PAD
+
+    def __init__(self, out, scale=(640, 640), pad=114, allow_scale_up=False, **pipe):
+        super().__init__(out, pad=pad)
+        self.pipe = dict(scale=tuple(scale), allow_scale_up=allow_scale_up, **pipe)
+
+    def _pack(self, images):
+        return pack_mm_batch(images, self.H, self.W, **self.pipe)
+
+    def _result(self, pk):
+        return [dict(ori_shape=g["ori_shape"], img_shape=g["img_shape"], scale_factor=g["scale_factor"], pad_param=g["pad_param"]) for g in pk["metas"]]
