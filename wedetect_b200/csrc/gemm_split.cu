@@ -397,6 +397,27 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                 } else if (p.resid_dtype == 1) {
                     // fp16 hi (+ lo) planes; alpha already carries 1 / kPlaneScale
                     const __half* rp = reinterpret_cast<const __half*>(p.resid) + pix * p.ld_res + nb;
+                    if (nb + WCOLS <= p.N && (p.ld_res & 15) == 0 && (p.resid_ps & 15) == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 31) == 0) {
+                        // whole 32-byte sectors per lane (16 columns per load), as for the fp32 residual above
+#pragma unroll
+                        for (int j = 0; j < WCOLS; j += 16) {
+                            uint32_t x[8];
+                            asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]) : "l"(rp + j));
+                            uint64_t xs[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) xs[q] = h2_to_f2(x[q]);
+                            if (p.resid_ps) {
+                                uint32_t y[8];
+                                asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                             : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7]) : "l"(rp + p.resid_ps + j));
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) xs[q] = add2(xs[q], h2_to_f2(y[q]));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) acc2[j / 2 + q] = fma2(alpha2, xs[q], acc2[j / 2 + q]);
+                        }
+                    } else
 #pragma unroll
                     for (int j = 0; j < WCOLS; j += 8) {
                         if (nb + j < p.N) {
