@@ -202,6 +202,8 @@ SPLIT_SHAPES = [
     (128 * 9, 4096, 1024, None),  # K = 4096 (ConvNeXt stage-3 pw2 shape)
     (1000, 768, 1208, None),      # similarity-like: N tail in the last 256 tile
     (384, 320, 256, 128),         # forced BN=128 pair with 2 n-tiles
+    (128 * 300, 192, 128, None),  # 3 k-blocks per tile, many tiles per CTA: two-stage + one-stage blocks that wrap around the ring
+    (128 * 150, 576, 64, None),   # 9 k-blocks, BN=64 single CTA (the 64 -> 64 3x3 convolutions' K)
 ]
 
 

@@ -30,7 +30,8 @@ struct GemmParams {
     int lblk;            // split mode: 64-wide k-blocks accumulated in TMEM before the partial sum moves to fp32 registers
     float alpha;
     float acc_scale;     // split mode: accumulator * acc_scale = A . W^T in real units (undoes the operands' power-of-two scales)
-    float trunc_comp;    // split mode: relative shrink of a TMEM block sum caused by the tensor pipe's truncating adds (undone in the epilogue)
+    float trunc_comp;    // split mode: relative shrink of a TMEM block sum of `lblk` k-blocks caused by the tensor pipe's truncating adds
+    float trunc_comp1;   // ... of a trailing one-k-block sum (odd number of k-blocks with lblk = 2), brought to trunc_comp as it is added
     const float* bias;
     const float* gamma;
     const void* resid;

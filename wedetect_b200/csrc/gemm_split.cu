@@ -183,15 +183,18 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
             // its hi x hi products: the small terms meet a small accumulator, so only the 4 * lblk large adds truncate at full size.
             for (int tile = t_first; tile < t_total; tile += t_step) {
                 for (int kit = 0; kit < k_iters; kit += lblk) {
+                    // (an odd number of k-blocks ends with a one-stage block; a block may wrap around the ring)
+                    const int nst = min(lblk, k_iters - kit);
+                    const int st1 = stage + 1 == C::kStages ? 0 : stage + 1;
                     mbar_wait(&bar_tempty[as], aphase ^ 1);   // the epilogue has moved this buffer's previous block to registers
                     mbar_wait(&bar_full[stage], phase);
-                    if (lblk == 2) mbar_wait(&bar_full[stage + 1], phase);   // (an even stage count: the pair never wraps)
+                    if (nst == 2) mbar_wait(&bar_full[st1], st1 == 0 ? phase ^ 1 : phase);
                     tc_fence_after();
                     __syncwarp();
                     if (elect_one()) {
                         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                        for (int h = 0; h < lblk; ++h) {
-                            const uint32_t sbase = smem0 + (uint32_t)((stage + h) * C::STAGE_BYTES);
+                        for (int h = 0; h < nst; ++h) {
+                            const uint32_t sbase = smem0 + (uint32_t)((h == 0 ? stage : st1) * C::STAGE_BYTES);
                             const uint32_t ah = (sbase >> 4) & 0x3FFFu, al = ((sbase + C::A_BYTES) >> 4) & 0x3FFFu;
                             const uint32_t bh = ((sbase + 2 * C::A_BYTES) >> 4) & 0x3FFFu, bl = ((sbase + 2 * C::A_BYTES + C::B_BYTES) >> 4) & 0x3FFFu;
 #pragma unroll
@@ -207,8 +210,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                                 }
                             }
                         }
-                        for (int h = 0; h < lblk; ++h) {
-                            const uint32_t sbase = smem0 + (uint32_t)((stage + h) * C::STAGE_BYTES);
+                        for (int h = 0; h < nst; ++h) {
+                            const uint32_t sbase = smem0 + (uint32_t)((h == 0 ? stage : st1) * C::STAGE_BYTES);
                             const uint32_t ah = (sbase >> 4) & 0x3FFFu, bh = ((sbase + 2 * C::A_BYTES) >> 4) & 0x3FFFu;
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
@@ -217,17 +220,17 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                                 else umma_bf16(tmem_d, dah, dbh, idesc, 1u);
                             }
                         }
-                        for (int h = 0; h < lblk; ++h) {
-                            if constexpr (kPair) umma_commit_2sm_mc(&bar_empty[stage + h], (uint16_t)3);
-                            else umma_commit(&bar_empty[stage + h]);
+                        for (int h = 0; h < nst; ++h) {
+                            if constexpr (kPair) umma_commit_2sm_mc(&bar_empty[h == 0 ? stage : st1], (uint16_t)3);
+                            else umma_commit(&bar_empty[h == 0 ? stage : st1]);
                         }
                         if constexpr (kPair) umma_commit_2sm_mc(&bar_tfull[as], (uint16_t)3);
                         else umma_commit(&bar_tfull[as]);
                     }
                     __syncwarp();
-                    stage += lblk;
+                    stage += nst;
                     if (stage >= C::kStages) {
-                        stage = 0;
+                        stage -= C::kStages;
                         phase ^= 1;
                     }
                     if (++as == C::NBUF) {
@@ -252,7 +255,9 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
         uint8_t* wbuf = smem_epi + pairbuf * 4096;
         const uint32_t srow_s = smem_u32(wbuf) + lane * 128;
         const bool store_issuer = (cg & 1) == 0 && lane == 0;
-        const int nblk = k_iters / lblk;   // (the host only allows lblk = 2 for an even number of k-blocks)
+        const int nblk = (k_iters + lblk - 1) / lblk;   // an odd number of k-blocks ends with a one-stage block ...
+        const bool short_last = (k_iters % lblk) != 0;    // ... whose (smaller) truncation shrink is brought to the full blocks' first
+        const uint64_t dlast = splat2(p.trunc_comp1 - p.trunc_comp);
         int as = 0;
         uint32_t aphase = 0;
         auto release_acc = [&](int a) {
@@ -317,6 +322,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) gemm_split_kernel(const __gr
                 for (int j = 0; j < 16; ++j) {
                     uint64_t tv;
                     asm("mov.b64 %0, {%1, %2};" : "=l"(tv) : "r"(t[2 * j]), "r"(t[2 * j + 1]));
+                    if (short_last && b == nblk - 1) tv = fma2(tv, dlast, tv);
                     acc2[j] = b == 0 ? tv : add2(acc2[j], tv);
                 }
                 if (++as == C::NBUF) {

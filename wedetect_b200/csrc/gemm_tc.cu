@@ -559,14 +559,14 @@ int compile_gemm(const wd_op& op, std::unique_ptr<CompiledOp>& out) {
     else P.clu = (g->block_n == 256 && P.epi_mode == 0 && P.num_m_tiles >= 2 && I[36] == 0) ? 2 : 1;
     WD_REQUIRE(!(g->split && g->block_n == 256), "gemm: split (fp16 hi/lo) mode has 64- and 128-wide tiles");
     if (g->split) {
-        // Accumulator blocks of two k-blocks need an even number of k-blocks per tile and an even pipeline depth (the single-CTA
-        // 128-wide configuration has three stages).
-        if (P.lblk == 2 && ((P.kc_iters * P.ntaps) % 2 != 0 || (g->block_n == 128 && P.clu == 1))) P.lblk = 1;
+        // Accumulator blocks of two k-blocks: an odd number of k-blocks ends with a one-block sum, a block may wrap around the ring.
+        if (P.lblk == 2 && P.kc_iters * P.ntaps < 2) P.lblk = 1;
         // Measured on B200 (tools/trunc_probe.py, profiles/trunc_probe_r02.json): the tensor pipe truncates when it adds a
         // k-step's products to the fp32 accumulator, so a TMEM block sum comes out too small by a data- and K-independent
         // relative amount: 8.9e-8 (~1.5 * 2^-24) per 64-wide block, kSplitComp2 for a two-stage block.  The epilogue undoes it.
         // I[41] = 1 turns the compensation off (the probe uses it).
         P.trunc_comp = no_comp ? 0.f : (P.lblk == 1 ? 8.9e-8f : kSplitComp2);
+        P.trunc_comp1 = no_comp ? 0.f : 8.9e-8f;
     }
     P.num_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
 
