@@ -121,6 +121,25 @@ class ClockSampler:
         except Exception:
             self.errors += 1
 
+    def start_thread(self, period=0.004):
+        """Background sampling for timed loops whose steps synchronise with the host (an inline NVML query between two such steps
+        would sit inside the timed region with the GPU idle: power queries take up to ~10 ms on some boxes)."""
+        import threading
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                self.sample()
+                self._stop.wait(period)
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
+
+    def stop_thread(self):
+        self._stop.set()
+        self._thr.join(timeout=2.0)
+        if not self.rows:
+            self.sample()
+
     def poll_until(self, event):
         """Sample every ~3 ms until the CUDA event has completed."""
         while not event.query():
@@ -410,17 +429,18 @@ def run_side_workload(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local, None) as clk:
         barrier()
+        clk.start_thread()
         e0.record()
         rows = []
         for _ in range(args.steps):
             s_ = step_dev()
-            clk.sample()
             if s_ is not None:
                 rows.append(s_)
         if not prop:     # the corpus exchange: ONE all-gather of the [N_local, K] score rows (retrieval.gather_rows)
             allrows = gather_rows(torch.cat(rows, 0), world * B * args.steps)
         e1.record()
-        clk.poll_until(e1)
+        e1.synchronize()
+        clk.stop_thread()
         barrier()
     ms = e0.elapsed_time(e1)
     launches = L.launch_count() - l0
