@@ -247,6 +247,19 @@ int wd_program_run_timed(wd_program* prog, void* stream, float* ms_per_op);
 int wd_program_find_stuck_op(wd_program* prog, void* stream, int timeout_ms, int* stuck_op);
 void wd_program_destroy(wd_program* prog);
 
+/* ---- JPEG decode on the device (optional) ---------------------------------
+ * Replaces the reference's per-image CPU decode (LoadImageFromFile -> mmcv.imfrombytes -> cv2.imdecode, config/wedetect_base.py:112,
+ * infer_wedetect.py:111; Image.open().convert("RGB"), generate_proposal.py:1089-1090) with nvJPEG writing interleaved pixels into
+ * device memory (the `src` buffer of WD_OP_CV_RESIZE_PAD / WD_OP_LETTERBOX).  libnvjpeg is loaded lazily: wd_jpeg_open fails loudly
+ * where it is missing, nothing else depends on it.  Not bit-identical to libjpeg-turbo on chroma-subsampled files (opt-in).
+ *   wd_jpeg_info    width / height (and component count, nvjpegChromaSubsampling_t value) of a compressed image in HOST memory
+ *   wd_jpeg_decode  decode into dst (DEVICE, [h, pitch] bytes, 3 interleaved channels; bgr != 0: B,G,R order) on `stream` */
+typedef struct wd_jpeg wd_jpeg;
+int wd_jpeg_open(wd_jpeg** out);
+int wd_jpeg_info(wd_jpeg* j, const uint8_t* data, uint64_t len, int* width, int* height, int* components, int* subsampling);
+int wd_jpeg_decode(wd_jpeg* j, const uint8_t* data, uint64_t len, uint8_t* dst, uint64_t pitch, int bgr, void* stream);
+void wd_jpeg_close(wd_jpeg* j);
+
 /* workspace size needed by WD_OP_POSTPROCESS for (B, anchors, K). */
 uint64_t wd_pp_workspace_bytes(int B, int anchors, int K, int nms_pre);
 

@@ -108,3 +108,86 @@ def test_predict_images_equals_test_step_on_the_oracle_pipeline():
     keep = out[0].pred_instances.scores > thr
     assert len(det["confidence"]) == min(10, int(keep.sum())) and det["xyxy"].shape == (len(det["confidence"]), 4) and det["class_id"].dtype == np.int64
     assert np.array_equal(det["confidence"], out[0].pred_instances.scores[keep][:10].cpu().numpy())
+
+
+def _photo_like(seed, h, w):
+    """Smooth structure + mild noise: what a JPEG codec is built for (pure noise would measure the quantiser, not the decoder)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([128 + 100 * np.sin(xx / (17 + 5 * c) + c) * np.cos(yy / (23 + 3 * c)) for c in range(3)], -1)
+    img += rng.normal(0, 6, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def test_device_jpeg_decode_feeds_the_pipeline():
+    """decode='nvjpeg': compressed bytes in, nvJPEG writes BGR pixels into the resize kernel's source buffer.  The geometry and
+    metainfo are exactly those of the host-decoded path; pixels are compared with cv2.imdecode (libjpeg-turbo): the two
+    decoders differ in IDCT rounding, colour conversion and chroma up-sampling: a few grey levels at most, < 1 on average."""
+    cv2 = pytest.importorskip("cv2")
+    from wedetect_b200.preprocess import MMTestPipeline, Letterbox, EncodedImage
+    shapes = [(480, 640), (720, 1280), (375, 500), (333, 500)]
+    blobs, decoded = [], []
+    for i, (h, w) in enumerate(shapes):
+        img = _photo_like(40 + i, h, w)
+        sub = cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444 if i == 0 else cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420
+        ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sub])
+        assert ok
+        blobs.append(enc.tobytes())
+        decoded.append(cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    grey = cv2.imencode(".jpg", _photo_like(50, 200, 300)[:, :, 0])[1]
+    blobs.append(grey.tobytes())
+    decoded.append(cv2.imdecode(grey, cv2.IMREAD_COLOR))
+    out_h = torch.zeros(len(blobs), 3, 640, 640, dtype=torch.uint8, device=D)
+    out_d = torch.zeros_like(out_h)
+    metas_h = MMTestPipeline(out_h).run(decoded)
+    pipe = MMTestPipeline(out_d)
+    items = pipe.encoded(blobs, lambda rest: [cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR) for b in rest])
+    assert all(isinstance(it, EncodedImage) for it in items)
+    metas_d = pipe.run(items)
+    torch.cuda.synchronize()
+    assert pipe.h2d_bytes < sum(d.size for d in decoded) // 4                       # only compressed bytes + tables crossed PCIe
+    for a, b in zip(metas_h, metas_d):
+        assert a["ori_shape"] == b["ori_shape"] and tuple(a["scale_factor"]) == tuple(b["scale_factor"]) and np.array_equal(a["pad_param"], b["pad_param"])
+    diff = (out_h.int() - out_d.int()).abs()
+    per_img = [int(diff[i].max()) for i in range(len(blobs))]
+    mean = [float(diff[i].float().mean()) for i in range(len(blobs))]
+    print("nvJPEG vs cv2 after resize/pad: max abs", per_img, "mean abs", [round(m, 3) for m in mean])
+    # measured on B200 / nvJPEG 12.4 vs OpenCV 4.13 (libjpeg-turbo): max abs [4, 6, 9, 8, 1], mean abs 0.34-0.63 grey levels
+    assert per_img[0] <= 6 and max(per_img) <= 12 and max(mean) <= 1.0
+    # a PNG (not a JPEG) and an array go through the host decoder inside the same call
+    png = cv2.imencode(".png", decoded[0])[1].tobytes()
+    items = pipe.encoded([png, decoded[1]], lambda rest: [cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR) for b in rest])
+    assert isinstance(items[0], np.ndarray) and np.array_equal(items[0], decoded[0]) and items[1] is decoded[1]
+    # the Uni entry point's RGB order
+    out_u = torch.zeros(1, 3, 640, 640, dtype=torch.uint8, device=D)
+    lb = Letterbox(out_u)
+    lb.run(lb.encoded([blobs[0]], None))
+    ref_u = torch.zeros_like(out_u)
+    Letterbox(ref_u).run([decoded[0][:, :, ::-1]])
+    torch.cuda.synchronize()
+    assert int((out_u.int() - ref_u.int()).abs().max()) <= 6
+
+
+def test_predict_images_with_device_decode(tmp_path):
+    """File names in, detections out, decode on the device: same boxes as the host-decoded run up to the decoder's pixel noise."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import synth
+    from wedetect_b200.api import init_detector
+    sd = synth.synth_state_dict("base", seed=0, with_text=False, regime="sparse")
+    model = init_detector(CFG, checkpoint=dict(state_dict=sd), device=D)
+    g = torch.Generator().manual_seed(3)
+    model.set_text_features(torch.nn.functional.normalize(torch.randn(1, 12, 768, generator=g), dim=-1))
+    files = []
+    for i, (h, w) in enumerate([(480, 640), (600, 400)]):
+        f = str(tmp_path / f"img{i}.jpg")
+        cv2.imwrite(f, _photo_like(60 + i, h, w), [cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+        files.append(f)
+    host = model.predict_images(files)
+    dev = model.predict_images(files, decode="nvjpeg")
+    for a, b in zip(host, dev):
+        assert a.metainfo["ori_shape"] == b.metainfo["ori_shape"] and a.metainfo["img_path"] == b.metainfo["img_path"]
+        n = min(len(a.pred_instances), len(b.pred_instances), 20)
+        assert n > 0
+        # the strongest detections survive +-1 grey level of decoder noise: same labels, boxes within a pixel
+        la, lb_ = a.pred_instances.labels[:5].tolist(), b.pred_instances.labels[:5].tolist()
+        assert len(set(la) & set(lb_)) >= 3

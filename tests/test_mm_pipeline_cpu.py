@@ -164,3 +164,21 @@ def test_geometry_branches():
     assert g["resize"][0] == 639 and g["pads"][:2] == (0, 1)
     with pytest.raises(NotImplementedError):             # ... and with allow_scale_up the second stage would resize again
         P.mm_test_geometry(1077, 500, allow_scale_up=True)
+
+
+def test_exif_orientation_parser():
+    """cv2.imdecode rotates by the EXIF orientation, nvJPEG does not: such files must be routed to the host decoder."""
+    import io
+    from PIL import Image
+    from wedetect_b200.preprocess import exif_orientation
+    im = Image.fromarray(np.zeros((8, 8, 3), np.uint8))
+    buf = io.BytesIO()
+    im.save(buf, "JPEG")
+    assert exif_orientation(buf.getvalue()) == 1
+    for val in (1, 3, 6, 8):
+        ex = Image.Exif()
+        ex[0x0112] = val
+        buf = io.BytesIO()
+        im.save(buf, "JPEG", exif=ex.tobytes())
+        assert exif_orientation(buf.getvalue()) == val
+    assert exif_orientation(b"\xff\xd8\xff\xd9") == 1 and exif_orientation(b"") == 1

@@ -22,7 +22,7 @@ EXPORTS = [
     "wd_last_error", "wd_version", "wd_launch_count", "wd_device_info", "wd_op_run", "wd_program_create",
     "wd_program_run", "wd_program_capture", "wd_program_replay", "wd_program_num_launches",
     "wd_program_destroy", "wd_pp_workspace_bytes", "wd_program_num_ops", "wd_program_run_timed",
-    "wd_program_find_stuck_op", "wd_act_plane_scale",
+    "wd_program_find_stuck_op", "wd_act_plane_scale", "wd_jpeg_open", "wd_jpeg_info", "wd_jpeg_decode", "wd_jpeg_close",
 ]
 
 
@@ -85,6 +85,11 @@ def load(require_gpu=True, device=0):
         lib.wd_program_destroy.restype = None
         lib.wd_pp_workspace_bytes.argtypes = [ctypes.c_int] * 4
         lib.wd_pp_workspace_bytes.restype = ctypes.c_uint64
+        lib.wd_jpeg_open.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+        lib.wd_jpeg_info.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint64] + [ctypes.POINTER(ctypes.c_int)] * 4
+        lib.wd_jpeg_decode.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p]
+        lib.wd_jpeg_close.argtypes = [ctypes.c_void_p]
+        lib.wd_jpeg_close.restype = None
         _lib = lib
     if require_gpu:
         sm, major, minor = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
@@ -112,6 +117,37 @@ def launch_count():
 def run_op(op, stream=0):
     lib = load()
     check(lib.wd_op_run(ctypes.byref(op), ctypes.c_void_p(stream)), f"wd_op_run(kind={op.kind})")
+
+
+class JpegDecoder:
+    """nvJPEG decoder state on the current device (wd_jpeg_*): info() parses the header on the host, decode() writes
+    interleaved pixels into device memory on a stream."""
+
+    def __init__(self):
+        lib = load()
+        self._lib = lib
+        h = ctypes.c_void_p()
+        check(lib.wd_jpeg_open(ctypes.byref(h)), "wd_jpeg_open")
+        self._h = h
+
+    def info(self, data):
+        w, h, nc, css = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        check(self._lib.wd_jpeg_info(self._h, data, len(data), ctypes.byref(w), ctypes.byref(h), ctypes.byref(nc), ctypes.byref(css)), "wd_jpeg_info")
+        return w.value, h.value, nc.value, css.value
+
+    def decode(self, data, dst_ptr, pitch, bgr=True, stream=0):
+        check(self._lib.wd_jpeg_decode(self._h, data, len(data), ctypes.c_void_p(dst_ptr), pitch, 1 if bgr else 0, ctypes.c_void_p(stream)), "wd_jpeg_decode")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.wd_jpeg_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Program:

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libwedetect_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_split.cu", "rowops.cu", "postprocess.cu", "preprocess.cu", "mlp_fused.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_split.cu", "rowops.cu", "postprocess.cu", "preprocess.cu", "mlp_fused.cu", "jpeg.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 # exact-arithmetic files: no FMA contraction so the CPU oracle can reproduce every comparison

@@ -316,16 +316,20 @@ class YOLOWorldDetector:
             out["keep_ratio_first"] = "WeDetectKeepRatioResize" in types
         return out
 
-    def predict_images(self, images, texts=None, rescale=True):
+    def predict_images(self, images, texts=None, rescale=True, decode="host"):
         """infer_wedetect.py:102-117 for a batch of images: LoadImageFromFile (host decode; arrays are taken as decoded BGR),
         WeDetectKeepRatioResize + WeDetectLetterResize on the device (cv2-exact, transforms.py:94-123,180-272) straight into the
         detector's input, then test_step.  texts: list of prompts (one shared set), or None for the reparameterized features.
-        Returns one DetDataSample per image with the metainfo PackDetInputs would carry."""
+        Returns one DetDataSample per image with the metainfo PackDetInputs would carry.  decode="nvjpeg": JPEG files / byte strings
+        are decoded on the device (a few grey levels from cv2's libjpeg-turbo on chroma-subsampled files; opt-in)."""
         if self._sd is None:
             raise RuntimeError("load_state_dict first")
-        arrays = decode_images_bgr(images)
+        if decode not in ("host", "nvjpeg"):
+            raise ValueError(f"decode={decode!r}")
+        images = list(images)
+        arrays = decode_images_bgr(images) if decode == "host" else None
         pc = self.pipeline_cfg()
-        (W, H), B = pc["scale"], len(arrays)
+        (W, H), B = pc["scale"], len(images)
         if texts is not None:
             flat = [t[0] if isinstance(t, (list, tuple)) else t for t in texts]
             src = self.forward_text([flat])
@@ -339,6 +343,8 @@ class YOLOWorldDetector:
             pipe = getattr(p, "_mm_pipe", None)
             if pipe is None:
                 pipe = p._mm_pipe = MMTestPipeline(p.image, **pc)
+            if arrays is None:
+                arrays = pipe.encoded(images, decode_images_bgr)
             metas = pipe.run(arrays)
             samples = [DetDataSample(dict(m, img_id=i, img_path=(im if isinstance(im, str) else None))) for i, (m, im) in enumerate(zip(metas, images))]
             return self._predict_on(p, src, feats, None, samples, rescale, B, H, W)
@@ -448,16 +454,20 @@ class SimpleYOLOWorldDetector:
         p.image.copy_(inputs, non_blocking=True)
         return self._run(p, key, B, H, W, ratios, offsets, ori_shapes, rescale)
 
-    def forward(self, image_paths, rescale=True):
+    def forward(self, image_paths, rescale=True, decode="host"):
         """image_paths: list of file names, PIL images or uint8 [h,w,3] RGB arrays (generate_proposal.py:1082-1117).
-        Decoding stays with PIL; the letterbox (BILINEAR resize + 114 padding) runs on the device, bit-exact with PIL."""
-        arrays = decode_images(image_paths)
-        B, (H, W) = len(arrays), self.img_size
+        Decoding stays with PIL (decode="nvjpeg": JPEG files / byte strings are decoded on the device instead, opt-in); the letterbox
+        (BILINEAR resize + 114 padding) runs on the device, bit-exact with PIL."""
+        image_paths = list(image_paths)
+        arrays = decode_images(image_paths) if decode == "host" else None
+        B, (H, W) = len(image_paths), self.img_size
         key = (B, H, W, torch.uint8)
         p = self._plan(*key)
         if key not in self._letterbox:
             self._letterbox[key] = Letterbox(p.image)
         with _on(self.device):
+            if arrays is None:
+                arrays = self._letterbox[key].encoded(image_paths, decode_images)
             ratios, offsets, ori_shapes = self._letterbox[key].run(arrays)
         return self._run(p, key, B, H, W, ratios, offsets, ori_shapes, rescale)
 

@@ -86,6 +86,64 @@ def load_rgb(item):
     return item
 
 
+class EncodedImage:
+    """A JPEG still in its compressed form, to be decoded on the device by nvJPEG (wd_jpeg_*) straight into the source buffer of the
+    resize kernels; (h, w) come from the header."""
+
+    def __init__(self, blob, h, w):
+        self.blob, self.h, self.w = blob, int(h), int(w)
+        self.shape, self.size = (self.h, self.w, 3), self.h * self.w * 3
+
+
+_JPEG_SOI = b"\xff\xd8\xff"
+
+
+def exif_orientation(blob):
+    """EXIF orientation tag (0x0112) of a JPEG byte string, 1 when absent: cv2.imdecode(IMREAD_COLOR) rotates by it, nvJPEG and PIL's
+    plain open() do not."""
+    i, n = 2, len(blob)
+    while i + 4 <= n and blob[i] == 0xFF:
+        marker, seglen = blob[i + 1], int.from_bytes(blob[i + 2: i + 4], "big")
+        if marker == 0xDA or seglen < 2:          # start of scan: no more headers
+            break
+        if marker == 0xE1 and blob[i + 4: i + 10] == b"Exif\x00\x00":
+            t = i + 10
+            order = "little" if blob[t: t + 2] == b"II" else "big"
+            ifd = t + int.from_bytes(blob[t + 4: t + 8], order)
+            if ifd + 2 > n:
+                return 1
+            for k in range(int.from_bytes(blob[ifd: ifd + 2], order)):
+                e = ifd + 2 + 12 * k
+                if e + 12 > n:
+                    break
+                if int.from_bytes(blob[e: e + 2], order) == 0x0112:
+                    return int.from_bytes(blob[e + 8: e + 10], order)
+            return 1
+        i += 2 + seglen
+    return 1
+
+
+def read_encoded(item, decoder, honour_exif=False):
+    """File name / bytes of a 3-component (or grey) JPEG -> EncodedImage; anything else -> None (decoded on the host instead).
+    honour_exif: files whose EXIF orientation is not 1 also go to the host decoder (cv2 rotates them, nvJPEG would not)."""
+    blob = item if isinstance(item, (bytes, bytearray, memoryview)) else None
+    if blob is None and (isinstance(item, str) or hasattr(item, "__fspath__")):
+        with open(os.fsdecode(item), "rb") as f:
+            blob = f.read()
+    if blob is None:
+        return None
+    blob = bytes(blob)
+    if blob[:3] != _JPEG_SOI or (honour_exif and exif_orientation(blob) != 1):
+        return None
+    try:
+        w, h, nc, _ = decoder.info(blob)
+    except L.WdError:
+        return None
+    if w < 1 or h < 1 or nc not in (1, 3):
+        return None
+    return EncodedImage(blob, h, w)
+
+
 def load_bgr(item):
     """One input of the mmdet test pipeline -> uint8 [h, w, 3] BGR: a file name is decoded as LoadImageFromFile does (mmcv.imfrombytes,
     cv2 backend, flag 'color' = cv2.IMREAD_COLOR: infer_wedetect.py:111, config/wedetect_base.py:112); an array is taken as decoded."""
@@ -131,9 +189,10 @@ def pack_batch(images, H, W, with_src=True):
     src_bytes = coef_words = tmp_bytes = 0
     ratios, offsets, shapes = [], [], []
     for b, im in enumerate(images):
-        im = np.ascontiguousarray(im)
-        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
-            raise TypeError(f"expected uint8 [h, w, 3] RGB, got {im.dtype} {im.shape}")
+        if not isinstance(im, EncodedImage):
+            im = np.ascontiguousarray(im)
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise TypeError(f"expected uint8 [h, w, 3] RGB, got {im.dtype} {im.shape}")
         h, w = im.shape[:2]
         r, (nw, nh), (left, top), off = letterbox_params(w, h, (H, W))
         if nw < 1 or nh < 1:
@@ -152,7 +211,7 @@ def pack_batch(images, H, W, with_src=True):
         tables = np.concatenate([bh.reshape(-1), kh.reshape(-1), bv.reshape(-1), kv.reshape(-1)])
         # byte offsets are (lo, hi) int32 pairs in the ABI; one batch of decoded images stays below 2 GiB (checked below)
         desc[b] = (src_bytes, 0, w, h, nw, nh, left, top, first, rows, tmp_bytes, 0, coef_words, ksh, ksv, vfirst)
-        src_parts.append((src_bytes, im.reshape(-1)))
+        src_parts.append((src_bytes, im if isinstance(im, EncodedImage) else im.reshape(-1)))
         coef_parts.append(tables)
         src_bytes += (im.size + 15) // 16 * 16
         coef_words += tables.size
@@ -165,7 +224,8 @@ def pack_batch(images, H, W, with_src=True):
     if with_src:
         src = np.zeros(src_bytes, dtype=np.uint8)
         for off, flat in src_parts:
-            src[off: off + flat.size] = flat
+            if not isinstance(flat, EncodedImage):
+                src[off: off + flat.size] = flat
         out["src"] = src
     return out
 
@@ -173,9 +233,27 @@ def pack_batch(images, H, W, with_src=True):
 class Letterbox:
     """Letterboxes up to B decoded RGB images into `out` (uint8 [B, 3, H, W], device) on the current stream."""
     _KIND = L.OP_LETTERBOX
+    _BGR = False          # channel order nvJPEG writes for this entry point (the Uni path works on RGB, the mmdet path on BGR)
 
     def _pack(self, images):
         return pack_batch(images, self.H, self.W, with_src=False)
+
+    def decoder(self):
+        """nvJPEG state of this device (created on first use)."""
+        if getattr(self, "_jpeg", None) is None:
+            self._jpeg = L.JpegDecoder()
+        return self._jpeg
+
+    def encoded(self, items, host_decode):
+        """items -> list for run(): JPEG files / byte strings stay compressed (EncodedImage, decoded on the device), everything
+        else goes through `host_decode`."""
+        dec = self.decoder()
+        out = [it if isinstance(it, np.ndarray) else read_encoded(it, dec, honour_exif=self._BGR) for it in items]
+        rest = [i for i, o in enumerate(out) if o is None]
+        if rest:
+            for i, arr in zip(rest, host_decode([items[i] for i in rest])):
+                out[i] = arr
+        return out
 
     def _result(self, pk):
         return pk["ratios"], pk["offsets"], pk["shapes"]
@@ -227,15 +305,23 @@ class Letterbox:
         desc[: len(images)] = pk["desc"]
         src_np = self._host["src"].numpy()
         # pageable -> pinned: one memcpy per image, spread over a few threads (numpy releases the GIL for the copy)
-        list(_pool().map(lambda part: np.copyto(src_np[part[0]: part[0] + part[1].size], part[1]), pk["src_parts"]))
+        host_parts = [p_ for p_ in pk["src_parts"] if not isinstance(p_[1], EncodedImage)]
+        list(_pool().map(lambda part: np.copyto(src_np[part[0]: part[0] + part[1].size], part[1]), host_parts))
         self._host["coef"].numpy()[:n_coef] = pk["coef"].view(np.int32)
-        self._devb["src"][:n_src].copy_(self._host["src"][:n_src], non_blocking=True)
+        if host_parts:           # (a batch of compressed images only sends its JPEG bytes: nothing to copy here)
+            self._devb["src"][:n_src].copy_(self._host["src"][:n_src], non_blocking=True)
         self._devb["coef"][:n_coef].copy_(self._host["coef"][:n_coef], non_blocking=True)
         self._desc_dev.copy_(self._desc_host, non_blocking=True)
         self._copied = torch.cuda.Event()
         self._copied.record()
-        self._program.run(torch.cuda.current_stream().cuda_stream)
-        self.h2d_bytes = n_src + 4 * n_coef + 4 * self.B * DESC_WORDS
+        stream = torch.cuda.current_stream().cuda_stream
+        enc_bytes = 0
+        for off, part in pk["src_parts"]:      # compressed images: nvJPEG writes the pixels where the H2D copy would have put them
+            if isinstance(part, EncodedImage):
+                self.decoder().decode(part.blob, self._devb["src"].data_ptr() + off, 3 * part.w, bgr=self._BGR, stream=stream)
+                enc_bytes += len(part.blob)
+        self._program.run(stream)
+        self.h2d_bytes = (n_src if host_parts else 0) + enc_bytes + 4 * n_coef + 4 * self.B * DESC_WORDS
         return self._result(pk)
 
 
@@ -399,9 +485,10 @@ def pack_mm_batch(images, H, W, **pipe):
     coef_parts, src_parts, metas = [], [], []
     src_bytes = coef_words = 0
     for b, im in enumerate(images):
-        im = np.ascontiguousarray(im)
-        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
-            raise TypeError(f"expected uint8 [h, w, 3] BGR, got {im.dtype} {im.shape}")
+        if not isinstance(im, EncodedImage):
+            im = np.ascontiguousarray(im)
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise TypeError(f"expected uint8 [h, w, 3] BGR, got {im.dtype} {im.shape}")
         h, w = im.shape[:2]
         g = mm_test_geometry(h, w, **pipe)
         if g["img_shape"][:2] != (H, W):
@@ -411,7 +498,7 @@ def pack_mm_batch(images, H, W, **pipe):
             raise ValueError(f"image of {w}x{h} resizes to an empty {nw}x{nh} area")
         mode, tab, kx, ky, sbits, xmax = cv_resize_plan(h, w, nh, nw, g["interp"])
         desc[b] = (src_bytes, 0, w, h, nw, nh, g["pads"][2], g["pads"][0], mode, coef_words, kx, ky, sbits, xmax, 0, 0)
-        src_parts.append((src_bytes, im.reshape(-1)))
+        src_parts.append((src_bytes, im if isinstance(im, EncodedImage) else im.reshape(-1)))
         coef_parts.append(tab)
         src_bytes += (im.size + 15) // 16 * 16
         coef_words += tab.size
@@ -427,6 +514,7 @@ class MMTestPipeline(Letterbox):
     (uint8 [B, 3, H, W], channel order passed through).  run(images) returns one metainfo dict per image with the keys
     PackDetInputs forwards (ori_shape, img_shape, scale_factor, pad_param): config/wedetect_base.py:111-133."""
     _KIND = L.OP_CV_RESIZE_PAD
+    _BGR = True
 
     def __init__(self, out, scale=(640, 640), pad=114, allow_scale_up=False, **pipe):
         super().__init__(out, pad=pad)
