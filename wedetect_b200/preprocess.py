@@ -239,10 +239,15 @@ class Letterbox:
         return pack_batch(images, self.H, self.W, with_src=False)
 
     def decoder(self):
-        """nvJPEG state of this device (created on first use)."""
-        if getattr(self, "_jpeg", None) is None:
-            self._jpeg = L.JpegDecoder()
-        return self._jpeg
+        """nvJPEG state of the calling thread on this device (created on first use): the Huffman stage of nvjpegDecode runs on the
+        host, so a batch is decoded from the thread pool, one decoder state per worker."""
+        import threading
+        if getattr(self, "_tls", None) is None:
+            self._tls = threading.local()
+        if getattr(self._tls, "jpeg", None) is None:
+            with torch.cuda.device(self.dev):
+                self._tls.jpeg = L.JpegDecoder()
+        return self._tls.jpeg
 
     def encoded(self, items, host_decode):
         """items -> list for run(): JPEG files / byte strings stay compressed (EncodedImage, decoded on the device), everything
@@ -315,11 +320,18 @@ class Letterbox:
         self._copied = torch.cuda.Event()
         self._copied.record()
         stream = torch.cuda.current_stream().cuda_stream
-        enc_bytes = 0
-        for off, part in pk["src_parts"]:      # compressed images: nvJPEG writes the pixels where the H2D copy would have put them
-            if isinstance(part, EncodedImage):
-                self.decoder().decode(part.blob, self._devb["src"].data_ptr() + off, 3 * part.w, bgr=self._BGR, stream=stream)
-                enc_bytes += len(part.blob)
+        # compressed images: nvJPEG writes the pixels where the H2D copy would have put them (all on this stream, ahead of the kernel)
+        enc = [(off, part) for off, part in pk["src_parts"] if isinstance(part, EncodedImage)]
+        base = self._devb["src"].data_ptr()
+
+        def dec_one(job):
+            with torch.cuda.device(self.dev):
+                self.decoder().decode(job[1].blob, base + job[0], 3 * job[1].w, bgr=self._BGR, stream=stream)
+        if len(enc) > 1:
+            list(_pool().map(dec_one, enc))
+        elif enc:
+            dec_one(enc[0])
+        enc_bytes = sum(len(part.blob) for _, part in enc)
         self._program.run(stream)
         self.h2d_bytes = (n_src if host_parts else 0) + enc_bytes + 4 * n_coef + 4 * self.B * DESC_WORDS
         return self._result(pk)
