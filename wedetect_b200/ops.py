@@ -125,7 +125,7 @@ def pick_block_n(N, out_f32=False, split=False, m_tiles=2):
 # fp16 hi/lo mode: 64-wide k-blocks (1 or 2) a TMEM accumulator lives for before its partial sum moves to fp32 registers: the
 # tensor pipe truncates on every accumulate (gemm_split.cu).  Two-block accumulators halve the TMEM -> register traffic that
 # bounds the kernel (+8 % images/s) at the same distance from a float64 run of the reference (tools/trunc_probe.py,
-# profiles/e2e_*_r02*.json); the library falls back to 1 where a tile has an odd number of k-blocks.
+# profiles/e2e_*_r02*.json); an odd number of k-blocks ends with a one-block sum (its own correction).
 SPLIT_LBLK = int(_os.environ.get("WD_SPLIT_LBLK", "2"))
 
 # activations for which the fast path must use the exact formula (debug / accuracy studies): subset of {ACT_SILU, ACT_GELU}
