@@ -99,15 +99,14 @@ __device__ __forceinline__ uint64_t act2_exact(uint64_t x, float osc) {
         const uint64_t e = erf_gelu_abs2(x, t);
         return fma2(mul2(t, hs), e, mul2(x, hs));
     } else if constexpr (ACT == WD_ACT_SILU) {
-        // x / (1 + exp(-x)): MUFU.EX2, MUFU.RCP and one Newton step on the reciprocal
+        // x / (1 + 2^(-x log2 e)): MUFU.EX2 + MUFU.RCP.  The exponential's 2^-22 relative error already bounds the quotient, so the
+        // reciprocal (2^-23) is not refined; x -> -inf gives 2^(+big) = inf, 1 / inf = 0, x * 0 = -0: the right limit, no clamp needed.
         float m0, m1;
         upk2(mul2(x, splat2(-1.4426950408889634f)), m0, m1);
-        const uint64_t d = add2(pk2(ex2_approx(fminf(m0, 126.f)), ex2_approx(fminf(m1, 126.f))), splat2(1.f));
+        const uint64_t d = add2(pk2(ex2_approx(m0), ex2_approx(m1)), splat2(1.f));
         float d0, d1;
         upk2(d, d0, d1);
-        uint64_t r = pk2(rcp_approx(d0), rcp_approx(d1));
-        r = fma2(r, fma2(neg2(d), r, splat2(1.f)), r);
-        return mul2(mul2(x, splat2(osc)), r);
+        return mul2(mul2(x, splat2(osc)), pk2(rcp_approx(d0), rcp_approx(d1)));
     } else if constexpr (ACT == WD_ACT_RELU) {
         float a, b;
         upk2(x, a, b);
