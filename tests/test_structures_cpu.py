@@ -158,3 +158,71 @@ def test_uni_forward_tensor_host_logic_with_a_stub_plan(monkeypatch):
     assert stub.meta[0][:, 6].tolist() == [1.0, 1.0] and stub.meta[0][0, 5] == 8.0       # offsets still removed, ratio not applied
     with pytest.raises(RuntimeError):
         det.SimpleYOLOWorldDetector("base", 768, 256, P, device="cpu").score_text(torch.zeros(3, 768))
+
+
+def test_pipeline_cfg_and_predict_images_host_logic(monkeypatch):
+    """predict_images around stubs: the transform parameters come from cfg.test_pipeline (config/wedetect_base.py:111-118), the
+    device pipeline's metainfo lands in the samples (what PackDetInputs would have packed), prompts resolve like infer_wedetect.py,
+    and api.inference_detector applies the script's tail (score threshold, top-k, numpy)."""
+    import numpy as np
+    import wedetect_b200._lib as L
+    from wedetect_b200 import api, detector as det
+    monkeypatch.setattr(L, "load", lambda require_gpu=True, device=0: None)
+    m = det.YOLOWorldDetector(size="tiny", device="cpu", cuda_graph=False)
+    assert m.pipeline_cfg() == dict(scale=(640, 640), allow_scale_up=False, pad=114)           # no config: the shipped values
+    m.cfg = dict(test_pipeline=[dict(type="LoadImageFromFile"), dict(type="WeDetectKeepRatioResize", scale=(96, 64)),
+                                dict(type="WeDetectLetterResize", scale=(96, 64), allow_scale_up=False, pad_val=dict(img=114)), dict(type="PackDetInputs")])
+    pc = m.pipeline_cfg()
+    assert pc["scale"] == (96, 64) and pc["pad"] == 114 and pc["allow_scale_up"] is False and pc["keep_ratio_first"] is True
+    m.cfg["test_pipeline"][1]["scale"] = (64, 64)
+    with pytest.raises(NotImplementedError):
+        m.pipeline_cfg()
+    m.cfg["test_pipeline"][1]["scale"] = (96, 64)
+
+    B, H, W = 2, 64, 96
+
+    class StubPlan:
+        def __init__(self):
+            self.image = torch.zeros(B, 3, H, W, dtype=torch.uint8)
+            self._graph, self._text_key, self.K = False, None, None
+
+        def set_text(self, f):
+            self.K = f.shape[0]
+
+        def set_meta(self, mm, c):
+            self.meta = (mm.clone(), c.clone())
+
+        def run(self):
+            pass
+
+        def results(self):
+            return dict(boxes=torch.rand(B, 5, 4), scores=torch.tensor([[0.9, 0.8, 0.5, 0.2, 0.1]] * B), labels=torch.ones(B, 5, dtype=torch.int32),
+                        anchors=torch.zeros(B, 5, dtype=torch.int32), counts=torch.tensor([5, 2], dtype=torch.int32))
+
+    class StubPipe:
+        def __init__(self, out, **pipe):
+            self.pipe = pipe
+
+        def run(self, arrays):
+            self.seen = [a.shape for a in arrays]
+            return [dict(ori_shape=a.shape[:2], img_shape=(H, W, 3), scale_factor=(0.5, 0.5), pad_param=np.array([1, 2, 0, 0], np.float32)) for a in arrays]
+
+    stub = StubPlan()
+    m._sd = {}
+    monkeypatch.setattr(m, "_plan", lambda *a: stub)
+    monkeypatch.setattr(det, "MMTestPipeline", StubPipe)
+    imgs = [np.zeros((100, 192, 3), np.uint8), np.zeros((128, 60, 3), np.uint8)]
+    with pytest.raises(TypeError):
+        m.predict_images(imgs)                                           # neither texts nor reparameterized features
+    m.set_text_features(torch.randn(3, 768))
+    out = m.predict_images(imgs)
+    assert stub._mm_pipe.pipe["scale"] == (96, 64) and stub._mm_pipe.seen == [(100, 192, 3), (128, 60, 3)] and stub.K == 3
+    assert [len(o.pred_instances) for o in out] == [5, 2] and out[1].metainfo["ori_shape"] == (128, 60) and out[0].metainfo["img_id"] == 0
+    meta, clamp = stub.meta
+    assert meta[0].tolist() == pytest.approx([0.0, 1.0, 0.5, 0.5, 0.0, 0.0, 1.0, 0.0]) and clamp.tolist() == [[192.0, 100.0], [60.0, 128.0]]
+    with pytest.raises(ValueError):
+        m.predict_images(imgs, decode="gpu")
+    one = api.inference_detector(m, imgs[0], None, max_dets=2, score_thr=0.3)
+    assert one["confidence"].tolist() == pytest.approx([0.9, 0.8]) and one["xyxy"].shape == (2, 4) and one["class_id"].dtype == np.int64
+    many = api.inference_detector(m, imgs, None, score_thr=0.85)
+    assert [len(d["confidence"]) for d in many] == [1, 1]
