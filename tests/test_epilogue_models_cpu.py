@@ -14,8 +14,8 @@ def kernel_gelu_coefficients():
     body = src[src.index("#ifndef WD_GELU_TWO_INTERVAL"): src.index("#else")]
     c = [float(v) for v in re.findall(r"splat2\((-?[0-9.]+e?-?[0-9]*)f\)", body)]
     clamp = float(re.search(r"fminf\(a0, ([0-9.]+)f\)", body).group(1))
-    assert len(c) == 11 and c[-2:] == [-1.0, 1.0]            # 9 polynomial coefficients (highest first), then the (-1, 1) of 1 - 2^r
-    return np.array(c[:9], np.float32), np.float32(clamp)
+    assert len(c) == 10 and c[-2:] == [-1.0, 1.0]            # 8 polynomial coefficients (highest first), then the (-1, 1) of 1 - 2^r
+    return np.array(c[:8], np.float32), np.float32(clamp)
 
 
 def gelu_model(x, c, clamp):
@@ -53,4 +53,4 @@ def test_gelu_polynomial_is_the_committed_fit():
     target = np.array([math.log2(math.erfc(v / math.sqrt(2.0))) / v for v in t])
     p = np.polyval(c.astype(np.float64), t)
     w = np.exp2(target * t) * math.log(2.0) * t                # d erf / d P
-    assert np.abs((p - target) * w).max() <= 2e-8
+    assert np.abs((p - target) * w).max() <= 4e-8

@@ -29,14 +29,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // erf(|x| / sqrt 2) on a pair, and |x| in `t`: ONE formula for the whole range,
-//     erf(T / sqrt 2) = 1 - 2^(T P(T)),   T = min(|x|, 5.9),   P = degree-8 minimax fit of log2(erfc(T / sqrt 2)) / T
-// (weighted for the error of erf, fitted in float64: 2e-9; tools/erf_fit.py).  It is the large-argument form of N. Juffa's erff with
+//     erf(T / sqrt 2) = 1 - 2^(T P(T)),   T = min(|x|, 5.9),   P = degree-7 minimax fit of log2(erfc(T / sqrt 2)) / T
+// (weighted for the error of erf, fitted in float64: 1.6e-8; tools/erf_fit.py - float32 Horner rounding dominates from degree 7 on).  It is the large-argument form of N. Juffa's erff with
 // the GELU's 1 / sqrt 2 and the exponential's log2(e) folded into the coefficients, extended down to T = 0: there 2^(.) -> 1 and
 // the subtraction loses RELATIVE accuracy of erf, which the GELU does not need - erf is added to 1.  Working on |x| keeps the sign
-// out of it: 0.5 x (1 + erf(x / sqrt 2)) = h + |h| erf(|x| / sqrt 2) with h = 0.5 x.  Nine packed FMAs / multiplies and one MUFU.EX2
+// out of it: 0.5 x (1 + erf(x / sqrt 2)) = h + |h| erf(|x| / sqrt 2) with h = 0.5 x.  Eight packed FMAs / multiplies and one MUFU.EX2
 // per element instead of the two-interval form's fifteen plus compare / select (kept below under WD_GELU_TWO_INTERVAL).
-// Against a float64 GELU over [-8, 8] (2 M points, fp32 Horner): max abs error 4.2e-7 (at |x| = 4.5, < 1 ulp of the result), rms
-// 7.8e-8 - torch's own fp32 GELU on the same points: 1.2e-6 / 1.4e-7.
+// Against a float64 GELU over [-8, 8] (2 M points, fp32 Horner): max abs error 3.4e-7 (at |x| = 4.5, < 1 ulp of the result), rms
+// 5.7e-8 - torch's own fp32 GELU on the same points: 1.2e-6 / 1.4e-7.
 #ifndef WD_GELU_TWO_INTERVAL
 __device__ __forceinline__ uint64_t erf_gelu_abs2(uint64_t x, uint64_t& t) {
     float x0, x1;
@@ -44,14 +44,13 @@ __device__ __forceinline__ uint64_t erf_gelu_abs2(uint64_t x, uint64_t& t) {
     const float a0 = fabsf(x0), a1 = fabsf(x1);
     const uint64_t ta = pk2(a0, a1);
     t = pk2(fminf(a0, 5.9f), fminf(a1, 5.9f));      // beyond 5.9 the result is 1 to fp32 precision (and P is only fitted up to there)
-    uint64_t p = fma2(splat2(5.128691213940328e-07f), t, splat2(-9.560329999658279e-06f));
-    p = fma2(p, t, splat2(7.497435581171885e-05f));
-    p = fma2(p, t, splat2(-0.0002843491092789918f));
-    p = fma2(p, t, splat2(1.499301924923202e-05f));
-    p = fma2(p, t, splat2(0.006931117735803127f));
-    p = fma2(p, t, splat2(-0.0524347648024559f));
-    p = fma2(p, t, splat2(-0.4592214524745941f));
-    p = fma2(p, t, splat2(-1.151104211807251f));
+    uint64_t p = fma2(splat2(-2.8348981686576735e-06f), t, splat2(3.937751898774877e-05f));
+    p = fma2(p, t, splat2(-0.00018617944442667067f));
+    p = fma2(p, t, splat2(-0.00013693823711946607f));
+    p = fma2(p, t, splat2(0.007063422352075577f));
+    p = fma2(p, t, splat2(-0.052496179938316345f));
+    p = fma2(p, t, splat2(-0.4592081904411316f));
+    p = fma2(p, t, splat2(-1.1511051654815674f));
     float r0, r1;
     upk2(mul2(p, t), r0, r1);
     t = ta;                                          // the caller's |x|
