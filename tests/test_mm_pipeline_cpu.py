@@ -182,3 +182,42 @@ def test_exif_orientation_parser():
         im.save(buf, "JPEG", exif=ex.tobytes())
         assert exif_orientation(buf.getvalue()) == val
     assert exif_orientation(b"\xff\xd8\xff\xd9") == 1 and exif_orientation(b"") == 1
+
+
+def test_read_encoded_routes_files_to_the_right_decoder(tmp_path):
+    """Which inputs stay compressed for the device decoder: 1- / 3-component JPEG bytes or files; PNGs, arrays, CMYK JPEGs and (on the
+    cv2-compatible path) EXIF-rotated JPEGs go to the host decoder.  The nvJPEG header parse is stubbed (no GPU here)."""
+    import io
+    from PIL import Image
+    from wedetect_b200.preprocess import EncodedImage, pack_mm_batch, read_encoded
+
+    class StubDecoder:
+        def info(self, blob):
+            im = Image.open(io.BytesIO(blob))
+            return im.size[0], im.size[1], len(im.getbands()), 0
+
+    def jpeg(mode="RGB", size=(40, 30), **kw):
+        b = io.BytesIO()
+        Image.new(mode, size).save(b, "JPEG", **kw)
+        return b.getvalue()
+
+    dec = StubDecoder()
+    e = read_encoded(jpeg(), dec)
+    assert isinstance(e, EncodedImage) and (e.h, e.w) == (30, 40) and e.shape == (30, 40, 3) and e.size == 3600
+    assert isinstance(read_encoded(jpeg("L"), dec), EncodedImage)
+    assert read_encoded(jpeg("CMYK"), dec) is None
+    png = io.BytesIO()
+    Image.new("RGB", (8, 8)).save(png, "PNG")
+    assert read_encoded(png.getvalue(), dec) is None and read_encoded(np.zeros((4, 4, 3), np.uint8), dec) is None
+    ex = Image.Exif()
+    ex[0x0112] = 6
+    rotated = jpeg(exif=ex.tobytes())
+    assert read_encoded(rotated, dec, honour_exif=True) is None and isinstance(read_encoded(rotated, dec), EncodedImage)
+    f = tmp_path / "a.jpg"
+    f.write_bytes(jpeg(size=(1280, 720)))
+    e = read_encoded(str(f), dec)
+    assert (e.h, e.w) == (720, 1280)
+    # a compressed image packs like a decoded one of the same shape: same descriptor, no host bytes to copy
+    pk_e = pack_mm_batch([e], 640, 640)
+    pk_d = pack_mm_batch([np.zeros((720, 1280, 3), np.uint8)], 640, 640)
+    assert np.array_equal(pk_e["desc"], pk_d["desc"]) and np.array_equal(pk_e["coef"], pk_d["coef"]) and pk_e["src_parts"][0][1] is e
